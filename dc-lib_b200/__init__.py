@@ -1,0 +1,347 @@
+"""dc-lib_b200 -- Python mirror of the DC-lib interface over libdc_b200.so.
+
+The product is the shared library (host C++ API of include/DC.h + the C ABI of
+include/dc_cuda.h + the sm_100a kernels).  This module only binds it with ctypes so
+that tests and bench.py can drive it the way a C/C++/Fortran caller would; function
+names follow the reference (include/DC.h:95-146).  Nothing here computes assembly
+values and there is no CPU fallback: if the library is missing or no CUDA device
+is present the device entry points raise.
+
+The directory name contains '-', so import it through the repo-root shim:
+    import dc_lib_b200 as dc
+"""
+import ctypes
+import os
+import subprocess
+from ctypes import POINTER, byref, c_double, c_int, c_int32, c_int64, c_uint16, c_uint32, c_void_p, c_char_p
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdc_b200.so")
+
+OP_LAPLACIAN, OP_ELASTICITY = 0, 1
+MODE_DETERMINISTIC, MODE_ATOMIC, MODE_LIST = 0, 1, 2
+OP_DIM = {OP_LAPLACIAN: 1, OP_ELASTICITY: 3}
+
+
+def build_library(force=False):
+    """Compile libdc_b200.so in-tree (nvcc cross-compiles sm_100a without a GPU)."""
+    if force:
+        subprocess.check_call(["make", "-C", _HERE, "clean"], stdout=subprocess.DEVNULL)
+    subprocess.check_call(["make", "-C", _HERE, "-j8"], stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(dc-lib_b200 has no CPU fallback)")
+        _lib = ctypes.CDLL(LIB_PATH, mode=os.RTLD_LOCAL)
+        _declare(_lib)
+    return _lib
+
+
+class Unit(ctypes.Structure):
+    _fields_ = [("edgeFirst", c_int64), ("itemFirst", c_int64), ("haloFirst", c_int64),
+                ("edgeCount", c_int32), ("nodeFirst", c_int32), ("nodeCount", c_int32),
+                ("ownElemFirst", c_int32), ("ownElemCount", c_int32), ("haloCount", c_int32),
+                ("taskFirst", c_int32), ("taskCount", c_int32), ("pad_", c_int32)]
+
+
+class Task(ctypes.Structure):
+    _fields_ = [("itemRel", c_uint32), ("iters", c_uint16), ("kind", c_uint16),
+                ("mask", c_uint32), ("first", c_uint32)]
+
+
+class ContribList(ctypes.Structure):
+    _fields_ = [("nbEdges", c_int64), ("nbItems", c_int64), ("edge", POINTER(c_int64)),
+                ("ptr", POINTER(c_int64)), ("item", POINTER(c_uint32))]
+
+
+class Plan(ctypes.Structure):
+    _fields_ = [("maxSlots", c_int32), ("nbUnits", c_int64), ("nbTasks", c_int64),
+                ("nbItems", c_int64), ("nbHalo", c_int64), ("units", POINTER(Unit)),
+                ("tasks", POINTER(Task)), ("items", POINTER(c_uint16)),
+                ("haloElems", POINTER(c_int32)), ("diagRel", POINTER(c_int32)),
+                ("big", ContribList), ("nbSlotsTotal", c_int64), ("nbItemsUseful", c_int64)]
+
+
+def _declare(L):
+    vp, ip = c_void_p, POINTER(c_int)
+    L.dc_cuda_last_error.restype = c_char_p
+    L.dc_cuda_create.argtypes = [POINTER(c_void_p), c_int]
+    L.dc_cuda_destroy.argtypes = [vp]
+    L.dc_cuda_destroy.restype = None
+    L.dc_cuda_set_mesh.argtypes = [vp, vp, vp, vp, vp, c_int, c_int, c_int]
+    L.dc_cuda_set_mesh_device.argtypes = [vp, vp, vp, vp, vp, c_int, c_int, c_int64, c_int]
+    L.dc_cuda_update_coords.argtypes = [vp, vp, vp]
+    L.dc_cuda_upload_plan.argtypes = [vp, POINTER(Plan)]
+    L.dc_cuda_upload_lists.argtypes = [vp, vp, vp, vp, c_int64, c_int64]
+    L.dc_cuda_assemble.argtypes = [vp, c_int, vp, c_int, c_int, vp, vp]
+    L.dc_cuda_values.argtypes = [vp, c_int, POINTER(c_void_p)]
+    L.dc_cuda_download_values.argtypes = [vp, c_int, vp, vp]
+    L.dc_cuda_permute_double_2d.argtypes = [vp, vp, vp, c_int64, c_int, vp]
+    L.dc_cuda_permute_int_2d.argtypes = [vp, vp, vp, c_int64, c_int, vp]
+    L.dc_cuda_renumber.argtypes = [vp, vp, c_int64, c_int, vp]
+    L.dc_cuda_reset_edges.argtypes = [vp, c_int64, c_int64, c_int, vp]
+    L.dc_cuda_launch_count.argtypes = [vp]
+    L.dc_cuda_launch_count.restype = c_int64
+    L.dc_cuda_sync.argtypes = [vp]
+    L.dc_plan_build.argtypes = [POINTER(Plan), vp, c_int, c_int, vp, vp, c_int, vp, c_int64, c_int, c_int]
+    L.dc_contrib_build.argtypes = [POINTER(ContribList), vp, c_int, c_int, vp, vp, c_int, vp, c_int64]
+    L.dc_plan_free.argtypes = [POINTER(Plan)]
+    L.dc_plan_free.restype = None
+    L.dc_contrib_free.argtypes = [POINTER(ContribList)]
+    L.dc_contrib_free.restype = None
+    L.dc_flatten_tree.argtypes = [vp, c_int64]
+    L.dc_flatten_tree.restype = c_int64
+    L.dc_get_time_.restype = c_double
+    L.dc_create_tree_.argtypes = [vp, ip, ip, ip]
+    L.dc_finalize_tree_.argtypes = [vp, vp, vp, vp, vp, vp, ip, ip, ip, ip, ip]
+    L.dc_store_tree_.argtypes = [c_char_p, ip, ip, ip, ip]
+    L.dc_read_tree_.argtypes = [c_char_p, ip, ip, ip, ip]
+    L.dc_permute_double_2d_array_.argtypes = [vp, ip, ip]
+    L.dc_permute_int_2d_array_.argtypes = [vp, ip, ip, ip]
+    L.dc_permute_int_1d_array_.argtypes = [vp, ip]
+    L.dc_renumber_int_array_.argtypes = [vp, ip]
+    L.dc_create_permutation_.argtypes = [vp, vp, ip, ip]
+    L.dc_tree_traversal_.argtypes = [vp, vp, vp, vp, vp]
+    L.dc_assembly_.argtypes = [vp, vp, vp, vp, ip]
+    L.dc_set_vec_size_.argtypes = [ip]
+    L.dc_set_max_elem_per_part_.argtypes = [ip]
+    L.dc_set_num_threads_.argtypes = [ip]
+
+
+def _p(a):
+    """Raw address of a numpy array / torch tensor / None."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return a.data_ptr()          # torch tensor
+
+
+def _i(v):
+    return byref(c_int(int(v)))
+
+
+def _i32(a):
+    a = np.ascontiguousarray(a, dtype=np.int32)
+    return a
+
+
+# --------------------------------------------------------------------------- host API
+# Same names and argument meaning as the reference (include/DC.h:95-146); arrays are
+# numpy arrays modified in place where the reference modifies them in place.
+
+def DC_set_vec_size(v):
+    lib().dc_set_vec_size_(_i(v))
+
+
+def DC_set_max_elem_per_part(v):
+    lib().dc_set_max_elem_per_part_(_i(v))
+
+
+def DC_set_num_threads(v):
+    lib().dc_set_num_threads_(_i(v))
+
+
+def DC_create_tree(elemToNode, nbElem, dimElem, nbNodes):
+    assert elemToNode.dtype == np.int32 and elemToNode.flags.c_contiguous
+    lib().dc_create_tree_(_p(elemToNode), _i(nbElem), _i(dimElem), _i(nbNodes))
+
+
+def DC_finalize_tree(nodeToNodeRow, elemToNode, nbElem, dimElem):
+    assert nodeToNodeRow.dtype == np.int32
+    dummy = c_int(0)
+    lib().dc_finalize_tree_(_p(nodeToNodeRow), _p(elemToNode), None, None, None,
+                            ctypes.cast(byref(dummy), c_void_p), _i(nbElem), _i(dimElem), _i(1), _i(0), _i(0))
+
+
+def DC_store_tree(path, nbElem, nbNodes):
+    lib().dc_store_tree_(str(path).encode(), _i(nbElem), _i(nbNodes), _i(0), _i(0))
+
+
+def DC_read_tree(path, nbElem, nbNodes):
+    comm = c_int(0)
+    lib().dc_read_tree_(str(path).encode(), _i(nbElem), _i(nbNodes), _i(0), byref(comm))
+    return comm.value
+
+
+def DC_permute_double_2d_array(tab, nbItem, dimItem):
+    assert tab.dtype == np.float64 and tab.flags.c_contiguous
+    lib().dc_permute_double_2d_array_(_p(tab), _i(nbItem), _i(dimItem))
+
+
+def DC_permute_int_2d_array(tab, nbItem, dimItem, offset=0):
+    assert tab.dtype == np.int32 and tab.flags.c_contiguous
+    lib().dc_permute_int_2d_array_(_p(tab), _i(nbItem), _i(dimItem), _i(offset))
+
+
+def DC_permute_int_1d_array(tab, size):
+    assert tab.dtype == np.int32 and tab.flags.c_contiguous
+    lib().dc_permute_int_1d_array_(_p(tab), _i(size))
+
+
+def DC_renumber_int_array(tab, size):
+    assert tab.dtype == np.int32 and tab.flags.c_contiguous
+    lib().dc_renumber_int_array_(_p(tab), _i(size))
+
+
+def DC_create_permutation(part, nbPart):
+    part = _i32(part)
+    perm = np.full(part.shape[0], -1, dtype=np.int32)
+    lib().dc_create_permutation_(_p(perm), _p(part), _i(part.shape[0]), _i(nbPart))
+    return perm
+
+
+def DC_free_tree():
+    lib().dc_free_tree_()
+
+
+def flatten_tree():
+    """Pre-order records of the current tree: [nbTreeNodes, 8] int32
+    {firstElem,lastElem,lastSep,firstNode,lastNode,isSep,isLeaf,hasSep}."""
+    n = lib().dc_flatten_tree(None, 0)
+    out = np.zeros((n, 8), dtype=np.int32)
+    lib().dc_flatten_tree(_p(out), n)
+    return out
+
+
+# --------------------------------------------------------------------------- schedule
+
+class HostPlan:
+    """Owns a dc_plan_t built by dc_plan_build()."""
+
+    def __init__(self, conn, nbNodes, row, col, colBase, treeRec, maxSlots=832, nbThreads=0):
+        self.c = Plan()
+        conn = np.ascontiguousarray(conn, dtype=np.int32)
+        nrec = 0 if treeRec is None else treeRec.shape[0]
+        rc = lib().dc_plan_build(byref(self.c), _p(conn), conn.shape[0], nbNodes, _p(row), _p(col), colBase,
+                                 _p(treeRec), nrec, maxSlots, nbThreads)
+        if rc:
+            raise RuntimeError(f"dc_plan_build failed with code {rc}")
+
+    def stats(self):
+        c = self.c
+        return dict(units=c.nbUnits, tasks=c.nbTasks, items=c.nbItems, items_useful=c.nbItemsUseful,
+                    halo=c.nbHalo, slots_total=c.nbSlotsTotal, max_slots=c.maxSlots, big_edges=c.big.nbEdges)
+
+    def __del__(self):
+        try:
+            lib().dc_plan_free(byref(self.c))
+        except Exception:
+            pass
+
+
+class Context:
+    """Thin wrapper of the C ABI (include/dc_cuda.h).  Array arguments are numpy arrays
+    (host entry points) or torch CUDA tensors (device entry points)."""
+
+    def __init__(self, device=0):
+        self.h = c_void_p()
+        self._keep = []
+        if lib().dc_cuda_create(byref(self.h), device):
+            raise RuntimeError("dc_cuda_create: " + lib().dc_cuda_last_error().decode())
+
+    def _ck(self, rc, what):
+        if rc:
+            raise RuntimeError(f"{what}: {lib().dc_cuda_last_error().decode()} (code {rc})")
+
+    def set_mesh(self, conn, coord, row, col, colBase=0):
+        conn = np.ascontiguousarray(conn, dtype=np.int32)
+        coord = np.ascontiguousarray(coord, dtype=np.float64)
+        row, col = _i32(row), _i32(col)
+        self.nbElem, self.nbNodes, self.nnz = conn.shape[0], coord.shape[0], int(row[-1])
+        self._ck(lib().dc_cuda_set_mesh(self.h, _p(conn), _p(coord), _p(row), _p(col), self.nbElem,
+                                        self.nbNodes, colBase), "dc_cuda_set_mesh")
+
+    def set_mesh_device(self, conn, coord, row, col, nnz, colBase=0):
+        self._keep = [conn, coord, row, col]
+        self.nbElem, self.nbNodes, self.nnz = conn.shape[0], coord.shape[0], int(nnz)
+        self._ck(lib().dc_cuda_set_mesh_device(self.h, _p(conn), _p(coord), _p(row), _p(col), self.nbElem,
+                                               self.nbNodes, self.nnz, colBase), "dc_cuda_set_mesh_device")
+
+    def update_coords(self, coord, stream=None):
+        self._ck(lib().dc_cuda_update_coords(self.h, _p(coord), stream), "dc_cuda_update_coords")
+
+    def upload_plan(self, plan):
+        self._ck(lib().dc_cuda_upload_plan(self.h, byref(plan.c)), "dc_cuda_upload_plan")
+
+    def upload_lists(self, conn, nbNodes, row, col, colBase=0):
+        cl = ContribList()
+        conn = np.ascontiguousarray(conn, dtype=np.int32)
+        rc = lib().dc_contrib_build(byref(cl), _p(conn), conn.shape[0], nbNodes, _p(row), _p(col), colBase, None, 0)
+        if rc:
+            raise RuntimeError(f"dc_contrib_build failed with code {rc}")
+        try:
+            self._ck(lib().dc_cuda_upload_lists(self.h, ctypes.cast(cl.edge, c_void_p), ctypes.cast(cl.ptr, c_void_p),
+                                                ctypes.cast(cl.item, c_void_p), cl.nbEdges, cl.nbItems),
+                     "dc_cuda_upload_lists")
+        finally:
+            lib().dc_contrib_free(byref(cl))
+
+    def assemble(self, op, params, mode, values, stream=None):
+        """values: torch CUDA float64 tensor with nnz*dim*dim entries."""
+        prm = np.ascontiguousarray(params if params is not None else [], dtype=np.float64)
+        self._ck(lib().dc_cuda_assemble(self.h, op, _p(prm) if prm.size else None, prm.size, mode, _p(values), stream),
+                 "dc_cuda_assemble")
+
+    def assemble_to_host(self, op, params, mode, out, stream=None):
+        """The call a reference user makes: values land in the HOST array `out`."""
+        dim = OP_DIM[op]
+        d = c_void_p()
+        self._ck(lib().dc_cuda_values(self.h, dim, byref(d)), "dc_cuda_values")
+        prm = np.ascontiguousarray(params if params is not None else [], dtype=np.float64)
+        self._ck(lib().dc_cuda_assemble(self.h, op, _p(prm) if prm.size else None, prm.size, mode, d, stream),
+                 "dc_cuda_assemble")
+        self._ck(lib().dc_cuda_download_values(self.h, dim, _p(out), stream), "dc_cuda_download_values")
+        self._ck(lib().dc_cuda_sync(stream), "dc_cuda_sync")
+
+    def launch_count(self):
+        return int(lib().dc_cuda_launch_count(self.h))
+
+    def close(self):
+        if self.h:
+            lib().dc_cuda_destroy(self.h)
+            self.h = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def permute_double_2d(d_in, d_out, d_perm, dimItem, stream=None):
+    rc = lib().dc_cuda_permute_double_2d(_p(d_in), _p(d_out), _p(d_perm), d_perm.shape[0], dimItem, stream)
+    if rc:
+        raise RuntimeError(lib().dc_cuda_last_error().decode())
+
+
+def permute_int_2d(d_in, d_out, d_perm, dimItem, stream=None):
+    rc = lib().dc_cuda_permute_int_2d(_p(d_in), _p(d_out), _p(d_perm), d_perm.shape[0], dimItem, stream)
+    if rc:
+        raise RuntimeError(lib().dc_cuda_last_error().decode())
+
+
+def renumber(d_tab, d_perm, isFortran=True, stream=None):
+    rc = lib().dc_cuda_renumber(_p(d_tab), _p(d_perm), d_tab.numel(), 1 if isFortran else 0, stream)
+    if rc:
+        raise RuntimeError(lib().dc_cuda_last_error().decode())
+
+
+def reset_edges(d_values, firstEdge, lastEdge, perEdge, stream=None):
+    rc = lib().dc_cuda_reset_edges(_p(d_values), firstEdge, lastEdge, perEdge, stream)
+    if rc:
+        raise RuntimeError(lib().dc_cuda_last_error().decode())
+
+
+from .meshgen import kuhn_cube, jitter_coords, build_csr, hub_collapse  # noqa: E402,F401

@@ -1,0 +1,360 @@
+/* dc_cuda_api.cu -- implementation of the C ABI in include/dc_cuda.h.
+ * There is no CPU fallback anywhere in this file: every entry point either runs
+ * on the selected CUDA device or returns an error. */
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include "dc_cuda.h"
+#include "dc_kernels.cuh"
+
+using namespace dcdev;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char *what, cudaError_t e = cudaSuccess)
+{
+    g_err = what;
+    if (e != cudaSuccess) {
+        g_err += ": ";
+        g_err += cudaGetErrorString(e);
+    }
+    return code;
+}
+#define CK(call)                                                   \
+    do {                                                           \
+        cudaError_t e_ = (call);                                   \
+        if (e_ != cudaSuccess) return fail(-10, #call, e_);        \
+    } while (0)
+
+struct dc_cuda_ctx {
+    int device = 0;
+    int smCount = 148;
+    int nbElem = 0, nbNodes = 0, colBase = 0;
+    int64_t nnz = 0;
+    bool ownsMesh = false;
+    int *d_conn = nullptr, *d_row = nullptr, *d_col = nullptr;
+    double *d_coord = nullptr;
+    /* plan */
+    int maxSlots = 0;
+    int64_t nbUnits = 0, nbBigEdges = 0;
+    dc_unit_t *d_units = nullptr;
+    dc_task_t *d_tasks = nullptr;
+    uint16_t *d_items = nullptr;
+    int *d_halo = nullptr, *d_diagRel = nullptr;
+    int64_t *d_bigEdge = nullptr, *d_bigPtr = nullptr;
+    uint32_t *d_bigItem = nullptr;
+    /* full lists (DC_MODE_LIST) */
+    int64_t nbListEdges = 0;
+    int64_t *d_listEdge = nullptr, *d_listPtr = nullptr;
+    uint32_t *d_listItem = nullptr;
+    /* context-owned values */
+    double *d_values = nullptr;
+    int64_t valuesLen = 0;
+    int64_t launches = 0;
+};
+
+extern "C" const char *dc_cuda_last_error(void) { return g_err.c_str(); }
+
+extern "C" int dc_cuda_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" int dc_cuda_create(dc_cuda_ctx **out, int device)
+{
+    if (!out) return fail(-1, "dc_cuda_create: null output");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(-2, "dc_cuda_create: no CUDA device (this library has no CPU fallback)", e);
+    if (device < 0 || device >= n) return fail(-3, "dc_cuda_create: bad device index");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(-4, "dc_cuda_create: kernels are built for sm_100a only");
+    dc_cuda_ctx *c = new dc_cuda_ctx;
+    c->device = device;
+    c->smCount = prop.multiProcessorCount;
+    *out = c;
+    return 0;
+}
+
+static void free_mesh(dc_cuda_ctx *c)
+{
+    if (c->ownsMesh) {
+        cudaFree(c->d_conn); cudaFree(c->d_coord); cudaFree(c->d_row); cudaFree(c->d_col);
+    }
+    c->d_conn = c->d_row = c->d_col = nullptr;
+    c->d_coord = nullptr;
+    c->ownsMesh = false;
+}
+static void free_plan(dc_cuda_ctx *c)
+{
+    cudaFree(c->d_units); cudaFree(c->d_tasks); cudaFree(c->d_items); cudaFree(c->d_halo);
+    cudaFree(c->d_diagRel); cudaFree(c->d_bigEdge); cudaFree(c->d_bigPtr); cudaFree(c->d_bigItem);
+    c->d_units = nullptr; c->d_tasks = nullptr; c->d_items = nullptr; c->d_halo = c->d_diagRel = nullptr;
+    c->d_bigEdge = c->d_bigPtr = nullptr; c->d_bigItem = nullptr;
+    c->nbUnits = c->nbBigEdges = 0;
+}
+static void free_lists(dc_cuda_ctx *c)
+{
+    cudaFree(c->d_listEdge); cudaFree(c->d_listPtr); cudaFree(c->d_listItem);
+    c->d_listEdge = c->d_listPtr = nullptr; c->d_listItem = nullptr;
+    c->nbListEdges = 0;
+}
+
+extern "C" void dc_cuda_destroy(dc_cuda_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    free_mesh(c); free_plan(c); free_lists(c);
+    cudaFree(c->d_values);
+    delete c;
+}
+
+template <typename T>
+static int upload(T **dst, const T *src, int64_t count)
+{
+    *dst = nullptr;
+    CK(cudaMalloc((void **)dst, sizeof(T) * (size_t)(count > 0 ? count : 1)));
+    if (count > 0) CK(cudaMemcpy(*dst, src, sizeof(T) * (size_t)count, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+extern "C" int dc_cuda_set_mesh(dc_cuda_ctx *c, const int *h_conn, const double *h_coord, const int *h_row,
+                                const int *h_col, int nbElem, int nbNodes, int colBase)
+{
+    if (!c) return fail(-1, "dc_cuda_set_mesh: null context");
+    CK(cudaSetDevice(c->device));
+    free_mesh(c);
+    c->ownsMesh = true;
+    c->nbElem = nbElem; c->nbNodes = nbNodes; c->colBase = colBase;
+    c->nnz = h_row[nbNodes];
+    int rc;
+    if ((rc = upload(&c->d_conn, h_conn, (int64_t)nbElem * 4))) return rc;
+    if ((rc = upload(&c->d_coord, h_coord, (int64_t)nbNodes * 3))) return rc;
+    if ((rc = upload(&c->d_row, h_row, (int64_t)nbNodes + 1))) return rc;
+    if ((rc = upload(&c->d_col, h_col, c->nnz))) return rc;
+    return 0;
+}
+
+extern "C" int dc_cuda_set_mesh_device(dc_cuda_ctx *c, const int *d_conn, const double *d_coord,
+                                       const int *d_row, const int *d_col, int nbElem, int nbNodes,
+                                       int64_t nnz, int colBase)
+{
+    if (!c) return fail(-1, "dc_cuda_set_mesh_device: null context");
+    if ((reinterpret_cast<uintptr_t>(d_conn) & 15) != 0)
+        return fail(-5, "dc_cuda_set_mesh_device: connectivity must be 16-byte aligned");
+    CK(cudaSetDevice(c->device));
+    free_mesh(c);
+    c->ownsMesh = false;
+    c->d_conn = const_cast<int *>(d_conn);
+    c->d_coord = const_cast<double *>(d_coord);
+    c->d_row = const_cast<int *>(d_row);
+    c->d_col = const_cast<int *>(d_col);
+    c->nbElem = nbElem; c->nbNodes = nbNodes; c->nnz = nnz; c->colBase = colBase;
+    return 0;
+}
+
+extern "C" int dc_cuda_update_coords(dc_cuda_ctx *c, const double *h_coord, void *stream)
+{
+    if (!c || !c->d_coord) return fail(-1, "dc_cuda_update_coords: no mesh");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(c->d_coord, h_coord, sizeof(double) * 3 * (size_t)c->nbNodes, cudaMemcpyHostToDevice,
+                       (cudaStream_t)stream));
+    return 0;
+}
+
+extern "C" int dc_cuda_upload_plan(dc_cuda_ctx *c, const struct dc_plan_s *p)
+{
+    if (!c || !p) return fail(-1, "dc_cuda_upload_plan: null argument");
+    CK(cudaSetDevice(c->device));
+    free_plan(c);
+    int rc;
+    if ((rc = upload(&c->d_units, p->units, p->nbUnits))) return rc;
+    if ((rc = upload(&c->d_tasks, p->tasks, p->nbTasks))) return rc;
+    if ((rc = upload(&c->d_items, p->items, p->nbItems))) return rc;
+    if ((rc = upload(&c->d_halo, p->haloElems, p->nbHalo))) return rc;
+    if ((rc = upload(&c->d_diagRel, p->diagRel, (int64_t)c->nbNodes))) return rc;
+    if (p->big.nbEdges > 0) {
+        if ((rc = upload(&c->d_bigEdge, p->big.edge, p->big.nbEdges))) return rc;
+        if ((rc = upload(&c->d_bigPtr, p->big.ptr, p->big.nbEdges + 1))) return rc;
+        if ((rc = upload(&c->d_bigItem, p->big.item, p->big.nbItems))) return rc;
+    }
+    c->nbUnits = p->nbUnits;
+    c->nbBigEdges = p->big.nbEdges;
+    c->maxSlots = p->maxSlots;
+    return 0;
+}
+
+extern "C" int dc_cuda_upload_lists(dc_cuda_ctx *c, const int64_t *h_edge, const int64_t *h_ptr,
+                                    const uint32_t *h_item, int64_t nbEdges, int64_t nbItems)
+{
+    if (!c) return fail(-1, "dc_cuda_upload_lists: null context");
+    CK(cudaSetDevice(c->device));
+    free_lists(c);
+    int rc;
+    if ((rc = upload(&c->d_listEdge, h_edge, nbEdges))) return rc;
+    if ((rc = upload(&c->d_listPtr, h_ptr, nbEdges + 1))) return rc;
+    if ((rc = upload(&c->d_listItem, h_item, nbItems))) return rc;
+    c->nbListEdges = nbEdges;
+    return 0;
+}
+
+template <class Op>
+static size_t unit_smem_bytes(int maxSlots, int threads)
+{
+    constexpr int DD = UnitSmem<Op>::DD;
+    constexpr int RS = UnitSmem<Op>::RS;
+    size_t a = (size_t)maxSlots * 16, b = (size_t)(threads / 32) * 32 * DD * 8;
+    return 16 + (a > b ? a : b) + (size_t)maxSlots * RS * 8;
+}
+
+template <class Op>
+static int assemble_t(dc_cuda_ctx *c, int mode, double *d_values, cudaStream_t s)
+{
+    constexpr int DD = Op::D * Op::D;
+    constexpr int THREADS = 256;
+    if (mode == DC_MODE_DETERMINISTIC) {
+        if (!c->d_units && c->nbBigEdges == 0) return fail(-6, "dc_cuda_assemble: no plan uploaded");
+        if (c->nbUnits > 0) {
+            size_t smem = unit_smem_bytes<Op>(c->maxSlots, THREADS);
+            auto kern = gather_units<Op, THREADS>;
+            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<(unsigned)c->nbUnits, THREADS, smem, s>>>(c->d_units, c->d_tasks, c->d_items, c->d_halo,
+                                                               c->d_diagRel, c->d_conn, c->d_coord, d_values,
+                                                               c->maxSlots);
+            c->launches++;
+        }
+        if (c->nbBigEdges > 0) {
+            gather_lists<Op><<<(unsigned)((c->nbBigEdges + 127) / 128), 128, 0, s>>>(
+                c->d_bigEdge, c->d_bigPtr, c->d_bigItem, c->nbBigEdges, c->d_conn, c->d_coord, d_values);
+            c->launches++;
+        }
+    } else if (mode == DC_MODE_ATOMIC) {
+        const int64_t n = c->nnz * DD;
+        reset_values<<<c->smCount * 8, 256, 0, s>>>(d_values, n);
+        scatter_atomic<Op><<<(unsigned)((c->nbElem + 127) / 128), 128, 0, s>>>(
+            c->d_conn, c->d_coord, c->d_row, c->d_col, c->colBase, c->nbElem, d_values);
+        c->launches += 2;
+    } else if (mode == DC_MODE_LIST) {
+        if (!c->d_listPtr) return fail(-6, "dc_cuda_assemble: no contribution lists uploaded");
+        gather_lists<Op><<<(unsigned)((c->nbListEdges + 127) / 128), 128, 0, s>>>(
+            c->d_listEdge, c->d_listPtr, c->d_listItem, c->nbListEdges, c->d_conn, c->d_coord, d_values);
+        c->launches++;
+    } else {
+        return fail(-7, "dc_cuda_assemble: unknown mode");
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int dc_cuda_assemble(dc_cuda_ctx *c, int op, const double *h_params, int nbParams, int mode,
+                                double *d_values, void *stream)
+{
+    if (!c || !c->d_conn) return fail(-1, "dc_cuda_assemble: no mesh");
+    if (!d_values) return fail(-1, "dc_cuda_assemble: null values");
+    if (nbParams > DC_MAX_PARAMS) return fail(-8, "dc_cuda_assemble: too many operator parameters");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (nbParams > 0)
+        CK(cudaMemcpyToSymbolAsync(c_params, h_params, sizeof(double) * (size_t)nbParams, 0,
+                                   cudaMemcpyHostToDevice, s));
+    switch (op) {
+        case DC_OP_P1_TET_LAPLACIAN:
+            return assemble_t<OpLaplacian>(c, mode, d_values, s);
+        case DC_OP_P1_TET_ELASTICITY:
+            if (nbParams < 2) return fail(-8, "dc_cuda_assemble: elasticity needs {lambda, mu}");
+            return assemble_t<OpElasticity>(c, mode, d_values, s);
+        default:
+            return fail(-9, "dc_cuda_assemble: unknown operator");
+    }
+}
+
+extern "C" int dc_cuda_values(dc_cuda_ctx *c, int dim, double **d_values)
+{
+    if (!c || !d_values) return fail(-1, "dc_cuda_values: null argument");
+    CK(cudaSetDevice(c->device));
+    const int64_t need = c->nnz * dim * dim;
+    if (need > c->valuesLen) {
+        cudaFree(c->d_values);
+        c->d_values = nullptr;
+        CK(cudaMalloc((void **)&c->d_values, sizeof(double) * (size_t)(need > 0 ? need : 1)));
+        c->valuesLen = need;
+    }
+    *d_values = c->d_values;
+    return 0;
+}
+
+extern "C" int dc_cuda_download_values(dc_cuda_ctx *c, int dim, double *h_values, void *stream)
+{
+    if (!c || !c->d_values) return fail(-1, "dc_cuda_download_values: no values");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(h_values, c->d_values, sizeof(double) * (size_t)(c->nnz * dim * dim),
+                       cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return 0;
+}
+
+static unsigned grid_for(int64_t work, int perBlock)
+{
+    int64_t b = (work + perBlock - 1) / perBlock;
+    const int64_t cap = 148 * 16;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (unsigned)b;
+}
+
+extern "C" int dc_cuda_permute_double_2d(const double *d_in, double *d_out, const int *d_perm,
+                                         int64_t nbItem, int dimItem, void *stream)
+{
+    if (nbItem <= 0) return 0;
+    permute_rows<double><<<grid_for(nbItem * dimItem, 256), 256, 0, (cudaStream_t)stream>>>(d_in, d_out, d_perm,
+                                                                                           nbItem, dimItem);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int dc_cuda_permute_int_2d(const int *d_in, int *d_out, const int *d_perm, int64_t nbItem,
+                                      int dimItem, void *stream)
+{
+    if (nbItem <= 0) return 0;
+    const bool vec = dimItem == 4 && ((reinterpret_cast<uintptr_t>(d_in) | reinterpret_cast<uintptr_t>(d_out)) & 15) == 0;
+    if (vec)
+        permute_rows_int4<<<grid_for(nbItem, 256), 256, 0, (cudaStream_t)stream>>>(
+            reinterpret_cast<const int4 *>(d_in), reinterpret_cast<int4 *>(d_out), d_perm, nbItem);
+    else
+        permute_rows<int><<<grid_for(nbItem * dimItem, 256), 256, 0, (cudaStream_t)stream>>>(d_in, d_out, d_perm,
+                                                                                            nbItem, dimItem);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int dc_cuda_renumber(int *d_tab, const int *d_perm, int64_t size, int isFortran, void *stream)
+{
+    if (size <= 0) return 0;
+    renumber<<<grid_for(size, 256), 256, 0, (cudaStream_t)stream>>>(d_tab, d_perm, size, isFortran ? 1 : 0);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int dc_cuda_reset_edges(double *d_values, int64_t firstEdge, int64_t lastEdge, int perEdge,
+                                   void *stream)
+{
+    if (lastEdge < firstEdge) return 0;
+    const int64_t n = (lastEdge - firstEdge + 1) * perEdge;
+    reset_values<<<grid_for(n / 2 + 1, 256), 256, 0, (cudaStream_t)stream>>>(d_values + firstEdge * perEdge, n);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int64_t dc_cuda_launch_count(const dc_cuda_ctx *c) { return c ? c->launches : 0; }
+
+extern "C" int dc_cuda_sync(void *stream)
+{
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
+}

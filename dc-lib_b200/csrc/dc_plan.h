@@ -1,0 +1,92 @@
+/* dc_plan.h -- device schedule ("plan") of one assembly, shared by the host-side
+ * plan builder (host/dc_plan.cc) and the CUDA side (csrc/dc_cuda_api.cu).
+ *
+ * The reference schedules the assembly by walking tree_t at run time and calling
+ * a host callback per leaf (src/tree_traversal.cc:27-103).  On the GPU the same
+ * tree is flattened once into WORK UNITS: a unit is a non-separator subtree of
+ * the D&C tree (or a row sub-range of one leaf) small enough for one CTA.  It
+ * owns the subtree's node interval, hence the CSR edge interval
+ * [row[firstNode], row[lastNode+1]) that DC_finalize_tree computes for the reset
+ * (src/tree_creation.cc:185-186), and writes every value of that interval
+ * exactly once -- the reset is fused into that single write.  The elements a unit
+ * needs are its own contiguous range [firstElem, lastSep] plus the "halo":
+ * elements of ancestor separators that touch one of its nodes.
+ *
+ * Inside a unit every CSR edge is summed in ascending element index, which is the
+ * order the reference's traversal produces (left < right < separator in element
+ * index, executed (left || right) -> separator), so values are bit-identical.
+ */
+#ifndef DC_PLAN_H
+#define DC_PLAN_H
+#include <stdint.h>
+
+#define DC_ITEM_NULL   0xFFFFu      /* padding entry of an item row              */
+#define DC_SLOT_LIMIT  4095         /* slots are 12-bit: item = slot<<4 | a<<2 | b */
+#define DC_TASK_EDGES  0            /* 32 consecutive edges of the unit            */
+#define DC_TASK_DIAG   1            /* the diagonal edges of 32 consecutive nodes  */
+
+typedef struct {
+    int64_t edgeFirst;      /* first CSR edge of the unit                          */
+    int64_t itemFirst;      /* first uint16 item of the unit                       */
+    int64_t haloFirst;      /* first entry of haloElems                            */
+    int32_t edgeCount;
+    int32_t nodeFirst, nodeCount;
+    int32_t ownElemFirst, ownElemCount;   /* slots [0, ownElemCount)                */
+    int32_t haloCount;                    /* slots [ownElemCount, +haloCount)       */
+    int32_t taskFirst, taskCount;
+    int32_t pad_;
+} dc_unit_t;                /* 64 bytes */
+
+typedef struct {
+    uint32_t itemRel;       /* items of this task start at unit.itemFirst+itemRel  */
+    uint16_t iters;         /* item rows ([iter][lane], 32 lanes each)             */
+    uint16_t kind;          /* DC_TASK_EDGES / DC_TASK_DIAG                        */
+    uint32_t mask;          /* EDGES: lanes that are diagonal edges (skipped);     */
+                            /* DIAG : lanes that hold a node                       */
+    uint32_t first;         /* EDGES: edge offset in unit; DIAG: node offset       */
+} dc_task_t;                /* 16 bytes */
+
+/* Fallback list for rows too large for a unit (and for generic operators):
+ * explicit per-edge contribution lists, item = elem<<4 | a<<2 | b. */
+typedef struct {
+    int64_t  nbEdges;
+    int64_t  nbItems;
+    int64_t *edge;          /* [nbEdges]   CSR edge index                          */
+    int64_t *ptr;           /* [nbEdges+1] offsets into item                       */
+    uint32_t *item;         /* [nbItems]                                           */
+} dc_contrib_list_t;
+
+typedef struct dc_plan_s {
+    int32_t  maxSlots;      /* largest slot count of any unit                      */
+    int64_t  nbUnits, nbTasks, nbItems, nbHalo;
+    dc_unit_t *units;
+    dc_task_t *tasks;
+    uint16_t  *items;
+    int32_t   *haloElems;
+    int32_t   *diagRel;     /* [nbNodes] edge offset (in its unit) of node's diagonal, -1 if none */
+    dc_contrib_list_t big;  /* rows that did not fit a unit                        */
+    /* statistics */
+    int64_t  nbSlotsTotal;  /* sum of slots over units (element setups performed)  */
+    int64_t  nbItemsUseful; /* items that are not padding                          */
+} dc_plan_t;
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+/* Build the plan on the host.  conn: [nbElem][4] 1-based renumbered tree-order
+ * connectivity; row/col: CSR pattern (col numbering base colBase, any order
+ * within a row); leaves: nbLeaves x 8 ints {firstElem,lastElem,lastSep,firstNode,
+ * lastNode,isSep,isLeaf,parent-free flag} in PRE-ORDER of the tree -- see
+ * dc_plan_build_from_tree for the pointer-tree front end.  Returns 0 on success. */
+int  dc_plan_build(dc_plan_t *plan, const int *conn, int nbElem, int nbNodes, const int *row,
+                   const int *col, int colBase, const int *treeRec, int64_t nbTreeRec,
+                   int maxSlots, int nbThreads);
+int  dc_contrib_build(dc_contrib_list_t *out, const int *conn, int nbElem, int nbNodes,
+                      const int *row, const int *col, int colBase, const int *rows,
+                      int64_t nbRows);
+void dc_plan_free(dc_plan_t *plan);
+void dc_contrib_free(dc_contrib_list_t *c);
+#ifdef __cplusplus
+}
+#endif
+#endif

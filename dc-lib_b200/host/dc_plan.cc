@@ -1,0 +1,413 @@
+/* dc_plan.cc -- host-side builder of the device schedule (see csrc/dc_plan.h).
+ *
+ * Input is what the reference's user holds after DC_create_tree /
+ * DC_renumber_int_array / DC_finalize_tree: tree-ordered, renumbered connectivity,
+ * the CSR pattern, and the tree (flattened in the pre-order of src/IO.cc:102-140).
+ * Everything here is O(nbElem) integer work, parallel over units.
+ */
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include <algorithm>
+#include <omp.h>
+#include "../csrc/dc_plan.h"
+
+namespace {
+
+struct Mesh {
+    const int *conn;     /* 1-based */
+    int nbElem, nbNodes;
+    const int *row, *col;
+    int colBase;
+    std::vector<int64_t> n2ePtr;
+    std::vector<int> n2eVal;   /* incident elements of each node, ascending */
+};
+
+void build_node_to_elem(Mesh &m)
+{
+    const int64_t nc = (int64_t)m.nbElem * 4;
+    m.n2ePtr.assign((size_t)m.nbNodes + 1, 0);
+    for (int64_t k = 0; k < nc; k++) m.n2ePtr[(size_t)m.conn[k]]++;   /* node n (1-based) -> slot n */
+    for (int n = 0; n < m.nbNodes; n++) m.n2ePtr[(size_t)n + 1] += m.n2ePtr[n];
+    m.n2eVal.resize((size_t)nc);
+    std::vector<int64_t> fill(m.n2ePtr.begin(), m.n2ePtr.end() - 1);
+    for (int e = 0; e < m.nbElem; e++)
+        for (int j = 0; j < 4; j++) m.n2eVal[(size_t)fill[m.conn[(int64_t)e * 4 + j] - 1]++] = e;
+}
+
+struct UnitSeed {
+    int nodeFirst, nodeCount, ownFirst, ownCount;
+    std::vector<int> halo;     /* sorted */
+};
+
+/* halo = incident elements of the node range that are not in [ownFirst, ownFirst+ownCount) */
+void collect_halo(const Mesh &m, int nodeFirst, int nodeCount, int ownFirst, int ownCount,
+                  std::vector<int> &halo)
+{
+    halo.clear();
+    for (int64_t k = m.n2ePtr[nodeFirst]; k < m.n2ePtr[(size_t)nodeFirst + nodeCount]; k++) {
+        int e = m.n2eVal[(size_t)k];
+        if (e < ownFirst || e >= ownFirst + ownCount) halo.push_back(e);
+    }
+    std::sort(halo.begin(), halo.end());
+    halo.erase(std::unique(halo.begin(), halo.end()), halo.end());
+}
+
+struct Selector {
+    const Mesh &m;
+    const int *rec;
+    int64_t nbRec, cursor = 0;
+    int maxSlots;
+    std::vector<UnitSeed> seeds;
+    std::vector<int> bigRows;
+    std::vector<int> scratch;
+
+    /* rows [nodeFirst, nodeFirst+nodeCount) without a usable subtree: cut greedily */
+    void split_rows(int nodeFirst, int nodeCount)
+    {
+        int start = nodeFirst, end = nodeFirst + nodeCount;
+        while (start < end) {
+            int stop = start;
+            std::vector<int> acc;
+            while (stop < end) {
+                std::vector<int> trial(acc);
+                for (int64_t k = m.n2ePtr[stop]; k < m.n2ePtr[(size_t)stop + 1]; k++)
+                    trial.push_back(m.n2eVal[(size_t)k]);
+                std::sort(trial.begin(), trial.end());
+                trial.erase(std::unique(trial.begin(), trial.end()), trial.end());
+                if ((int)trial.size() > maxSlots) break;
+                acc.swap(trial);
+                stop++;
+            }
+            if (stop == start) {           /* a single row exceeds the slot budget */
+                bigRows.push_back(start);
+                start++;
+                continue;
+            }
+            UnitSeed s{start, stop - start, 0, 0, {}};
+            s.halo.swap(acc);
+            seeds.push_back(std::move(s));
+            start = stop;
+        }
+    }
+
+    /* consume one subtree from the pre-order record stream without emitting */
+    void skip()
+    {
+        const int *r = rec + 8 * cursor++;
+        if (r[6]) return;
+        skip();
+        skip();
+        if (r[7]) skip();
+    }
+
+    void select()
+    {
+        const int *r = rec + 8 * cursor++;
+        const int firstElem = r[0], lastSep = r[2], firstNode = r[3], lastNode = r[4];
+        const bool isSep = r[5], isLeaf = r[6], hasSep = r[7];
+        const int own = lastSep - firstElem + 1, nodes = lastNode - firstNode + 1;
+        if (isSep) {            /* separator subtrees own no rows: they appear as halo */
+            --cursor;
+            skip();
+            return;
+        }
+        bool taken = false;
+        if (own <= maxSlots && nodes > 0) {
+            collect_halo(m, firstNode, nodes, firstElem, own, scratch);
+            if (own + (int)scratch.size() <= maxSlots) {
+                UnitSeed s{firstNode, nodes, firstElem, own, {}};
+                s.halo = scratch;
+                seeds.push_back(std::move(s));
+                taken = true;
+            }
+        }
+        if (taken) {
+            --cursor;
+            skip();
+            return;
+        }
+        if (isLeaf) {
+            if (nodes > 0) split_rows(firstNode, nodes);
+            return;
+        }
+        select();               /* left  */
+        select();               /* right */
+        if (hasSep) skip();
+    }
+};
+
+struct UnitOut {
+    std::vector<dc_task_t> tasks;
+    std::vector<uint16_t> items;
+    int64_t useful = 0;
+};
+
+inline int slot_of(const UnitSeed &s, int e)
+{
+    if (e >= s.ownFirst && e < s.ownFirst + s.ownCount) return e - s.ownFirst;
+    return s.ownCount + (int)(std::lower_bound(s.halo.begin(), s.halo.end(), e) - s.halo.begin());
+}
+
+/* items of every edge of the unit, grouped per edge in ascending element order */
+void build_unit(const Mesh &m, const UnitSeed &s, int32_t *diagRel, UnitOut &out,
+                std::vector<std::vector<uint16_t>> &perEdge, int &error)
+{
+    const int64_t edgeFirst = m.row[s.nodeFirst];
+    const int edgeCount = m.row[s.nodeFirst + s.nodeCount] - (int)edgeFirst;
+    if ((int)perEdge.size() < edgeCount) perEdge.resize((size_t)edgeCount);
+    for (int k = 0; k < edgeCount; k++) perEdge[k].clear();
+
+    for (int n = s.nodeFirst; n < s.nodeFirst + s.nodeCount; n++) {
+        const int r0 = m.row[n], r1 = m.row[n + 1];
+        diagRel[n] = -1;
+        for (int k = r0; k < r1; k++)
+            if (m.col[k] - m.colBase == n) diagRel[n] = (int)(k - edgeFirst);
+        for (int64_t q = m.n2ePtr[n]; q < m.n2ePtr[(size_t)n + 1]; q++) {
+            const int e = m.n2eVal[(size_t)q];
+            const int *c = m.conn + (int64_t)e * 4;
+            int a = 0;
+            while (a < 4 && c[a] - 1 != n) a++;
+            const int slot = slot_of(s, e);
+            for (int b = 0; b < 4; b++) {
+                const int target = c[b] - 1 + m.colBase;
+                int k = r0;
+                while (k < r1 && m.col[k] != target) k++;
+                if (k == r1) { error = 1; continue; }    /* pattern lacks an element edge */
+                perEdge[(size_t)(k - edgeFirst)].push_back((uint16_t)((slot << 4) | (a << 2) | b));
+            }
+        }
+    }
+    /* edge tasks: 32 consecutive edges, item rows [iter][lane]; diagonal lanes are
+     * left to the diagonal tasks */
+    for (int base = 0; base < edgeCount; base += 32) {
+        dc_task_t t;
+        t.kind = DC_TASK_EDGES;
+        t.first = (uint32_t)base;
+        t.mask = 0;
+        t.itemRel = (uint32_t)out.items.size();
+        size_t iters = 0;
+        for (int l = 0; l < 32 && base + l < edgeCount; l++) iters = std::max(iters, perEdge[(size_t)(base + l)].size());
+        /* which lanes are diagonals? */
+        for (int n = s.nodeFirst; n < s.nodeFirst + s.nodeCount; n++) {
+            int d = diagRel[n];
+            if (d >= base && d < base + 32) t.mask |= 1u << (d - base);
+        }
+        iters = 0;
+        for (int l = 0; l < 32 && base + l < edgeCount; l++)
+            if (!((t.mask >> l) & 1u)) iters = std::max(iters, perEdge[(size_t)(base + l)].size());
+        t.iters = (uint16_t)iters;
+        out.items.resize(out.items.size() + iters * 32, (uint16_t)DC_ITEM_NULL);
+        uint16_t *dst = out.items.data() + t.itemRel;
+        for (int l = 0; l < 32 && base + l < edgeCount; l++) {
+            if ((t.mask >> l) & 1u) continue;
+            const std::vector<uint16_t> &v = perEdge[(size_t)(base + l)];
+            for (size_t i = 0; i < v.size(); i++) dst[i * 32 + l] = v[i];
+            out.useful += (int64_t)v.size();
+        }
+        out.tasks.push_back(t);
+    }
+    /* diagonal tasks: 32 consecutive nodes */
+    for (int base = 0; base < s.nodeCount; base += 32) {
+        dc_task_t t;
+        t.kind = DC_TASK_DIAG;
+        t.first = (uint32_t)base;
+        t.mask = 0;
+        t.itemRel = (uint32_t)out.items.size();
+        size_t iters = 0;
+        for (int l = 0; l < 32 && base + l < s.nodeCount; l++) {
+            int d = diagRel[s.nodeFirst + base + l];
+            if (d < 0) continue;
+            t.mask |= 1u << l;
+            iters = std::max(iters, perEdge[(size_t)d].size());
+        }
+        t.iters = (uint16_t)iters;
+        out.items.resize(out.items.size() + iters * 32, (uint16_t)DC_ITEM_NULL);
+        uint16_t *dst = out.items.data() + t.itemRel;
+        for (int l = 0; l < 32 && base + l < s.nodeCount; l++) {
+            if (!((t.mask >> l) & 1u)) continue;
+            const std::vector<uint16_t> &v = perEdge[(size_t)diagRel[s.nodeFirst + base + l]];
+            for (size_t i = 0; i < v.size(); i++) dst[i * 32 + l] = v[i];
+            out.useful += (int64_t)v.size();
+        }
+        if (t.mask) out.tasks.push_back(t); else out.items.resize(t.itemRel);
+    }
+}
+
+template <typename T>
+T *dup(const std::vector<T> &v)
+{
+    T *p = (T *)malloc(sizeof(T) * (v.size() ? v.size() : 1));
+    if (v.size()) memcpy(p, v.data(), sizeof(T) * v.size());
+    return p;
+}
+
+}  // namespace
+
+extern "C" int dc_contrib_build(dc_contrib_list_t *out, const int *conn, int nbElem, int nbNodes,
+                                const int *row, const int *col, int colBase, const int *rows,
+                                int64_t nbRows)
+{
+    Mesh m{conn, nbElem, nbNodes, row, col, colBase, {}, {}};
+    build_node_to_elem(m);
+    std::vector<int64_t> edge, ptr;
+    std::vector<uint32_t> item;
+    ptr.push_back(0);
+    int error = 0;
+    std::vector<std::vector<uint32_t>> perEdge;
+    for (int64_t r = 0; r < (rows ? nbRows : (int64_t)nbNodes); r++) {
+        const int n = rows ? rows[r] : (int)r;
+        const int r0 = row[n], r1 = row[n + 1];
+        perEdge.assign((size_t)(r1 - r0), {});
+        for (int64_t q = m.n2ePtr[n]; q < m.n2ePtr[(size_t)n + 1]; q++) {
+            const int e = m.n2eVal[(size_t)q];
+            const int *c = conn + (int64_t)e * 4;
+            int a = 0;
+            while (a < 4 && c[a] - 1 != n) a++;
+            for (int b = 0; b < 4; b++) {
+                int k = r0;
+                while (k < r1 && col[k] != c[b] - 1 + colBase) k++;
+                if (k == r1) { error = 1; continue; }
+                perEdge[(size_t)(k - r0)].push_back(((uint32_t)e << 4) | (uint32_t)(a << 2) | (uint32_t)b);
+            }
+        }
+        for (int k = r0; k < r1; k++) {
+            edge.push_back(k);
+            item.insert(item.end(), perEdge[(size_t)(k - r0)].begin(), perEdge[(size_t)(k - r0)].end());
+            ptr.push_back((int64_t)item.size());
+        }
+    }
+    out->nbEdges = (int64_t)edge.size();
+    out->nbItems = (int64_t)item.size();
+    out->edge = dup(edge);
+    out->ptr = dup(ptr);
+    out->item = dup(item);
+    return error ? -2 : 0;
+}
+
+extern "C" int dc_plan_build(dc_plan_t *plan, const int *conn, int nbElem, int nbNodes,
+                             const int *row, const int *col, int colBase, const int *treeRec,
+                             int64_t nbTreeRec, int maxSlots, int nbThreads)
+{
+    memset(plan, 0, sizeof *plan);
+    if (maxSlots < 16 || maxSlots > DC_SLOT_LIMIT) return -1;
+    if (nbElem >= (1 << 28)) { /* fallback items hold the element in 28 bits */ }
+    Mesh m{conn, nbElem, nbNodes, row, col, colBase, {}, {}};
+    build_node_to_elem(m);
+
+    Selector sel{m, treeRec, nbTreeRec, 0, maxSlots, {}, {}, {}};
+    if (treeRec && nbTreeRec > 0) sel.select();
+    else sel.split_rows(0, nbNodes);          /* no tree: plain row blocks */
+
+    /* every row must belong to exactly one unit or to the fallback list */
+    {
+        std::vector<char> covered((size_t)nbNodes, 0);
+        for (const UnitSeed &s : sel.seeds)
+            for (int n = s.nodeFirst; n < s.nodeFirst + s.nodeCount; n++) covered[n]++;
+        for (int n : sel.bigRows) covered[n]++;
+        for (int n = 0; n < nbNodes; n++) if (covered[n] != 1) return -3;
+    }
+
+    const int64_t nbUnits = (int64_t)sel.seeds.size();
+    std::vector<dc_unit_t> units((size_t)nbUnits);
+    std::vector<int32_t> diagRel((size_t)nbNodes, -1);
+    const int nt = nbThreads > 0 ? nbThreads : omp_get_max_threads();
+    std::vector<std::vector<dc_task_t>> tTasks((size_t)nt);
+    std::vector<std::vector<uint16_t>> tItems((size_t)nt);
+    std::vector<int> unitThread((size_t)nbUnits);
+    int error = 0;
+    int64_t useful = 0;
+
+    #pragma omp parallel num_threads(nt) reduction(|:error) reduction(+:useful)
+    {
+        const int tid = omp_get_thread_num();
+        UnitOut out;
+        std::vector<std::vector<uint16_t>> perEdge;
+        #pragma omp for schedule(dynamic, 64)
+        for (int64_t u = 0; u < nbUnits; u++) {
+            const UnitSeed &s = sel.seeds[(size_t)u];
+            out.tasks.clear();
+            out.items.clear();
+            out.useful = 0;
+            build_unit(m, s, diagRel.data(), out, perEdge, error);
+            dc_unit_t &d = units[(size_t)u];
+            memset(&d, 0, sizeof d);
+            d.edgeFirst = row[s.nodeFirst];
+            d.edgeCount = row[s.nodeFirst + s.nodeCount] - row[s.nodeFirst];
+            d.nodeFirst = s.nodeFirst;
+            d.nodeCount = s.nodeCount;
+            d.ownElemFirst = s.ownFirst;
+            d.ownElemCount = s.ownCount;
+            d.haloCount = (int32_t)s.halo.size();
+            d.taskFirst = (int32_t)tTasks[tid].size();     /* thread-local, fixed up below */
+            d.taskCount = (int32_t)out.tasks.size();
+            d.itemFirst = (int64_t)tItems[tid].size();
+            unitThread[(size_t)u] = tid;
+            tTasks[tid].insert(tTasks[tid].end(), out.tasks.begin(), out.tasks.end());
+            tItems[tid].insert(tItems[tid].end(), out.items.begin(), out.items.end());
+            useful += out.useful;
+        }
+    }
+    if (error) return -2;
+
+    std::vector<int64_t> taskBase((size_t)nt + 1, 0), itemBase((size_t)nt + 1, 0);
+    for (int t = 0; t < nt; t++) {
+        taskBase[(size_t)t + 1] = taskBase[t] + (int64_t)tTasks[t].size();
+        itemBase[(size_t)t + 1] = itemBase[t] + (int64_t)tItems[t].size();
+    }
+    if (taskBase[nt] >= INT32_MAX) return -4;
+    plan->nbTasks = taskBase[nt];
+    plan->nbItems = itemBase[nt];
+    plan->tasks = (dc_task_t *)malloc(sizeof(dc_task_t) * (size_t)(plan->nbTasks ? plan->nbTasks : 1));
+    plan->items = (uint16_t *)malloc(sizeof(uint16_t) * (size_t)(plan->nbItems ? plan->nbItems : 1));
+    for (int t = 0; t < nt; t++) {
+        if (!tTasks[t].empty()) memcpy(plan->tasks + taskBase[t], tTasks[t].data(), sizeof(dc_task_t) * tTasks[t].size());
+        if (!tItems[t].empty()) memcpy(plan->items + itemBase[t], tItems[t].data(), sizeof(uint16_t) * tItems[t].size());
+        std::vector<dc_task_t>().swap(tTasks[t]);
+        std::vector<uint16_t>().swap(tItems[t]);
+    }
+    int64_t haloTotal = 0, slotsTotal = 0;
+    int maxUsed = 0;
+    for (int64_t u = 0; u < nbUnits; u++) {
+        dc_unit_t &d = units[(size_t)u];
+        const int t = unitThread[(size_t)u];
+        d.taskFirst += (int32_t)taskBase[t];
+        d.itemFirst += itemBase[t];
+        d.haloFirst = haloTotal;
+        haloTotal += d.haloCount;
+        slotsTotal += d.ownElemCount + d.haloCount;
+        maxUsed = std::max(maxUsed, d.ownElemCount + d.haloCount);
+    }
+    plan->haloElems = (int32_t *)malloc(sizeof(int32_t) * (size_t)(haloTotal ? haloTotal : 1));
+    for (int64_t u = 0; u < nbUnits; u++) {
+        const std::vector<int> &h = sel.seeds[(size_t)u].halo;
+        if (!h.empty()) memcpy(plan->haloElems + units[(size_t)u].haloFirst, h.data(), sizeof(int32_t) * h.size());
+    }
+    plan->nbHalo = haloTotal;
+    plan->nbUnits = nbUnits;
+    plan->units = dup(units);
+    plan->diagRel = dup(diagRel);
+    plan->maxSlots = maxUsed;
+    plan->nbSlotsTotal = slotsTotal;
+    plan->nbItemsUseful = useful;
+    if (!sel.bigRows.empty()) {
+        int rc = dc_contrib_build(&plan->big, conn, nbElem, nbNodes, row, col, colBase,
+                                  sel.bigRows.data(), (int64_t)sel.bigRows.size());
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+extern "C" void dc_contrib_free(dc_contrib_list_t *c)
+{
+    free(c->edge); free(c->ptr); free(c->item);
+    memset(c, 0, sizeof *c);
+}
+
+extern "C" void dc_plan_free(dc_plan_t *plan)
+{
+    free(plan->units); free(plan->tasks); free(plan->items); free(plan->haloElems); free(plan->diagRel);
+    dc_contrib_free(&plan->big);
+    memset(plan, 0, sizeof *plan);
+}

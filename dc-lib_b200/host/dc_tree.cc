@@ -106,6 +106,12 @@ static void metis_recursive(std::vector<int> &part, std::vector<int64_t> &xadj,
 {
     int64_t n = nbNodes, ncon = 1, np = nbPart, objval = 0;
     std::vector<int64_t> p((size_t)(nbNodes > 0 ? nbNodes : 1), 0);
+    if (nbPart < 2 || nbNodes < 1) {
+        /* one part: METIS leaves the vector untouched (the reference then reads
+         * uninitialised memory); the only sensible answer is "everything in part 0" */
+        part.assign((size_t)nbNodes, 0);
+        return;
+    }
     if (adjncy.empty()) adjncy.push_back(0);
     METIS_PartGraphRecursive(&n, &ncon, xadj.data(), adjncy.data(), nullptr, nullptr, nullptr,
                              &np, nullptr, nullptr, nullptr, &objval, p.data());

@@ -1,0 +1,85 @@
+/* dc_cuda.h -- thin C ABI between the host library (C/C++/Fortran callers) and the
+ * CUDA side of dc-b200.  Plain pointers, sizes and int return codes only; no C++
+ * or torch types.  0 = success, negative = error (dc_cuda_last_error() explains).
+ *
+ * What each entry point replaces in the reference (all CPU there):
+ *   dc_cuda_assemble          the per-step hot path: DC_tree_traversal walking the
+ *                             tree and running the user's element callbacks
+ *                             (src/tree_traversal.cc:27-117), including the CSR
+ *                             reset over the DC_finalize_tree edge intervals
+ *                             (src/tree_creation.cc:185-186, tree_traversal.cc:39-41)
+ *   dc_cuda_set_mesh / plan   the user data reached through `userArgs`
+ *                             (tree_traversal.cc:51,56,61) and the tree_t schedule
+ *                             (include/DC.h:27-36)
+ *   dc_cuda_permute_* /       DC_permute_double_2d_array / DC_permute_int_2d_array /
+ *   dc_cuda_renumber          DC_permute_int_1d_array / DC_renumber_int_array
+ *                             (src/permutations.cc:22-115)
+ * Pointers named d_* are DEVICE pointers, h_* are HOST pointers.  `stream` is a
+ * cudaStream_t passed as void* (NULL = legacy default stream).
+ */
+#ifndef DC_CUDA_H
+#define DC_CUDA_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dc_cuda_ctx dc_cuda_ctx;
+struct dc_plan_s;   /* dc_plan_t, see dc-lib_b200/csrc/dc_plan.h */
+
+enum { DC_OP_P1_TET_LAPLACIAN = 0, DC_OP_P1_TET_ELASTICITY = 1 };
+enum {
+    DC_MODE_DETERMINISTIC = 0,  /* work units, every edge summed in ascending element order */
+    DC_MODE_ATOMIC        = 1,  /* reset + one thread per element + red.global.add.f64      */
+    DC_MODE_LIST          = 2   /* one thread per edge over explicit contribution lists     */
+};
+
+const char *dc_cuda_last_error(void);
+int  dc_cuda_device_count(void);
+
+int  dc_cuda_create(dc_cuda_ctx **ctx, int device);
+void dc_cuda_destroy(dc_cuda_ctx *ctx);
+
+/* Mesh + CSR pattern, copied from host memory.  h_conn: [nbElem][4] 1-based,
+ * renumbered, tree order; h_coord: [nbNodes][3]; h_row: [nbNodes+1]; h_col: [nnz]. */
+int  dc_cuda_set_mesh(dc_cuda_ctx *ctx, const int *h_conn, const double *h_coord,
+                      const int *h_row, const int *h_col, int nbElem, int nbNodes, int colBase);
+/* Same, adopting arrays that already live in device memory (not copied, not freed). */
+int  dc_cuda_set_mesh_device(dc_cuda_ctx *ctx, const int *d_conn, const double *d_coord,
+                             const int *d_row, const int *d_col, int nbElem, int nbNodes,
+                             int64_t nnz, int colBase);
+/* New node coordinates for the next assembly (host -> device, asynchronous). */
+int  dc_cuda_update_coords(dc_cuda_ctx *ctx, const double *h_coord, void *stream);
+
+/* Schedule built by dc_plan_build() (host); copied to the device. */
+int  dc_cuda_upload_plan(dc_cuda_ctx *ctx, const struct dc_plan_s *plan);
+/* Explicit contribution lists for DC_MODE_LIST (all edges). */
+int  dc_cuda_upload_lists(dc_cuda_ctx *ctx, const int64_t *h_edge, const int64_t *h_ptr,
+                          const uint32_t *h_item, int64_t nbEdges, int64_t nbItems);
+
+/* One assembly: d_values[nnz * dim*dim] is reset and filled.  params: operator
+ * coefficients on the host ({} for the Laplacian, {lambda, mu} for elasticity). */
+int  dc_cuda_assemble(dc_cuda_ctx *ctx, int op, const double *h_params, int nbParams, int mode,
+                      double *d_values, void *stream);
+/* Convenience: values owned by the context. */
+int  dc_cuda_values(dc_cuda_ctx *ctx, int dim, double **d_values);
+int  dc_cuda_download_values(dc_cuda_ctx *ctx, int dim, double *h_values, void *stream);
+
+/* Permutation family on device arrays: d_out[perm[i]] = d_in[i] (rows of dimItem). */
+int  dc_cuda_permute_double_2d(const double *d_in, double *d_out, const int *d_perm,
+                               int64_t nbItem, int dimItem, void *stream);
+int  dc_cuda_permute_int_2d(const int *d_in, int *d_out, const int *d_perm, int64_t nbItem,
+                            int dimItem, void *stream);
+int  dc_cuda_renumber(int *d_tab, const int *d_perm, int64_t size, int isFortran, void *stream);
+/* Zero d_values[first*perEdge, (last+1)*perEdge) -- the reset of one edge interval. */
+int  dc_cuda_reset_edges(double *d_values, int64_t firstEdge, int64_t lastEdge, int perEdge,
+                         void *stream);
+
+/* Number of kernels this context has launched (for honest launch accounting). */
+int64_t dc_cuda_launch_count(const dc_cuda_ctx *ctx);
+int  dc_cuda_sync(void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

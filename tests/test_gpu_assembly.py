@@ -1,0 +1,142 @@
+"""Parity tests proper: the CUDA assembly, called through the C ABI (include/dc_cuda.h),
+against the CPU oracle on the same seeded meshes and against the golden vectors produced by
+the reference itself.  Deterministic / list modes: bit-exact.  Atomic mode: max relative
+error <= 1e-12 (the north-star tolerance; order of the red.global adds is free)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import common
+import dc_lib_b200 as dc
+from common import GOLDEN, LAMBDA, MU, MineLib, md5, oracle_serial, prepare_mesh, tree_records
+
+pytestmark = pytest.mark.gpu
+
+with open(os.path.join(GOLDEN, "golden.json")) as f:
+    GOLD = json.load(f)
+
+OPS = {1: (dc.OP_LAPLACIAN, None), 3: (dc.OP_ELASTICITY, [LAMBDA, MU])}
+REL_TOL = 1e-12
+
+
+def _ctx(mesh, slots=832, lists=False, with_tree=True):
+    ctx = dc.Context(0)
+    ctx.set_mesh(mesh["conn"], mesh["coord"], mesh["row"], mesh["col"], 0)
+    rec = tree_records(mesh) if with_tree else None
+    plan = dc.HostPlan(mesh["conn"], mesh["N"], mesh["row"], mesh["col"], 0, rec, slots)
+    ctx.upload_plan(plan)
+    if lists:
+        ctx.upload_lists(mesh["conn"], mesh["N"], mesh["row"], mesh["col"], 0)
+    return ctx, plan
+
+
+def _run(ctx, mesh, dim, mode):
+    import torch
+    op, prm = OPS[dim]
+    vals = torch.full((mesh["nnz"] * dim * dim,), float("nan"), dtype=torch.float64, device="cuda:0")
+    ctx.assemble(op, prm, mode, vals)
+    torch.cuda.synchronize()
+    return vals.cpu().numpy()
+
+
+def _rel_err(got, want):
+    scale = np.abs(want).max()
+    return np.abs(got - want).max() / scale
+
+
+@pytest.mark.parametrize("key", [k for k, v in GOLD.items() if v["n"] <= 20])
+@pytest.mark.parametrize("dim", [1, 3])
+def test_deterministic_matches_reference_golden(tmp_path, key, dim):
+    """Values produced by the reference's own traversal (golden md5) == GPU deterministic mode."""
+    g = GOLD[key]
+    mesh = prepare_mesh(MineLib(g["vec"]), g["n"], tmp_path, hub=g["hub"])
+    ctx, _ = _ctx(mesh)
+    got = _run(ctx, mesh, dim, dc.MODE_DETERMINISTIC)
+    assert md5(got) == g[f"values_md5_d{dim}"]
+    raw = os.path.join(GOLDEN, f"{key}_values_d1.npy")
+    if dim == 1 and os.path.exists(raw):
+        assert np.load(raw).tobytes() == got.tobytes()
+
+
+@pytest.mark.parametrize("key,dim", [("kuhn40_vec0", 1), ("kuhn40_vec4", 3), ("kuhn40_vec4", 1)])
+def test_baseline_configs_c1_c2(tmp_path, key, dim):
+    """BASELINE configs: 40^3 cube, Laplacian on the pure tree (C1) and elasticity on the
+    D&C + colouring tree (C2)."""
+    g = GOLD[key]
+    mesh = prepare_mesh(MineLib(g["vec"]), g["n"], tmp_path)
+    ctx, _ = _ctx(mesh)
+    got = _run(ctx, mesh, dim, dc.MODE_DETERMINISTIC)
+    assert md5(got) == g[f"values_md5_d{dim}"]
+    fast = _run(ctx, mesh, dim, dc.MODE_ATOMIC)
+    assert _rel_err(fast, got) <= REL_TOL
+
+
+@pytest.mark.parametrize("n,vec,dim,slots,hub", [
+    (8, 0, 1, 832, False), (8, 4, 3, 832, False), (12, 0, 3, 200, False), (12, 2, 1, 64, False),
+    (16, 8, 3, 832, False), (18, 0, 3, 832, True), (18, 4, 1, 100, True), (3, 0, 3, 832, False),
+    (1, 0, 1, 832, False)])
+def test_all_modes_against_oracle(tmp_path, n, vec, dim, slots, hub):
+    """Small slot budgets force leaf splitting and the big-row fallback; hub meshes have
+    nodes of valence ~100 (BASELINE config C5)."""
+    mesh = prepare_mesh(MineLib(vec), n, tmp_path, hub=hub)
+    want = oracle_serial(mesh, dim)
+    ctx, plan = _ctx(mesh, slots=slots, lists=True)
+    det = _run(ctx, mesh, dim, dc.MODE_DETERMINISTIC)
+    assert det.tobytes() == want.tobytes()
+    lst = _run(ctx, mesh, dim, dc.MODE_LIST)
+    assert lst.tobytes() == want.tobytes()
+    fast = _run(ctx, mesh, dim, dc.MODE_ATOMIC)
+    assert _rel_err(fast, want) <= REL_TOL
+    if slots <= 100 and hub:
+        assert plan.c.big.nbEdges > 0           # the fallback really ran
+
+
+def test_plan_without_tree_is_still_bit_exact(tmp_path):
+    mesh = prepare_mesh(MineLib(0), 10, tmp_path)
+    ctx, _ = _ctx(mesh, slots=400, with_tree=False)
+    for dim in (1, 3):
+        assert _run(ctx, mesh, dim, dc.MODE_DETERMINISTIC).tobytes() == oracle_serial(mesh, dim).tobytes()
+
+
+def test_host_array_entry_point_and_coordinate_update(tmp_path):
+    """The call a reference user makes: host values array out, new coordinates in."""
+    mesh = prepare_mesh(MineLib(0), 8, tmp_path)
+    ctx, _ = _ctx(mesh)
+    out = np.full(mesh["nnz"] * 9, np.nan)
+    ctx.assemble_to_host(dc.OP_ELASTICITY, [LAMBDA, MU], dc.MODE_DETERMINISTIC, out)
+    assert out.tobytes() == oracle_serial(mesh, 3).tobytes()
+    moved = dict(mesh)
+    moved["coord"] = np.ascontiguousarray(mesh["coord"] * 1.25 + 0.1)
+    ctx.update_coords(moved["coord"])
+    ctx.assemble_to_host(dc.OP_ELASTICITY, [LAMBDA, MU], dc.MODE_DETERMINISTIC, out)
+    assert out.tobytes() == oracle_serial(moved, 3).tobytes()
+    assert ctx.launch_count() == 2
+
+
+def test_repeatable_and_physical_properties_at_larger_size(tmp_path):
+    """Size-independent properties on a mesh the oracle does not need to finish: run-to-run
+    bitwise repeatability, zero row sums of the Laplacian (constants are in its kernel),
+    block symmetry K_ij = K_ji^T, rigid translations in the kernel of elasticity."""
+    n = 48
+    mesh = prepare_mesh(MineLib(4), n, tmp_path)
+    ctx, _ = _ctx(mesh)
+    a = _run(ctx, mesh, 1, dc.MODE_DETERMINISTIC)
+    b = _run(ctx, mesh, 1, dc.MODE_DETERMINISTIC)
+    assert a.tobytes() == b.tobytes()
+    row, col = mesh["row"], mesh["col"]
+    rows = np.repeat(np.arange(mesh["N"]), np.diff(row))
+    rowsum = np.zeros(mesh["N"])
+    np.add.at(rowsum, rows, a)
+    assert np.abs(rowsum).max() <= 1e-10 * np.abs(a).max()
+    import scipy.sparse as sp
+    A = sp.csr_matrix((a, col, row), shape=(mesh["N"], mesh["N"]))
+    assert abs(A - A.T).max() == 0.0                       # bitwise symmetric
+    e = _run(ctx, mesh, 3, dc.MODE_DETERMINISTIC).reshape(-1, 3, 3)
+    for comp in range(3):
+        acc = np.zeros((mesh["N"], 3))
+        np.add.at(acc, rows, e[:, :, comp])
+        assert np.abs(acc).max() <= 1e-10 * np.abs(e).max()
+    fast = _run(ctx, mesh, 3, dc.MODE_ATOMIC)
+    assert _rel_err(fast, e.reshape(-1)) <= REL_TOL

@@ -1,0 +1,92 @@
+"""Invariants of the device schedule built on the host (host/dc_plan.cc)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import common
+import dc_lib_b200 as dc
+from common import MineLib, prepare_mesh, tree_records
+
+
+def _plan_arrays(p):
+    c = p.c
+    units = [c.units[i] for i in range(c.nbUnits)]
+    tasks = [c.tasks[i] for i in range(c.nbTasks)]
+    items = np.ctypeslib.as_array(c.items, shape=(max(c.nbItems, 1),))[:c.nbItems]
+    halo = np.ctypeslib.as_array(c.haloElems, shape=(max(c.nbHalo, 1),))[:c.nbHalo]
+    return units, tasks, items, halo
+
+
+@pytest.mark.parametrize("n,vec,slots,hub", [(8, 0, 832, False), (10, 4, 832, False), (10, 0, 200, False),
+                                             (12, 0, 64, False), (18, 0, 832, True), (18, 0, 120, True)])
+def test_plan_covers_every_contribution_once(tmp_path, n, vec, slots, hub):
+    mesh = prepare_mesh(MineLib(vec), n, tmp_path, hub=hub)
+    rec = tree_records(mesh)
+    plan = dc.HostPlan(mesh["conn"], mesh["N"], mesh["row"], mesh["col"], 0, rec, slots)
+    units, tasks, items, halo = _plan_arrays(plan)
+    E, N, nnz = mesh["E"], mesh["N"], mesh["nnz"]
+    conn = mesh["conn"].astype(np.int64) - 1
+    row, col = mesh["row"], mesh["col"]
+    # expected number of contributions per edge
+    want = np.zeros(nnz, dtype=np.int64)
+    pos = {}
+    for i in range(N):
+        for k in range(row[i], row[i + 1]):
+            pos[(i, int(col[k]))] = k
+    for e in range(E):
+        for a in range(4):
+            for b in range(4):
+                want[pos[(int(conn[e, a]), int(conn[e, b]))]] += 1
+    got = np.zeros(nnz, dtype=np.int64)
+    rows_seen = np.zeros(N, dtype=np.int64)
+    for u in units:
+        rows_seen[u.nodeFirst:u.nodeFirst + u.nodeCount] += 1
+        assert u.edgeFirst == row[u.nodeFirst] and u.edgeCount == row[u.nodeFirst + u.nodeCount] - row[u.nodeFirst]
+        nslots = u.ownElemCount + u.haloCount
+        assert nslots <= slots
+        elems = list(range(u.ownElemFirst, u.ownElemFirst + u.ownElemCount)) + \
+            halo[u.haloFirst:u.haloFirst + u.haloCount].tolist()
+        for t in tasks[u.taskFirst:u.taskFirst + u.taskCount]:
+            block = items[u.itemFirst + t.itemRel:u.itemFirst + t.itemRel + 32 * t.iters].reshape(t.iters, 32)
+            for lane in range(32):
+                if t.kind == 0:
+                    if (t.mask >> lane) & 1 or t.first + lane >= u.edgeCount:
+                        assert (block[:, lane] == 0xFFFF).all()
+                        continue
+                    k = u.edgeFirst + t.first + lane
+                else:
+                    if not (t.mask >> lane) & 1:
+                        assert (block[:, lane] == 0xFFFF).all()
+                        continue
+                    node = u.nodeFirst + t.first + lane
+                    k = u.edgeFirst + plan.c.diagRel[node]
+                    assert col[k] == node
+                i_row = int(np.searchsorted(row, k, side="right") - 1)
+                last = -1
+                for it in block[:, lane]:
+                    if it == 0xFFFF:
+                        continue
+                    e = elems[it >> 4]
+                    a, b = (it >> 2) & 3, it & 3
+                    assert conn[e, a] == i_row and conn[e, b] == col[k]
+                    assert e > last                      # ascending element order inside an edge
+                    last = e
+                    got[k] += 1
+    big = plan.c.big
+    for q in range(big.nbEdges):
+        k = big.edge[q]
+        rows_seen[int(np.searchsorted(row, k, side="right") - 1)] += 0
+        got[k] += big.ptr[q + 1] - big.ptr[q]
+    covered = rows_seen.copy()
+    for q in range(big.nbEdges):
+        covered[int(np.searchsorted(row, big.edge[q], side="right") - 1)] = 1
+    assert (covered == 1).all()
+    assert np.array_equal(got, want)
+    assert plan.c.nbItemsUseful + big.nbItems == 16 * E
+
+
+def test_plan_without_tree_uses_row_blocks(tmp_path):
+    mesh = prepare_mesh(MineLib(0), 8, tmp_path)
+    plan = dc.HostPlan(mesh["conn"], mesh["N"], mesh["row"], mesh["col"], 0, None, 300)
+    assert plan.c.nbUnits > 1 and plan.c.nbItemsUseful == 16 * mesh["E"]
