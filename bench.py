@@ -1,0 +1,252 @@
+#!/usr/bin/env python
+"""bench.py -- assembled elements/s of the DC-lib assembly path on B200 (BASELINE.json metric).
+
+A step = one reset + assembly of the whole CSR matrix (every value written once) on a
+synthetic jittered Kuhn-cube mesh.  `value` times the device-resident path with CUDA events;
+`e2e` times the call a reference user makes (host coordinates in, host nodeToNodeValue out,
+through the C ABI) with the copies inside the timed region; `roofline` relates the dominant
+kernel to the measured HBM copy bandwidth; `cpu_baseline` times the reference's own CPU
+traversal (oracle/_ref, OpenMP) on a bounded sample.  `--impl reference` prints the reference
+arm alone.  See DESIGN.md for the byte model.
+"""
+import argparse
+import json
+import os
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LAMBDA, MU = 0.5769230769230769, 0.3846153846153846      # E = 1, nu = 0.3
+WORKLOADS = {
+    # name: (cube size, operatorDim, colouring vector length)
+    "target350": (350, 3, 0),     # north-star target: >= 256M tets, elasticity
+    "c3": (256, 1, 0),            # BASELINE config 3: ~100M tets, Laplacian
+    "c2": (40, 3, 4),             # BASELINE config 2: 40^3, elasticity, D&C + colouring
+    "m100": (100, 3, 0),          # 6M tets, elasticity (METIS tree)
+    "m64": (64, 3, 0),
+}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi-equivalent sampling (NVML) of SM clock and throttle reasons during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                     nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+            while not self.stop_flag:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.02)
+        except Exception as e:          # NVML missing: report that instead of inventing numbers
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def build_workload(dc, n, vec, rank=0):
+    """Appendix-A driver with the product library: mesh -> tree -> permute/renumber -> CSR -> finalize."""
+    t0 = time.time()
+    conn, N = dc.kuhn_cube(n)
+    coord = dc.jitter_coords(n, seed=12345 + rank)
+    E = conn.shape[0]
+    dc.DC_set_vec_size(vec)
+    dc.DC_create_tree(conn, E, 4, N)
+    dc.DC_permute_double_2d_array(coord, N, 3)
+    dc.DC_renumber_int_array(conn.reshape(-1), 4 * E)
+    row, col = dc.build_csr(conn, N)
+    dc.DC_finalize_tree(row, conn, E, 4)
+    rec = dc.flatten_tree()
+    return dict(conn=conn, coord=coord, row=row, col=col, E=E, N=N, nnz=int(row[-1]), rec=rec, n=n,
+                setup_s=time.time() - t0)
+
+
+def cpu_reference(dim, steps, warmup):
+    """The reference's own CPU path (oracle/_ref, OpenMP tasks, all host threads) on a bounded
+    sample: the 40^3 cube (384k tets), same operator.  Falls back to the oracle port (serial)
+    when oracle/_ref was not built."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import common
+    cores = os.cpu_count() or 1
+    with tempfile.TemporaryDirectory() as tmp:
+        if common.have_ref(0):
+            lib, kind = common.RefLib(0), "reference"
+        else:
+            lib, kind, cores = common.MineLib(0), "port", 1
+        mesh = common.prepare_mesh(lib, 40, tmp)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        if kind == "reference":
+            lib.traversal(mesh, dim)
+        else:
+            common.oracle_serial(mesh, dim)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    ms = 1e3 * sum(times) / len(times)
+    return {"value": mesh["E"] / (ms * 1e-3), "unit": "elements/s", "cores": cores, "kind": kind,
+            "sample": f"40^3 Kuhn cube (384000 tets), operatorDim {dim}, reference DC_tree_traversal "
+                      f"({'OpenMP tasks' if kind == 'reference' else 'oracle serial loop'}) with the oracle's "
+                      f"callbacks, mean of {steps} after {warmup} warm-up", "ms_per_step": ms}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="dc_b200", choices=["dc_b200", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("DC_BENCH_WORKLOAD", "m100"))
+    ap.add_argument("--slots", type=int, default=int(os.environ.get("DC_BENCH_SLOTS", "400")))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    n, dim, vec = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    config = {"workload": f"{args.workload}: jittered Kuhn cube {n}^3 ({6 * n ** 3} tets) per GPU, "
+                          f"operatorDim {dim} ({'isotropic elasticity' if dim == 3 else 'P1 Laplacian'}), "
+                          f"{'D&C + colouring VEC_SIZE ' + str(vec) if vec else 'pure D&C'} tree, "
+                          "reset + assembly per step",
+              "mode": "deterministic", "unit_slots": args.slots,
+              "l2": "value arrays larger than L2 (no flush needed)" if 6 * n ** 3 * 2.5 * dim * dim * 8 > 2.5e8
+                    else "working set fits L2; see roofline note"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        base = cpu_reference(dim, max(args.steps, 1), max(args.warmup, 1))
+        line = {"impl": "reference", "metric": "assembled elements/s (fp64, CSR scatter-add)", "value": base["value"],
+                "unit": "elements/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": base.pop("ms_per_step"), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": config, "cpu_baseline": base,
+                "e2e": {"value": base["value"], "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import numpy as np
+    import torch
+    import dc_lib_b200 as dc
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; dc-b200 has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    w = build_workload(dc, n, vec, rank)
+    E, N, nnz = w["E"], w["N"], w["nnz"]
+    t0 = time.time()
+    plan = dc.HostPlan(w["conn"], N, w["row"], w["col"], 0, w["rec"], args.slots)
+    plan_s = time.time() - t0
+    ctx = dc.Context(local)
+    ctx.set_mesh(w["conn"], w["coord"], w["row"], w["col"], 0)
+    ctx.upload_plan(plan)
+    op, prm = (dc.OP_ELASTICITY, [LAMBDA, MU]) if dim == 3 else (dc.OP_LAPLACIAN, None)
+    vals = torch.empty(nnz * dim * dim, dtype=torch.float64, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing -------------------------------------------------------
+    for _ in range(args.warmup):
+        ctx.assemble(op, prm, dc.MODE_DETERMINISTIC, vals, stream)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        ctx.assemble(op, prm, dc.MODE_DETERMINISTIC, vals, stream)
+    e1.record()
+    barrier()
+    launches = ctx.launch_count() - l0
+    ms = e0.elapsed_time(e1) / args.steps
+    sampler.stop_flag = True
+    sampler.join()
+
+    # ---- end to end through the host-array entry point ---------------------------------
+    h_coord = torch.from_numpy(w["coord"]).pin_memory()
+    h_vals = torch.empty(nnz * dim * dim, dtype=torch.float64).pin_memory()
+    e2e_steps = max(2, min(args.steps, 5))
+    for _ in range(2):
+        ctx.update_coords(h_coord.numpy(), stream)
+        ctx.assemble_to_host(op, prm, dc.MODE_DETERMINISTIC, h_vals.numpy(), stream)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ctx.update_coords(h_coord.numpy(), stream)
+        ctx.assemble_to_host(op, prm, dc.MODE_DETERMINISTIC, h_vals.numpy(), stream)
+    barrier()
+    e2e_ms = 1e3 * (time.perf_counter() - t0) / e2e_steps
+    checksum = float(h_vals.numpy()[:: max(1, h_vals.numel() // 1000003)].sum())
+
+    if world > 1:
+        t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = float(t[0]), float(t[1])
+        dist.barrier()
+    if rank != 0:
+        return
+
+    peak, peak_src = measured_peak()
+    b_alg = 16 * E + 24 * N + 4 * (N + 1) + 4 * nnz + 8 * dim * dim * nnz
+    achieved = b_alg / (ms * 1e-3) / 1e9
+    st = plan.stats()
+    line = {
+        "metric": "assembled elements/s (fp64, CSR scatter-add)", "value": world * E / (ms * 1e-3), "unit": "elements/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "kernel": "gather_units",
+                     "algorithmic_bytes_per_launch": b_alg, "bytes_per_element": b_alg / E},
+        "e2e": {"value": world * E / (e2e_ms * 1e-3), "unit": "elements/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": 24 * N, "d2h_bytes_per_step": 8 * dim * dim * nnz, "steps": e2e_steps,
+                "checksum": checksum},
+        "gpu_launches": launches, "clocks": sampler.summary(),
+        "setup": {"tree_and_csr_s": w["setup_s"], "plan_s": plan_s, "units": st["units"],
+                  "element_setups_per_element": st["slots_total"] / E,
+                  "item_padding_efficiency": st["items_useful"] / max(st["items"], 1), "host_cores": os.cpu_count()},
+    }
+    if not args.no_cpu_baseline:
+        base = cpu_reference(dim, 5, 1)
+        base.pop("ms_per_step")
+        line["cpu_baseline"] = base
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -52,7 +52,7 @@ class Unit(ctypes.Structure):
     _fields_ = [("edgeFirst", c_int64), ("itemFirst", c_int64), ("haloFirst", c_int64),
                 ("edgeCount", c_int32), ("nodeFirst", c_int32), ("nodeCount", c_int32),
                 ("ownElemFirst", c_int32), ("ownElemCount", c_int32), ("haloCount", c_int32),
-                ("taskFirst", c_int32), ("taskCount", c_int32), ("pad_", c_int32)]
+                ("taskFirst", c_int32), ("taskCount", c_int32), ("itemCount", c_int32)]
 
 
 class Task(ctypes.Structure):
@@ -66,7 +66,8 @@ class ContribList(ctypes.Structure):
 
 
 class Plan(ctypes.Structure):
-    _fields_ = [("maxSlots", c_int32), ("nbUnits", c_int64), ("nbTasks", c_int64),
+    _fields_ = [("maxSlots", c_int32), ("maxHalo", c_int32), ("maxTasks", c_int32), ("maxItems", c_int32),
+                ("nbUnits", c_int64), ("nbTasks", c_int64),
                 ("nbItems", c_int64), ("nbHalo", c_int64), ("units", POINTER(Unit)),
                 ("tasks", POINTER(Task)), ("items", POINTER(c_uint16)),
                 ("haloElems", POINTER(c_int32)), ("diagRel", POINTER(c_int32)),
@@ -94,6 +95,7 @@ def _declare(L):
     L.dc_cuda_launch_count.argtypes = [vp]
     L.dc_cuda_launch_count.restype = c_int64
     L.dc_cuda_sync.argtypes = [vp]
+    L.dc_cuda_set_option.argtypes = [vp, c_char_p, c_int]
     L.dc_plan_build.argtypes = [POINTER(Plan), vp, c_int, c_int, vp, vp, c_int, vp, c_int64, c_int, c_int]
     L.dc_contrib_build.argtypes = [POINTER(ContribList), vp, c_int, c_int, vp, vp, c_int, vp, c_int64]
     L.dc_plan_free.argtypes = [POINTER(Plan)]
@@ -304,6 +306,9 @@ class Context:
                  "dc_cuda_assemble")
         self._ck(lib().dc_cuda_download_values(self.h, dim, _p(out), stream), "dc_cuda_download_values")
         self._ck(lib().dc_cuda_sync(stream), "dc_cuda_sync")
+
+    def set_option(self, name, value):
+        self._ck(lib().dc_cuda_set_option(self.h, name.encode(), int(value)), "dc_cuda_set_option")
 
     def launch_count(self):
         return int(lib().dc_cuda_launch_count(self.h))

@@ -37,7 +37,8 @@ struct dc_cuda_ctx {
     int *d_conn = nullptr, *d_row = nullptr, *d_col = nullptr;
     double *d_coord = nullptr;
     /* plan */
-    int maxSlots = 0;
+    int maxSlots = 0, maxHalo = 0, maxTasks = 0, maxItems = 0;
+    int threads = 256;       /* CTA size of the unit kernel (128 or 256) */
     int64_t nbUnits = 0, nbBigEdges = 0;
     dc_unit_t *d_units = nullptr;
     dc_task_t *d_tasks = nullptr;
@@ -188,6 +189,9 @@ extern "C" int dc_cuda_upload_plan(dc_cuda_ctx *c, const struct dc_plan_s *p)
     c->nbUnits = p->nbUnits;
     c->nbBigEdges = p->big.nbEdges;
     c->maxSlots = p->maxSlots;
+    c->maxHalo = p->maxHalo;
+    c->maxTasks = p->maxTasks;
+    c->maxItems = p->maxItems;
     return 0;
 }
 
@@ -205,29 +209,28 @@ extern "C" int dc_cuda_upload_lists(dc_cuda_ctx *c, const int64_t *h_edge, const
     return 0;
 }
 
-template <class Op>
-static size_t unit_smem_bytes(int maxSlots, int threads)
+template <class Op, int THREADS, int MINB>
+static int launch_units(dc_cuda_ctx *c, double *d_values, cudaStream_t s)
 {
-    constexpr int DD = UnitSmem<Op>::DD;
-    constexpr int RS = UnitSmem<Op>::RS;
-    size_t a = (size_t)maxSlots * 16, b = (size_t)(threads / 32) * 32 * DD * 8;
-    return 16 + (a > b ? a : b) + (size_t)maxSlots * RS * 8;
+    const UnitLayout L = UnitSmem<Op>::layout(c->maxSlots, c->maxHalo, c->maxTasks, c->maxItems, THREADS);
+    if (L.total > 227 * 1024) return fail(-11, "dc_cuda_assemble: unit does not fit in shared memory");
+    auto kern = gather_units<Op, THREADS, MINB>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    kern<<<(unsigned)c->nbUnits, THREADS, (size_t)L.total, s>>>(c->d_units, c->d_tasks, c->d_items, c->d_halo,
+                                                                 c->d_diagRel, c->d_conn, c->d_coord, d_values, L);
+    return 0;
 }
 
 template <class Op>
 static int assemble_t(dc_cuda_ctx *c, int mode, double *d_values, cudaStream_t s)
 {
     constexpr int DD = Op::D * Op::D;
-    constexpr int THREADS = 256;
     if (mode == DC_MODE_DETERMINISTIC) {
         if (!c->d_units && c->nbBigEdges == 0) return fail(-6, "dc_cuda_assemble: no plan uploaded");
         if (c->nbUnits > 0) {
-            size_t smem = unit_smem_bytes<Op>(c->maxSlots, THREADS);
-            auto kern = gather_units<Op, THREADS>;
-            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kern<<<(unsigned)c->nbUnits, THREADS, smem, s>>>(c->d_units, c->d_tasks, c->d_items, c->d_halo,
-                                                               c->d_diagRel, c->d_conn, c->d_coord, d_values,
-                                                               c->maxSlots);
+            int rc = (c->threads == 128) ? launch_units<Op, 128, 4>(c, d_values, s)
+                                         : launch_units<Op, 256, 2>(c, d_values, s);
+            if (rc) return rc;
             c->launches++;
         }
         if (c->nbBigEdges > 0) {
@@ -349,6 +352,17 @@ extern "C" int dc_cuda_reset_edges(double *d_values, int64_t firstEdge, int64_t 
     reset_values<<<grid_for(n / 2 + 1, 256), 256, 0, (cudaStream_t)stream>>>(d_values + firstEdge * perEdge, n);
     CK(cudaGetLastError());
     return 0;
+}
+
+extern "C" int dc_cuda_set_option(dc_cuda_ctx *c, const char *name, int value)
+{
+    if (!c || !name) return fail(-1, "dc_cuda_set_option: null argument");
+    if (!strcmp(name, "unit_threads")) {
+        if (value != 128 && value != 256) return fail(-12, "dc_cuda_set_option: unit_threads must be 128 or 256");
+        c->threads = value;
+        return 0;
+    }
+    return fail(-12, "dc_cuda_set_option: unknown option");
 }
 
 extern "C" int64_t dc_cuda_launch_count(const dc_cuda_ctx *c) { return c ? c->launches : 0; }

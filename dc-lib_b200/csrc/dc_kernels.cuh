@@ -86,84 +86,150 @@ __device__ __forceinline__ void load_element(const int *__restrict__ conn, const
 
 /* ---- deterministic assembly over work units ------------------------------ */
 
+/* shared-memory geometry of a unit launch, computed on the host from the plan */
+struct UnitLayout {
+    int offStage;    /* region A: own connectivity (TMA target), later per-warp output staging */
+    int offHalo;     /* halo element ids                                                     */
+    int offTasks;    /* dc_task_t records                                                    */
+    int offItems;    /* uint16 items                                                         */
+    int offRecs;     /* element records                                                      */
+    int total;
+};
+
 template <class Op>
 struct UnitSmem {
     static constexpr int DD = Op::D * Op::D;
-    /* record stride in doubles: odd multiple of 2 words keeps 64-bit accesses of
+    /* record stride in doubles: an odd number of 8-byte words keeps 64-bit accesses of
      * different slots spread over the banks */
     static constexpr int RS = (Op::NS % 2 == 0) ? Op::NS + 1 : Op::NS;
+    static UnitLayout layout(int maxSlots, int maxHalo, int maxTasks, int maxItems, int threads)
+    {
+        auto up = [](int v) { return (v + 15) & ~15; };
+        UnitLayout L;
+        const int a = maxSlots * 16, b = (threads / 32) * 32 * DD * 8;
+        L.offStage = 32;
+        L.offHalo = L.offStage + up(a > b ? a : b);
+        L.offTasks = L.offHalo + up(maxHalo * 4);
+        L.offItems = L.offTasks + up(maxTasks * 16);
+        L.offRecs = L.offItems + up(maxItems * 2);
+        L.total = L.offRecs + maxSlots * RS * 8;
+        return L;
+    }
 };
 
-template <class Op, int THREADS>
-__global__ void __launch_bounds__(THREADS) gather_units(const dc_unit_t *__restrict__ units,
-                                                        const dc_task_t *__restrict__ tasks,
-                                                        const uint16_t *__restrict__ items,
-                                                        const int *__restrict__ haloElems,
-                                                        const int *__restrict__ diagRel,
-                                                        const int *__restrict__ conn,
-                                                        const double *__restrict__ coord,
-                                                        double *__restrict__ values, int maxSlots)
+template <class Op, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *__restrict__ units,
+                                                              const dc_task_t *__restrict__ tasks,
+                                                              const uint16_t *__restrict__ items,
+                                                              const int *__restrict__ haloElems,
+                                                              const int *__restrict__ diagRel,
+                                                              const int *__restrict__ conn,
+                                                              const double *__restrict__ coord,
+                                                              double *__restrict__ values, const UnitLayout L)
 {
     constexpr int DD = UnitSmem<Op>::DD;
     constexpr int RS = UnitSmem<Op>::RS;
     constexpr int NW = THREADS / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    /* layout: [0,16) mbarrier | region A: own connectivity (TMA target), later the
-     * per-warp output staging | region B: element records */
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
-    int4 *connS = reinterpret_cast<int4 *>(smem_raw + 16);
-    double *stage = reinterpret_cast<double *>(smem_raw + 16);
-    const size_t regionA = (size_t)((maxSlots * 16 > NW * 32 * DD * 8) ? maxSlots * 16 : NW * 32 * DD * 8);
-    double *recs = reinterpret_cast<double *>(smem_raw + 16 + regionA);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);          /* bar[0]: mesh data, bar[1]: schedule */
+    int4 *connS = reinterpret_cast<int4 *>(smem_raw + L.offStage);
+    double *stage = reinterpret_cast<double *>(smem_raw + L.offStage);
+    int *haloS = reinterpret_cast<int *>(smem_raw + L.offHalo);
+    dc_task_t *taskS = reinterpret_cast<dc_task_t *>(smem_raw + L.offTasks);
+    uint16_t *itemS = reinterpret_cast<uint16_t *>(smem_raw + L.offItems);
+    double *recs = reinterpret_cast<double *>(smem_raw + L.offRecs);
 
     const dc_unit_t u = units[blockIdx.x];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nSlots = u.ownElemCount + u.haloCount;
 
-    /* P0: own connectivity rows are contiguous in tree order -> one bulk copy */
-    if (tid == 0) mbar_init(bar, 1);
-    __syncthreads();
-    const uint32_t ownBytes = (uint32_t)u.ownElemCount * 16u;
-    if (tid == 0 && ownBytes) {
-        mbar_expect_tx(bar, ownBytes);
-        tma_bulk_g2s(connS, reinterpret_cast<const int4 *>(conn) + u.ownElemFirst, ownBytes, bar);
+    /* P0: everything the unit reads that is contiguous in HBM comes in as TMA bulk copies:
+     * own connectivity rows (tree order makes them one range), halo ids, tasks, items */
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
     }
-    if (ownBytes) mbar_wait(bar, 0);
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t ownBytes = (uint32_t)u.ownElemCount * 16u;
+        const uint32_t haloBytes = (uint32_t)((u.haloCount + 3) & ~3) * 4u;
+        mbar_expect_tx(&bar[0], ownBytes + haloBytes);
+        if (ownBytes) tma_bulk_g2s(connS, reinterpret_cast<const int4 *>(conn) + u.ownElemFirst, ownBytes, &bar[0]);
+        if (haloBytes) tma_bulk_g2s(haloS, haloElems + u.haloFirst, haloBytes, &bar[0]);
+        const uint32_t taskBytes = (uint32_t)u.taskCount * 16u, itemBytes = (uint32_t)u.itemCount * 2u;
+        mbar_expect_tx(&bar[1], taskBytes + itemBytes);
+        if (taskBytes) tma_bulk_g2s(taskS, tasks + u.taskFirst, taskBytes, &bar[1]);
+        if (itemBytes) tma_bulk_g2s(itemS, items + u.itemFirst, itemBytes, &bar[1]);
+    }
+    mbar_wait(&bar[0], 0);
 
-    /* P1: one record per touched element */
-    for (int s = tid; s < nSlots; s += THREADS) {
-        int4 c;
-        if (s < u.ownElemCount) c = connS[s];
-        else c = __ldg(reinterpret_cast<const int4 *>(conn) + __ldg(haloElems + u.haloFirst + (s - u.ownElemCount)));
-        const int n[4] = {c.x - 1, c.y - 1, c.z - 1, c.w - 1};
-        double x[4][3];
+    /* P1: one record per touched element; two elements per thread in flight so that the
+     * (L2-latency) coordinate gathers of one overlap the arithmetic of the other */
+    for (int s0 = tid; s0 < nSlots; s0 += 2 * THREADS) {
+        const int s1 = s0 + THREADS;
+        const bool two = s1 < nSlots;
+        int4 c0, c1;
+        c0 = (s0 < u.ownElemCount) ? connS[s0]
+                                   : __ldg(reinterpret_cast<const int4 *>(conn) + haloS[s0 - u.ownElemCount]);
+        c1 = c0;
+        if (two)
+            c1 = (s1 < u.ownElemCount) ? connS[s1]
+                                       : __ldg(reinterpret_cast<const int4 *>(conn) + haloS[s1 - u.ownElemCount]);
+        const int n0[4] = {c0.x - 1, c0.y - 1, c0.z - 1, c0.w - 1};
+        const int n1[4] = {c1.x - 1, c1.y - 1, c1.z - 1, c1.w - 1};
+        double x0[4][3], x1[4][3];
 #pragma unroll
         for (int a = 0; a < 4; a++)
 #pragma unroll
-            for (int k = 0; k < 3; k++) x[a][k] = __ldg(coord + (int64_t)n[a] * 3 + k);
+            for (int k = 0; k < 3; k++) {
+                x0[a][k] = __ldg(coord + (int64_t)n0[a] * 3 + k);
+                x1[a][k] = __ldg(coord + (int64_t)n1[a] * 3 + k);
+            }
         double rec[Op::NS];
-        Op::setup(x, c_params, rec);
+        Op::setup(x0, c_params, rec);
 #pragma unroll
-        for (int i = 0; i < Op::NS; i++) recs[s * RS + i] = rec[i];
+        for (int i = 0; i < Op::NS; i++) recs[s0 * RS + i] = rec[i];
+        if (two) {
+            Op::setup(x1, c_params, rec);
+#pragma unroll
+            for (int i = 0; i < Op::NS; i++) recs[s1 * RS + i] = rec[i];
+        }
     }
+    mbar_wait(&bar[1], 0);
     __syncthreads();   /* records complete; region A is free for staging from here on */
 
-    /* P2: tasks round-robin over warps */
+    /* P2: tasks round-robin over warps; a lane owns one CSR edge and sums its
+     * contributions in ascending element order (the order of the item rows) */
     double *myStage = stage + warp * 32 * DD;
     double *out = values + u.edgeFirst * DD;
     for (int t = warp; t < u.taskCount; t += NW) {
-        const dc_task_t task = tasks[u.taskFirst + t];
-        const uint16_t *it = items + u.itemFirst + task.itemRel + lane;
+        const dc_task_t task = taskS[t];
+        const uint16_t *it = itemS + task.itemRel + lane;
         double acc[DD];
 #pragma unroll
         for (int c = 0; c < DD; c++) acc[c] = 0.0;
-        uint32_t item = task.iters ? __ldg(it) : DC_ITEM_NULL;
-        for (int i = 0; i < task.iters; i++) {
-            const uint32_t cur = item;
-            if (i + 1 < task.iters) item = __ldg(it + (i + 1) * 32);
+        /* two contributions in flight per lane: the blocks are independent, only the
+         * final adds into acc are ordered (ascending element = item row order) */
+        int i = 0;
+        for (; i + 1 < task.iters; i += 2) {
+            const uint32_t cur0 = it[i * 32], cur1 = it[(i + 1) * 32];
+            double blk0[DD], blk1[DD];
+            if (cur0 != DC_ITEM_NULL) Op::block(recs + (cur0 >> 4) * RS, c_params, cur0 & 15u, blk0);
+            if (cur1 != DC_ITEM_NULL) Op::block(recs + (cur1 >> 4) * RS, c_params, cur1 & 15u, blk1);
+            if (cur0 != DC_ITEM_NULL) {
+#pragma unroll
+                for (int c = 0; c < DD; c++) acc[c] = __dadd_rn(acc[c], blk0[c]);
+            }
+            if (cur1 != DC_ITEM_NULL) {
+#pragma unroll
+                for (int c = 0; c < DD; c++) acc[c] = __dadd_rn(acc[c], blk1[c]);
+            }
+        }
+        if (i < task.iters) {
+            const uint32_t cur = it[i * 32];
             if (cur != DC_ITEM_NULL) {
                 double blk[DD];
-                Op::block(recs + (cur >> 4) * RS, (cur >> 2) & 3, cur & 3, blk);
+                Op::block(recs + (cur >> 4) * RS, c_params, cur & 15u, blk);
 #pragma unroll
                 for (int c = 0; c < DD; c++) acc[c] = __dadd_rn(acc[c], blk[c]);
             }
@@ -216,7 +282,7 @@ __global__ void __launch_bounds__(128) gather_lists(const int64_t *__restrict__ 
         const uint32_t it = __ldg(item + q);
         double rec[Op::NS], blk[DD];
         load_element<Op>(conn, coord, (int64_t)(it >> 4), rec);
-        Op::block(rec, (it >> 2) & 3, it & 3, blk);
+        Op::block(rec, c_params, it & 15u, blk);
 #pragma unroll
         for (int c = 0; c < DD; c++) acc[c] = __dadd_rn(acc[c], blk[c]);
     }
@@ -251,7 +317,7 @@ __global__ void __launch_bounds__(128) scatter_atomic(const int *__restrict__ co
             while (k < r1 && __ldg(col + k) != target) k++;
             if (k == r1) continue;
             double blk[DD];
-            Op::block(rec, a, b, blk);
+            Op::block(rec, c_params, (uint32_t)(4 * a + b), blk);
             double *dst = values + (int64_t)k * DD;
 #pragma unroll
             for (int q = 0; q < DD; q++) red_add_f64(dst + q, blk[q]);

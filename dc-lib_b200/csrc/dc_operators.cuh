@@ -5,10 +5,9 @@
  * and `+=`s it into nodeToNodeValue.  Host function pointers cannot run on the
  * GPU, so the callbacks are replaced by device operators with this contract:
  *
- *   setup(x[4][3], params)      once per element: whatever the operator wants to
- *                               keep for its 16 blocks (here the 4 basis-function
- *                               gradients and 1-2 scalars), NS doubles in total;
- *   block(slot, a, b, out[D*D]) the D x D block K_e[a][b] from that record.
+ *   setup(x[4][3], params, rec)        once per element: whatever the operator wants
+ *                                      to keep for its 16 blocks, NS doubles;
+ *   block(rec, params, 4*a+b, out[D*D]) the D x D block K_e[a][b] from that record.
  *
  * Every product / fma / sum is written with an explicit rounding intrinsic so
  * that nvcc cannot contract or reassociate: the sequence is the operator's
@@ -20,15 +19,12 @@
 
 namespace dcdev {
 
-/* record layout: g[a][k] at 3*a+k (a = 0..3), scalars from index 12 */
-#define DC_SLOT_G 12
-
 __device__ __forceinline__ double cross_comp(double p, double q, double r, double s)
 {
     return __fma_rn(p, q, -__dmul_rn(r, s));
 }
 
-/* Gradients of the P1 basis functions and |det|/6.  a,b,c = edges from node 0,
+/* Gradients of the P1 basis functions (g[3*a+k]) and |det|/6.  a,b,c = edges from node 0,
  * g1 = (b x c)/det, g2 = (c x a)/det, g3 = (a x b)/det, g0 = -((g1+g2)+g3). */
 __device__ __forceinline__ void tet_gradients(const double (&x)[4][3], double *g, double &vol)
 {
@@ -49,7 +45,7 @@ __device__ __forceinline__ void tet_gradients(const double (&x)[4][3], double *g
     n3[1] = cross_comp(a[2], b[0], a[0], b[2]);
     n3[2] = cross_comp(a[0], b[1], a[1], b[0]);
     double det = __fma_rn(a[2], n1[2], __fma_rn(a[1], n1[1], __dmul_rn(a[0], n1[0])));
-    double inv = __ddiv_rn(1.0, det);
+    double inv = __drcp_rn(det);          /* correctly rounded 1/det */
 #pragma unroll
     for (int k = 0; k < 3; k++) {
         double g1 = __dmul_rn(n1[k], inv), g2 = __dmul_rn(n2[k], inv), g3 = __dmul_rn(n3[k], inv);
@@ -61,61 +57,70 @@ __device__ __forceinline__ void tet_gradients(const double (&x)[4][3], double *g
     vol = __dmul_rn(fabs(det), 0.16666666666666666);
 }
 
-/* P1 Laplacian: K[a][b] = vol * (ga . gb), dot = fma(z,z, fma(y,y, x*x)). */
+/* P1 Laplacian: K[a][b] = vol * (ga . gb), dot = fma(z,z, fma(y,y, x*x)).
+ * The element matrix is symmetric bit for bit, so the record is its 10 distinct entries. */
 struct OpLaplacian {
     static constexpr int D = 1;
-    static constexpr int NS = DC_SLOT_G + 1;      /* gradients + vol */
+    static constexpr int NS = 10;
     static constexpr int NPARAM = 0;
+    __device__ __forceinline__ static void setup(const double (&x)[4][3], const double *, double *rec)
+    {
+        double g[12], vol;
+        tet_gradients(x, g, vol);
+        int q = 0;
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int b = a; b < 4; b++) {
+                double d = __fma_rn(g[3 * a + 2], g[3 * b + 2],
+                                    __fma_rn(g[3 * a + 1], g[3 * b + 1], __dmul_rn(g[3 * a], g[3 * b])));
+                rec[q++] = __dmul_rn(vol, d);
+            }
+    }
+    /* ab = 4*a+b */
+    template <typename R>
+    __device__ __forceinline__ static void block(R rec, const double *, uint32_t ab, double (&out)[1])
+    {
+        const uint32_t q = (uint32_t)(0x9863875265413210ULL >> (4 * ab)) & 15u;
+        out[0] = rec[q];
+    }
+};
+
+/* Isotropic linear elasticity, 3x3 blocks, volume folded symmetrically into the gradients:
+ * h_a = g_a * sqrt(vol); p[i][j] = ha_i*hb_j; dot = (p00+p11)+p22;
+ * K[a][b][i][j] = fma(mu, p[j][i], lambda*p[i][j]), diagonal: fma(mu, dot, that).
+ * params = {lambda, mu}.  The record is the 12 scaled gradient components. */
+struct OpElasticity {
+    static constexpr int D = 3;
+    static constexpr int NS = 12;
+    static constexpr int NPARAM = 2;
     __device__ __forceinline__ static void setup(const double (&x)[4][3], const double *, double *rec)
     {
         double vol;
         tet_gradients(x, rec, vol);
-        rec[DC_SLOT_G] = vol;
+        const double s = __dsqrt_rn(vol);
+#pragma unroll
+        for (int i = 0; i < 12; i++) rec[i] = __dmul_rn(rec[i], s);
     }
     template <typename R>
-    __device__ __forceinline__ static void block(R rec, int a, int b, double (&out)[1])
+    __device__ __forceinline__ static void block(R rec, const double *params, uint32_t ab, double (&out)[9])
     {
-        double ax = rec[3 * a], ay = rec[3 * a + 1], az = rec[3 * a + 2];
-        double bx = rec[3 * b], by = rec[3 * b + 1], bz = rec[3 * b + 2];
-        double d = __fma_rn(az, bz, __fma_rn(ay, by, __dmul_rn(ax, bx)));
-        out[0] = __dmul_rn(rec[DC_SLOT_G], d);
-    }
-};
-
-/* Isotropic linear elasticity, 3x3 blocks:
- * K[a][b][i][j] = lV*(ga_i gb_j) + mV*(ga_j gb_i) + delta_ij * mV*(ga . gb),
- * p[i][j] = ga_i*gb_j, dot = (p00+p11)+p22, lV = lambda*vol, mV = mu*vol,
- * entry = fma(mV, p[j][i], lV*p[i][j]), diagonal: fma(mV, dot, entry).
- * params = {lambda, mu}. */
-struct OpElasticity {
-    static constexpr int D = 3;
-    static constexpr int NS = DC_SLOT_G + 2;      /* gradients + lV + mV */
-    static constexpr int NPARAM = 2;
-    __device__ __forceinline__ static void setup(const double (&x)[4][3], const double *params, double *rec)
-    {
-        double vol;
-        tet_gradients(x, rec, vol);
-        rec[DC_SLOT_G] = __dmul_rn(params[0], vol);
-        rec[DC_SLOT_G + 1] = __dmul_rn(params[1], vol);
-    }
-    template <typename R>
-    __device__ __forceinline__ static void block(R rec, int a, int b, double (&out)[9])
-    {
-        double ga[3] = {rec[3 * a], rec[3 * a + 1], rec[3 * a + 2]};
-        double gb[3] = {rec[3 * b], rec[3 * b + 1], rec[3 * b + 2]};
-        double lV = rec[DC_SLOT_G], mV = rec[DC_SLOT_G + 1];
+        const uint32_t a = ab >> 2, b = ab & 3u;
+        const double ga[3] = {rec[3 * a], rec[3 * a + 1], rec[3 * a + 2]};
+        const double gb[3] = {rec[3 * b], rec[3 * b + 1], rec[3 * b + 2]};
+        const double lam = params[0], mu = params[1];
         double p[3][3];
 #pragma unroll
         for (int i = 0; i < 3; i++)
 #pragma unroll
             for (int j = 0; j < 3; j++) p[i][j] = __dmul_rn(ga[i], gb[j]);
-        double dot = __dadd_rn(__dadd_rn(p[0][0], p[1][1]), p[2][2]);
+        const double dot = __dadd_rn(__dadd_rn(p[0][0], p[1][1]), p[2][2]);
 #pragma unroll
         for (int i = 0; i < 3; i++)
 #pragma unroll
             for (int j = 0; j < 3; j++) {
-                double v = __fma_rn(mV, p[j][i], __dmul_rn(lV, p[i][j]));
-                if (i == j) v = __fma_rn(mV, dot, v);
+                double v = __fma_rn(mu, p[j][i], __dmul_rn(lam, p[i][j]));
+                if (i == j) v = __fma_rn(mu, dot, v);
                 out[i * 3 + j] = v;
             }
     }

@@ -34,7 +34,7 @@ typedef struct {
     int32_t ownElemFirst, ownElemCount;   /* slots [0, ownElemCount)                */
     int32_t haloCount;                    /* slots [ownElemCount, +haloCount)       */
     int32_t taskFirst, taskCount;
-    int32_t pad_;
+    int32_t itemCount;                    /* uint16 items of the unit (multiple of 32) */
 } dc_unit_t;                /* 64 bytes */
 
 typedef struct {
@@ -58,6 +58,9 @@ typedef struct {
 
 typedef struct dc_plan_s {
     int32_t  maxSlots;      /* largest slot count of any unit                      */
+    int32_t  maxHalo;       /* largest halo list (entries, padded to 4)            */
+    int32_t  maxTasks;      /* most tasks in one unit                              */
+    int32_t  maxItems;      /* most uint16 items in one unit                       */
     int64_t  nbUnits, nbTasks, nbItems, nbHalo;
     dc_unit_t *units;
     dc_task_t *tasks;

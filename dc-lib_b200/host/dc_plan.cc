@@ -343,6 +343,7 @@ extern "C" int dc_plan_build(dc_plan_t *plan, const int *conn, int nbElem, int n
             d.taskFirst = (int32_t)tTasks[tid].size();     /* thread-local, fixed up below */
             d.taskCount = (int32_t)out.tasks.size();
             d.itemFirst = (int64_t)tItems[tid].size();
+            d.itemCount = (int32_t)out.items.size();
             unitThread[(size_t)u] = tid;
             tTasks[tid].insert(tTasks[tid].end(), out.tasks.begin(), out.tasks.end());
             tItems[tid].insert(tItems[tid].end(), out.items.begin(), out.items.end());
@@ -368,18 +369,24 @@ extern "C" int dc_plan_build(dc_plan_t *plan, const int *conn, int nbElem, int n
         std::vector<uint16_t>().swap(tItems[t]);
     }
     int64_t haloTotal = 0, slotsTotal = 0;
-    int maxUsed = 0;
+    int maxUsed = 0, maxHalo = 0, maxTasks = 0, maxItems = 0;
     for (int64_t u = 0; u < nbUnits; u++) {
         dc_unit_t &d = units[(size_t)u];
         const int t = unitThread[(size_t)u];
         d.taskFirst += (int32_t)taskBase[t];
         d.itemFirst += itemBase[t];
-        d.haloFirst = haloTotal;
-        haloTotal += d.haloCount;
+        d.haloFirst = haloTotal;                       /* multiple of 4: bulk copies need 16-byte sources */
+        haloTotal += (d.haloCount + 3) & ~3;
         slotsTotal += d.ownElemCount + d.haloCount;
         maxUsed = std::max(maxUsed, d.ownElemCount + d.haloCount);
+        maxHalo = std::max(maxHalo, (d.haloCount + 3) & ~3);
+        maxTasks = std::max(maxTasks, d.taskCount);
+        maxItems = std::max(maxItems, d.itemCount);
     }
-    plan->haloElems = (int32_t *)malloc(sizeof(int32_t) * (size_t)(haloTotal ? haloTotal : 1));
+    plan->maxHalo = maxHalo;
+    plan->maxTasks = maxTasks;
+    plan->maxItems = maxItems;
+    plan->haloElems = (int32_t *)calloc((size_t)(haloTotal ? haloTotal : 1), sizeof(int32_t));
     for (int64_t u = 0; u < nbUnits; u++) {
         const std::vector<int> &h = sel.seeds[(size_t)u].halo;
         if (!h.empty()) memcpy(plan->haloElems + units[(size_t)u].haloFirst, h.data(), sizeof(int32_t) * h.size());

@@ -75,6 +75,9 @@ int  dc_cuda_renumber(int *d_tab, const int *d_perm, int64_t size, int isFortran
 int  dc_cuda_reset_edges(double *d_values, int64_t firstEdge, int64_t lastEdge, int perEdge,
                          void *stream);
 
+/* Tuning knobs: "unit_threads" = CTA size of the unit kernel (128 or 256, default 256). */
+int  dc_cuda_set_option(dc_cuda_ctx *ctx, const char *name, int value);
+
 /* Number of kernels this context has launched (for honest launch accounting). */
 int64_t dc_cuda_launch_count(const dc_cuda_ctx *ctx);
 int  dc_cuda_sync(void *stream);

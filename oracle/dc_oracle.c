@@ -84,24 +84,27 @@ void dco_laplacian_ke(const double x[4][3], double ke[16])
         }
 }
 
-/* ke[a*4+b][i*3+j] = lV*(ga_i gb_j) + mV*(ga_j gb_i) + delta_ij * mV*(ga . gb)
- * with p[i][j] = ga_i*gb_j, dot = (p00+p11)+p22, lV = lambda*vol, mV = mu*vol,
- * entry = fma(mV, p[j][i], lV*p[i][j]) and, on the diagonal, fma(mV, dot, entry). */
+/* Isotropic elasticity with the volume folded symmetrically into the gradients:
+ * h_a = g_a * sqrt(vol);  p[i][j] = ha_i*hb_j;  dot = (p00+p11)+p22;
+ * ke[a*4+b][i*3+j] = fma(mu, p[j][i], lambda*p[i][j]), and on the diagonal
+ * fma(mu, dot, that).  (= vol * (lambda ga_i gb_j + mu ga_j gb_i + delta_ij mu ga.gb)) */
 void dco_elasticity_ke(const double x[4][3], double lambda, double mu, double ke[16][9])
 {
-    double g[4][3], vol;
+    double g[4][3], h[4][3], vol;
     dco_tet_gradients(x, g, &vol);
-    double lV = lambda * vol, mV = mu * vol;
+    double s = sqrt(vol);
+    for (int a = 0; a < 4; a++)
+        for (int k = 0; k < 3; k++) h[a][k] = g[a][k] * s;
     for (int a = 0; a < 4; a++)
         for (int b = 0; b < 4; b++) {
             double p[3][3];
             for (int i = 0; i < 3; i++)
-                for (int j = 0; j < 3; j++) p[i][j] = g[a][i] * g[b][j];
+                for (int j = 0; j < 3; j++) p[i][j] = h[a][i] * h[b][j];
             double dot = (p[0][0] + p[1][1]) + p[2][2];
             for (int i = 0; i < 3; i++)
                 for (int j = 0; j < 3; j++) {
-                    double v = fma(mV, p[j][i], lV * p[i][j]);
-                    if (i == j) v = fma(mV, dot, v);
+                    double v = fma(mu, p[j][i], lambda * p[i][j]);
+                    if (i == j) v = fma(mu, dot, v);
                     ke[a * 4 + b][i * 3 + j] = v;
                 }
         }
