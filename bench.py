@@ -22,12 +22,14 @@ sys.path.insert(0, ROOT)
 
 LAMBDA, MU = 0.5769230769230769, 0.3846153846153846      # E = 1, nu = 0.3
 WORKLOADS = {
-    # name: (cube size, operatorDim, colouring vector length)
-    "target350": (350, 3, 0),     # north-star target: >= 256M tets, elasticity
-    "c3": (256, 1, 0),            # BASELINE config 3: ~100M tets, Laplacian
-    "c2": (40, 3, 4),             # BASELINE config 2: 40^3, elasticity, D&C + colouring
-    "m100": (100, 3, 0),          # 6M tets, elasticity (METIS tree)
-    "m64": (64, 3, 0),
+    # name: (cube size, operatorDim, colouring vector length, tree builder)
+    "target350": (350, 3, 0, "geometric"),   # north-star target: >= 256M tets, elasticity
+    "c3": (256, 1, 0, "geometric"),          # BASELINE config 3: ~100M tets, Laplacian
+    "e256": (256, 3, 0, "geometric"),        # 100M tets, elasticity
+    "e160": (160, 3, 0, "geometric"),        # 24.6M tets, elasticity
+    "c2": (40, 3, 4, "metis"),               # BASELINE config 2: 40^3, elasticity, D&C + colouring
+    "m100": (100, 3, 0, "metis"),            # 6M tets, elasticity (METIS tree, as the reference builds it)
+    "m64": (64, 3, 0, "metis"),
 }
 
 
@@ -62,7 +64,7 @@ class ClockSampler(threading.Thread):
                 for bit, name in names.items():
                     if r & bit:
                         self.reasons.add(name)
-                time.sleep(0.02)
+                time.sleep(0.005)
         except Exception as e:          # NVML missing: report that instead of inventing numbers
             self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
 
@@ -71,21 +73,26 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-def build_workload(dc, n, vec, rank=0):
-    """Appendix-A driver with the product library: mesh -> tree -> permute/renumber -> CSR -> finalize."""
+def build_workload(dc, n, vec, builder, rank=0):
+    """Appendix-A driver with the product library: mesh -> tree -> permute/renumber -> CSR -> finalize.
+    builder "metis" = DC_create_tree as the reference builds it; "geometric" = the same recursion
+    with coordinate bisection in place of METIS (DC_create_tree_geometric) for 10^8-element meshes."""
     t0 = time.time()
-    conn, N = dc.kuhn_cube(n)
-    coord = dc.jitter_coords(n, seed=12345 + rank)
+    conn, coord, N = dc.kuhn_cube_fast(n, seed=12345 + rank)
     E = conn.shape[0]
     dc.DC_set_vec_size(vec)
-    dc.DC_create_tree(conn, E, 4, N)
+    if builder == "geometric":
+        dc.DC_create_tree_geometric(conn, E, 4, N, coord)
+    else:
+        dc.DC_create_tree(conn, E, 4, N)
+    t1 = time.time()
     dc.DC_permute_double_2d_array(coord, N, 3)
     dc.DC_renumber_int_array(conn.reshape(-1), 4 * E)
-    row, col = dc.build_csr(conn, N)
+    row, col = dc.build_csr_fast(conn, N)
     dc.DC_finalize_tree(row, conn, E, 4)
     rec = dc.flatten_tree()
     return dict(conn=conn, coord=coord, row=row, col=col, E=E, N=N, nnz=int(row[-1]), rec=rec, n=n,
-                setup_s=time.time() - t0)
+                tree_s=t1 - t0, setup_s=time.time() - t0)
 
 
 def cpu_reference(dim, steps, warmup):
@@ -128,13 +135,14 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
-    n, dim, vec = WORKLOADS[args.workload]
+    n, dim, vec, builder = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     config = {"workload": f"{args.workload}: jittered Kuhn cube {n}^3 ({6 * n ** 3} tets) per GPU, "
                           f"operatorDim {dim} ({'isotropic elasticity' if dim == 3 else 'P1 Laplacian'}), "
-                          f"{'D&C + colouring VEC_SIZE ' + str(vec) if vec else 'pure D&C'} tree, "
+                          f"{'D&C + colouring VEC_SIZE ' + str(vec) if vec else 'pure D&C'} tree "
+                          f"({'METIS node partitions' if builder == 'metis' else 'coordinate-bisection node partitions'}), "
                           "reset + assembly per step",
               "mode": "deterministic", "unit_slots": args.slots,
               "l2": "value arrays larger than L2 (no flush needed)" if 6 * n ** 3 * 2.5 * dim * dim * 8 > 2.5e8
@@ -163,7 +171,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    w = build_workload(dc, n, vec, rank)
+    w = build_workload(dc, n, vec, builder, rank)
     E, N, nnz = w["E"], w["N"], w["nnz"]
     t0 = time.time()
     plan = dc.HostPlan(w["conn"], N, w["row"], w["col"], 0, w["rec"], args.slots)
@@ -171,6 +179,9 @@ def main():
     ctx = dc.Context(local)
     ctx.set_mesh(w["conn"], w["coord"], w["row"], w["col"], 0)
     ctx.upload_plan(plan)
+    st = plan.stats()
+    del plan
+    w["conn"] = w["row"] = w["col"] = w["rec"] = None          # host copies no longer needed
     op, prm = (dc.OP_ELASTICITY, [LAMBDA, MU]) if dim == 3 else (dc.OP_LAPLACIAN, None)
     vals = torch.empty(nnz * dim * dim, dtype=torch.float64, device="cuda")
     stream = torch.cuda.current_stream().cuda_stream
@@ -200,9 +211,9 @@ def main():
 
     # ---- end to end through the host-array entry point ---------------------------------
     h_coord = torch.from_numpy(w["coord"]).pin_memory()
-    h_vals = torch.empty(nnz * dim * dim, dtype=torch.float64).pin_memory()
-    e2e_steps = max(2, min(args.steps, 5))
-    for _ in range(2):
+    h_vals = torch.empty(nnz * dim * dim, dtype=torch.float64, pin_memory=True)
+    e2e_steps = max(2, min(args.steps, 5 if nnz * dim * dim < 5e8 else 2))
+    for _ in range(1):
         ctx.update_coords(h_coord.numpy(), stream)
         ctx.assemble_to_host(op, prm, dc.MODE_DETERMINISTIC, h_vals.numpy(), stream)
     barrier()
@@ -225,7 +236,6 @@ def main():
     peak, peak_src = measured_peak()
     b_alg = 16 * E + 24 * N + 4 * (N + 1) + 4 * nnz + 8 * dim * dim * nnz
     achieved = b_alg / (ms * 1e-3) / 1e9
-    st = plan.stats()
     line = {
         "metric": "assembled elements/s (fp64, CSR scatter-add)", "value": world * E / (ms * 1e-3), "unit": "elements/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
@@ -237,7 +247,7 @@ def main():
                 "h2d_bytes_per_step": 24 * N, "d2h_bytes_per_step": 8 * dim * dim * nnz, "steps": e2e_steps,
                 "checksum": checksum},
         "gpu_launches": launches, "clocks": sampler.summary(),
-        "setup": {"tree_and_csr_s": w["setup_s"], "plan_s": plan_s, "units": st["units"],
+        "setup": {"tree_s": w["tree_s"], "tree_and_csr_s": w["setup_s"], "plan_s": plan_s, "units": st["units"],
                   "element_setups_per_element": st["slots_total"] / E,
                   "item_padding_efficiency": st["items_useful"] / max(st["items"], 1), "host_cores": os.cpu_count()},
     }

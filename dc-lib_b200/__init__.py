@@ -102,10 +102,15 @@ def _declare(L):
     L.dc_plan_free.restype = None
     L.dc_contrib_free.argtypes = [POINTER(ContribList)]
     L.dc_contrib_free.restype = None
+    L.dcx_kuhn_cube.argtypes = [c_int, vp, vp, c_double, c_int]
+    L.dcx_kuhn_cube.restype = None
+    L.dcx_build_csr.argtypes = [vp, c_int, c_int, vp, vp, c_int]
+    L.dcx_build_csr.restype = c_int64
     L.dc_flatten_tree.argtypes = [vp, c_int64]
     L.dc_flatten_tree.restype = c_int64
     L.dc_get_time_.restype = c_double
     L.dc_create_tree_.argtypes = [vp, ip, ip, ip]
+    L.dc_create_tree_geometric_.argtypes = [vp, ip, ip, ip, vp, ip]
     L.dc_finalize_tree_.argtypes = [vp, vp, vp, vp, vp, vp, ip, ip, ip, ip, ip]
     L.dc_store_tree_.argtypes = [c_char_p, ip, ip, ip, ip]
     L.dc_read_tree_.argtypes = [c_char_p, ip, ip, ip, ip]
@@ -158,6 +163,14 @@ def DC_set_num_threads(v):
 def DC_create_tree(elemToNode, nbElem, dimElem, nbNodes):
     assert elemToNode.dtype == np.int32 and elemToNode.flags.c_contiguous
     lib().dc_create_tree_(_p(elemToNode), _i(nbElem), _i(dimElem), _i(nbNodes))
+
+
+def DC_create_tree_geometric(elemToNode, nbElem, dimElem, nbNodes, coord):
+    """DC_create_tree with recursive coordinate bisection instead of METIS (coord in the
+    ORIGINAL node numbering)."""
+    assert elemToNode.dtype == np.int32 and elemToNode.flags.c_contiguous
+    assert coord.dtype == np.float64 and coord.flags.c_contiguous
+    lib().dc_create_tree_geometric_(_p(elemToNode), _i(nbElem), _i(dimElem), _i(nbNodes), _p(coord), _i(coord.shape[1]))
 
 
 def DC_finalize_tree(nodeToNodeRow, elemToNode, nbElem, dimElem):
@@ -347,6 +360,26 @@ def reset_edges(d_values, firstEdge, lastEdge, perEdge, stream=None):
     rc = lib().dc_cuda_reset_edges(_p(d_values), firstEdge, lastEdge, perEdge, stream)
     if rc:
         raise RuntimeError(lib().dc_cuda_last_error().decode())
+
+
+def kuhn_cube_fast(n, amplitude=0.3, seed=12345):
+    """C++/OpenMP version of kuhn_cube + jitter_coords (identical arrays)."""
+    E, N = 6 * n ** 3, (n + 1) ** 3
+    conn = np.empty((E, 4), dtype=np.int32)
+    coord = np.empty((N, 3), dtype=np.float64)
+    lib().dcx_kuhn_cube(n, _p(conn), _p(coord), amplitude, seed)
+    return conn, coord, N
+
+
+def build_csr_fast(conn, nbNodes, colBase=0):
+    """C++/OpenMP version of build_csr (identical arrays)."""
+    row = np.empty(nbNodes + 1, dtype=np.int32)
+    nnz = lib().dcx_build_csr(_p(conn), conn.shape[0], nbNodes, _p(row), None, colBase)
+    if nnz < 0:
+        raise RuntimeError("CSR pattern exceeds 2^31-1 edges")
+    col = np.empty(nnz, dtype=np.int32)
+    lib().dcx_build_csr(_p(conn), conn.shape[0], nbNodes, _p(row), _p(col), colBase)
+    return row, col
 
 
 from .meshgen import kuhn_cube, jitter_coords, build_csr, hub_collapse  # noqa: E402,F401

@@ -69,6 +69,12 @@ void dc_create_tree_ (int *elemToNode, int *nbElem, int *dimElem, int *nbNodes)
     DC_create_tree(elemToNode, *nbElem, *dimElem, *nbNodes);
 }
 
+void dc_create_tree_geometric_ (int *elemToNode, int *nbElem, int *dimElem, int *nbNodes, double *coord,
+                               int *dimNode)
+{
+    DC_create_tree_geometric(elemToNode, *nbElem, *dimElem, *nbNodes, coord, *dimNode);
+}
+
 void dc_set_vec_size_ (int *vecSize) { DC_set_vec_size(*vecSize); }
 void dc_set_max_elem_per_part_ (int *maxElem) { DC_set_max_elem_per_part(*maxElem); }
 void dc_set_num_threads_ (int *nbThreads) { DC_set_num_threads(*nbThreads); }

@@ -28,12 +28,25 @@ void build_node_to_elem(Mesh &m)
 {
     const int64_t nc = (int64_t)m.nbElem * 4;
     m.n2ePtr.assign((size_t)m.nbNodes + 1, 0);
-    for (int64_t k = 0; k < nc; k++) m.n2ePtr[(size_t)m.conn[k]]++;   /* node n (1-based) -> slot n */
+    #pragma omp parallel for schedule(static) if (nc > (1 << 18))
+    for (int64_t k = 0; k < nc; k++) {
+        #pragma omp atomic
+        m.n2ePtr[(size_t)m.conn[k]]++;                 /* node n (1-based) -> slot n */
+    }
     for (int n = 0; n < m.nbNodes; n++) m.n2ePtr[(size_t)n + 1] += m.n2ePtr[n];
     m.n2eVal.resize((size_t)nc);
     std::vector<int64_t> fill(m.n2ePtr.begin(), m.n2ePtr.end() - 1);
+    #pragma omp parallel for schedule(static) if (nc > (1 << 18))
     for (int e = 0; e < m.nbElem; e++)
-        for (int j = 0; j < 4; j++) m.n2eVal[(size_t)fill[m.conn[(int64_t)e * 4 + j] - 1]++] = e;
+        for (int j = 0; j < 4; j++) {
+            int64_t slot;
+            #pragma omp atomic capture
+            slot = fill[(size_t)m.conn[(int64_t)e * 4 + j] - 1]++;
+            m.n2eVal[(size_t)slot] = e;
+        }
+    #pragma omp parallel for schedule(dynamic, 4096) if (nc > (1 << 18))
+    for (int n = 0; n < m.nbNodes; n++)
+        std::sort(m.n2eVal.begin() + m.n2ePtr[n], m.n2eVal.begin() + m.n2ePtr[(size_t)n + 1]);
 }
 
 struct UnitSeed {
@@ -54,18 +67,42 @@ void collect_halo(const Mesh &m, int nodeFirst, int nodeCount, int ownFirst, int
     halo.erase(std::unique(halo.begin(), halo.end()), halo.end());
 }
 
+struct TreeIdx {
+    int firstElem, lastSep, firstNode, lastNode;
+    bool isSep, isLeaf;
+    int64_t left, right;
+};
+
+/* pre-order records (node, left, right, sep) -> indexed nodes; separator subtrees are skipped */
+int64_t index_tree(const int *rec, int64_t nbRec, int64_t &cursor, std::vector<TreeIdx> &out, bool keep)
+{
+    if (cursor >= nbRec) return -1;
+    const int *r = rec + 8 * cursor++;
+    int64_t me = -1;
+    if (keep) {
+        me = (int64_t)out.size();
+        out.push_back(TreeIdx{r[0], r[2], r[3], r[4], r[5] != 0, r[6] != 0, -1, -1});
+    }
+    if (r[6]) return me;
+    const bool hasSep = r[7] != 0, descend = keep && !r[5];
+    int64_t l = index_tree(rec, nbRec, cursor, out, descend);
+    int64_t rr = index_tree(rec, nbRec, cursor, out, descend);
+    if (hasSep) index_tree(rec, nbRec, cursor, out, false);
+    if (keep) { out[(size_t)me].left = l; out[(size_t)me].right = rr; }
+    return me;
+}
+
 struct Selector {
     const Mesh &m;
-    const int *rec;
-    int64_t nbRec, cursor = 0;
     int maxSlots;
-    std::vector<UnitSeed> seeds;
-    std::vector<int> bigRows;
-    std::vector<int> scratch;
+    std::vector<TreeIdx> tree;
+    std::vector<std::vector<UnitSeed>> seedsT;
+    std::vector<std::vector<int>> bigT;
 
     /* rows [nodeFirst, nodeFirst+nodeCount) without a usable subtree: cut greedily */
     void split_rows(int nodeFirst, int nodeCount)
     {
+        const int tid = omp_get_thread_num();
         int start = nodeFirst, end = nodeFirst + nodeCount;
         while (start < end) {
             int stop = start;
@@ -81,60 +118,43 @@ struct Selector {
                 stop++;
             }
             if (stop == start) {           /* a single row exceeds the slot budget */
-                bigRows.push_back(start);
+                bigT[tid].push_back(start);
                 start++;
                 continue;
             }
             UnitSeed s{start, stop - start, 0, 0, {}};
             s.halo.swap(acc);
-            seeds.push_back(std::move(s));
+            seedsT[tid].push_back(std::move(s));
             start = stop;
         }
     }
 
-    /* consume one subtree from the pre-order record stream without emitting */
-    void skip()
+    /* take the subtree as one unit if it fits the slot budget, else descend */
+    void select(int64_t idx)
     {
-        const int *r = rec + 8 * cursor++;
-        if (r[6]) return;
-        skip();
-        skip();
-        if (r[7]) skip();
-    }
-
-    void select()
-    {
-        const int *r = rec + 8 * cursor++;
-        const int firstElem = r[0], lastSep = r[2], firstNode = r[3], lastNode = r[4];
-        const bool isSep = r[5], isLeaf = r[6], hasSep = r[7];
-        const int own = lastSep - firstElem + 1, nodes = lastNode - firstNode + 1;
-        if (isSep) {            /* separator subtrees own no rows: they appear as halo */
-            --cursor;
-            skip();
-            return;
-        }
-        bool taken = false;
+        if (idx < 0) return;
+        const TreeIdx t = tree[(size_t)idx];
+        if (t.isSep) return;               /* separator subtrees own no rows: they appear as halo */
+        const int own = t.lastSep - t.firstElem + 1, nodes = t.lastNode - t.firstNode + 1;
         if (own <= maxSlots && nodes > 0) {
-            collect_halo(m, firstNode, nodes, firstElem, own, scratch);
-            if (own + (int)scratch.size() <= maxSlots) {
-                UnitSeed s{firstNode, nodes, firstElem, own, {}};
-                s.halo = scratch;
-                seeds.push_back(std::move(s));
-                taken = true;
+            std::vector<int> halo;
+            collect_halo(m, t.firstNode, nodes, t.firstElem, own, halo);
+            if (own + (int)halo.size() <= maxSlots) {
+                UnitSeed s{t.firstNode, nodes, t.firstElem, own, {}};
+                s.halo.swap(halo);
+                seedsT[omp_get_thread_num()].push_back(std::move(s));
+                return;
             }
         }
-        if (taken) {
-            --cursor;
-            skip();
+        if (t.isLeaf) {
+            if (nodes > 0) split_rows(t.firstNode, nodes);
             return;
         }
-        if (isLeaf) {
-            if (nodes > 0) split_rows(firstNode, nodes);
-            return;
-        }
-        select();               /* left  */
-        select();               /* right */
-        if (hasSep) skip();
+        #pragma omp task default(shared) if (own > 20000)
+        select(t.left);
+        #pragma omp task default(shared) if (own > 20000)
+        select(t.right);
+        #pragma omp taskwait
     }
 };
 
@@ -158,12 +178,16 @@ void build_unit(const Mesh &m, const UnitSeed &s, int32_t *diagRel, UnitOut &out
     const int edgeCount = m.row[s.nodeFirst + s.nodeCount] - (int)edgeFirst;
     if ((int)perEdge.size() < edgeCount) perEdge.resize((size_t)edgeCount);
     for (int k = 0; k < edgeCount; k++) perEdge[k].clear();
+    std::vector<char> isDiag((size_t)edgeCount, 0);
 
     for (int n = s.nodeFirst; n < s.nodeFirst + s.nodeCount; n++) {
         const int r0 = m.row[n], r1 = m.row[n + 1];
         diagRel[n] = -1;
         for (int k = r0; k < r1; k++)
-            if (m.col[k] - m.colBase == n) diagRel[n] = (int)(k - edgeFirst);
+            if (m.col[k] - m.colBase == n) {
+                diagRel[n] = (int)(k - edgeFirst);
+                isDiag[(size_t)(k - edgeFirst)] = 1;
+            }
         for (int64_t q = m.n2ePtr[n]; q < m.n2ePtr[(size_t)n + 1]; q++) {
             const int e = m.n2eVal[(size_t)q];
             const int *c = m.conn + (int64_t)e * 4;
@@ -189,11 +213,8 @@ void build_unit(const Mesh &m, const UnitSeed &s, int32_t *diagRel, UnitOut &out
         t.itemRel = (uint32_t)out.items.size();
         size_t iters = 0;
         for (int l = 0; l < 32 && base + l < edgeCount; l++) iters = std::max(iters, perEdge[(size_t)(base + l)].size());
-        /* which lanes are diagonals? */
-        for (int n = s.nodeFirst; n < s.nodeFirst + s.nodeCount; n++) {
-            int d = diagRel[n];
-            if (d >= base && d < base + 32) t.mask |= 1u << (d - base);
-        }
+        for (int l = 0; l < 32 && base + l < edgeCount; l++)
+            if (isDiag[(size_t)(base + l)]) t.mask |= 1u << l;
         iters = 0;
         for (int l = 0; l < 32 && base + l < edgeCount; l++)
             if (!((t.mask >> l) & 1u)) iters = std::max(iters, perEdge[(size_t)(base + l)].size());
@@ -291,28 +312,53 @@ extern "C" int dc_plan_build(dc_plan_t *plan, const int *conn, int nbElem, int n
                              int64_t nbTreeRec, int maxSlots, int nbThreads)
 {
     memset(plan, 0, sizeof *plan);
+    const bool verbose = getenv("DC_PLAN_VERBOSE") != nullptr;
+    double t0 = omp_get_wtime();
+    auto lap = [&](const char *what) {
+        if (verbose) { double t1 = omp_get_wtime(); fprintf(stderr, "[dc_plan] %-12s %.2fs\n", what, t1 - t0); t0 = t1; }
+    };
     if (maxSlots < 16 || maxSlots > DC_SLOT_LIMIT) return -1;
     if (nbElem >= (1 << 28)) { /* fallback items hold the element in 28 bits */ }
     Mesh m{conn, nbElem, nbNodes, row, col, colBase, {}, {}};
     build_node_to_elem(m);
 
-    Selector sel{m, treeRec, nbTreeRec, 0, maxSlots, {}, {}, {}};
-    if (treeRec && nbTreeRec > 0) sel.select();
-    else sel.split_rows(0, nbNodes);          /* no tree: plain row blocks */
+    lap("node->elem");
+    const int nt = nbThreads > 0 ? nbThreads : omp_get_max_threads();
+    Selector sel{m, maxSlots, {}, {}, {}};
+    sel.seedsT.resize((size_t)nt);
+    sel.bigT.resize((size_t)nt);
+    if (treeRec && nbTreeRec > 0) {
+        int64_t cursor = 0;
+        index_tree(treeRec, nbTreeRec, cursor, sel.tree, true);
+        #pragma omp parallel num_threads(nt)
+        #pragma omp single
+        sel.select(0);
+    } else {
+        sel.split_rows(0, nbNodes);          /* no tree: plain row blocks */
+    }
+    lap("select");
+    std::vector<UnitSeed> seeds;
+    std::vector<int> bigRows;
+    for (int t = 0; t < nt; t++) {
+        for (UnitSeed &u : sel.seedsT[(size_t)t]) seeds.push_back(std::move(u));
+        bigRows.insert(bigRows.end(), sel.bigT[(size_t)t].begin(), sel.bigT[(size_t)t].end());
+    }
+    std::sort(seeds.begin(), seeds.end(), [](const UnitSeed &a, const UnitSeed &b) { return a.nodeFirst < b.nodeFirst; });
+    std::sort(bigRows.begin(), bigRows.end());
 
     /* every row must belong to exactly one unit or to the fallback list */
     {
         std::vector<char> covered((size_t)nbNodes, 0);
-        for (const UnitSeed &s : sel.seeds)
+        for (const UnitSeed &s : seeds)
             for (int n = s.nodeFirst; n < s.nodeFirst + s.nodeCount; n++) covered[n]++;
-        for (int n : sel.bigRows) covered[n]++;
+        for (int n : bigRows) covered[n]++;
         for (int n = 0; n < nbNodes; n++) if (covered[n] != 1) return -3;
     }
 
-    const int64_t nbUnits = (int64_t)sel.seeds.size();
+    lap("merge+check");
+    const int64_t nbUnits = (int64_t)seeds.size();
     std::vector<dc_unit_t> units((size_t)nbUnits);
     std::vector<int32_t> diagRel((size_t)nbNodes, -1);
-    const int nt = nbThreads > 0 ? nbThreads : omp_get_max_threads();
     std::vector<std::vector<dc_task_t>> tTasks((size_t)nt);
     std::vector<std::vector<uint16_t>> tItems((size_t)nt);
     std::vector<int> unitThread((size_t)nbUnits);
@@ -326,7 +372,7 @@ extern "C" int dc_plan_build(dc_plan_t *plan, const int *conn, int nbElem, int n
         std::vector<std::vector<uint16_t>> perEdge;
         #pragma omp for schedule(dynamic, 64)
         for (int64_t u = 0; u < nbUnits; u++) {
-            const UnitSeed &s = sel.seeds[(size_t)u];
+            const UnitSeed &s = seeds[(size_t)u];
             out.tasks.clear();
             out.items.clear();
             out.useful = 0;
@@ -351,6 +397,7 @@ extern "C" int dc_plan_build(dc_plan_t *plan, const int *conn, int nbElem, int n
         }
     }
     if (error) return -2;
+    lap("units");
 
     std::vector<int64_t> taskBase((size_t)nt + 1, 0), itemBase((size_t)nt + 1, 0);
     for (int t = 0; t < nt; t++) {
@@ -388,9 +435,10 @@ extern "C" int dc_plan_build(dc_plan_t *plan, const int *conn, int nbElem, int n
     plan->maxItems = maxItems;
     plan->haloElems = (int32_t *)calloc((size_t)(haloTotal ? haloTotal : 1), sizeof(int32_t));
     for (int64_t u = 0; u < nbUnits; u++) {
-        const std::vector<int> &h = sel.seeds[(size_t)u].halo;
+        const std::vector<int> &h = seeds[(size_t)u].halo;
         if (!h.empty()) memcpy(plan->haloElems + units[(size_t)u].haloFirst, h.data(), sizeof(int32_t) * h.size());
     }
+    lap("concat");
     plan->nbHalo = haloTotal;
     plan->nbUnits = nbUnits;
     plan->units = dup(units);
@@ -398,9 +446,9 @@ extern "C" int dc_plan_build(dc_plan_t *plan, const int *conn, int nbElem, int n
     plan->maxSlots = maxUsed;
     plan->nbSlotsTotal = slotsTotal;
     plan->nbItemsUseful = useful;
-    if (!sel.bigRows.empty()) {
+    if (!bigRows.empty()) {
         int rc = dc_contrib_build(&plan->big, conn, nbElem, nbNodes, row, col, colBase,
-                                  sel.bigRows.data(), (int64_t)sel.bigRows.size());
+                                  bigRows.data(), (int64_t)bigRows.size());
         if (rc) return rc;
     }
     return 0;

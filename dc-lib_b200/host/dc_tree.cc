@@ -20,6 +20,8 @@
 #include <cstdio>
 #include <vector>
 #include <unordered_map>
+#include <algorithm>
+#include <omp.h>
 #include "dc_internal.h"
 
 tree_t *treeHead = nullptr;
@@ -119,11 +121,94 @@ static void metis_recursive(std::vector<int> &part, std::vector<int64_t> &xadj,
     for (int i = 0; i < nbNodes; i++) part[i] = (int)p[i];
 }
 
+/* Recursive coordinate bisection into nbPart parts, numbered so that the parts of the
+ * left half of every bisection are [first, first + (last-first)/2] -- the same midpoint
+ * rule tree_creation uses to split a part range, hence the same shape of tree that a
+ * recursive-bisection METIS partition gives.  Used where METIS is too slow (10^8 elements);
+ * not part of the reference. */
+struct Rcb {
+    const double *coord;
+    int dimNode;
+    const int *ids;      /* local node -> row of coord (nullptr: identity) */
+    int *part;
+
+    inline double key(int local, int axis) const
+    {
+        return coord[(int64_t)(ids ? ids[local] : local) * dimNode + axis];
+    }
+    void split(int *idx, int64_t n, int firstPart, int lastPart)
+    {
+        if (firstPart == lastPart || n <= 0) {
+            for (int64_t i = 0; i < n; i++) part[idx[i]] = firstPart;
+            return;
+        }
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+        for (int64_t i = 0; i < n; i++)
+            for (int a = 0; a < dimNode && a < 3; a++) {
+                double v = key(idx[i], a);
+                lo[a] = v < lo[a] ? v : lo[a];
+                hi[a] = v > hi[a] ? v : hi[a];
+            }
+        int axis = 0;
+        for (int a = 1; a < dimNode && a < 3; a++)
+            if (hi[a] - lo[a] > hi[axis] - lo[axis]) axis = a;
+        const int pivot = firstPart + (lastPart - firstPart) / 2;
+        const int64_t nbParts = lastPart - firstPart + 1, leftParts = pivot - firstPart + 1;
+        int64_t nLeft = (n * leftParts + nbParts / 2) / nbParts;
+        if (nLeft < 0) nLeft = 0;
+        if (nLeft > n) nLeft = n;
+        if (nLeft > 0 && nLeft < n)
+            std::nth_element(idx, idx + nLeft, idx + n, [&](int p, int q) {
+                double kp = key(p, axis), kq = key(q, axis);
+                return kp < kq || (kp == kq && p < q);
+            });
+        #pragma omp task default(shared) if (n > 50000)
+        split(idx, nLeft, firstPart, pivot);
+        #pragma omp task default(shared) if (n > 50000)
+        split(idx + nLeft, n - nLeft, pivot + 1, lastPart);
+        #pragma omp taskwait
+    }
+};
+
+/* tab[perm[i]] <- tab[i] (rows of dim ints) from inside a task region */
+static void task_scatter_rows(int *tab, const int *perm, int n, int dim)
+{
+    std::vector<int> src(tab, tab + (int64_t)n * dim);
+    const int chunk = 1 << 16, nbChunks = (n + chunk - 1) / chunk;
+    #pragma omp taskloop default(shared) grainsize(1) if (nbChunks > 4)
+    for (int c = 0; c < nbChunks; c++) {
+        const int e0 = c * chunk, e1 = std::min(n, e0 + chunk);
+        for (int e = e0; e < e1; e++)
+            for (int j = 0; j < dim; j++) tab[(int64_t)perm[e] * dim + j] = src[(size_t)((int64_t)e * dim + j)];
+    }
+}
+
 struct TreeBuilder {
     int *conn;        /* 0-based connectivity, rows follow the current element order */
     int *posToOrig;   /* original element index of the row at each position */
     int dimElem;
     int maxElem;
+    const double *coord = nullptr;   /* node coordinates (original numbering): geometric mode */
+    int dimNode = 3;
+
+    /* node partition of a (sub)mesh: METIS on the nodal graph (reference behaviour) or
+     * coordinate bisection when coordinates were supplied */
+    void partition_nodes(std::vector<int> &part, const int *localConn, int64_t nbElem, int nbLocalNodes,
+                         int nbPart, const int *localToGlobal)
+    {
+        if (coord) {
+            part.assign((size_t)nbLocalNodes, 0);
+            std::vector<int> idx((size_t)nbLocalNodes);
+            for (int i = 0; i < nbLocalNodes; i++) idx[i] = i;
+            Rcb r{coord, dimNode, localToGlobal, part.data()};
+            r.split(idx.data(), nbLocalNodes, 0, nbPart - 1);
+            return;
+        }
+        std::vector<int64_t> xadj, adjncy;
+        build_nodal_graph(xadj, adjncy, localConn, nbElem, dimElem, nbLocalNodes);
+        #pragma omp critical(dc_metis)
+        metis_recursive(part, xadj, adjncy, nbLocalNodes, nbPart);
+    }
 
     void sep_partitioning(tree_t *&tree, int firstSepElem, int lastSepElem, int firstNode,
                           int lastNode);
@@ -145,6 +230,7 @@ void TreeBuilder::tree_creation(tree_t *&tree, int *sepToNode, const int *nodePa
         return;
     }
     const int pivot = firstPart + (lastPart - firstPart) / 2;
+    int nbLeftOut = 0, nbSepOut = 0;
 
     int nbLeftNodes = 0, nbRightNodes = 0;
     if (!isSep) {
@@ -152,35 +238,70 @@ void TreeBuilder::tree_creation(tree_t *&tree, int *sepToNode, const int *nodePa
         nbRightNodes = (lastNode - firstNode + 1) - nbLeftNodes;
     }
 
-    /* class 0: every node in a part <= pivot, 1: every node beyond it, 2: straddles */
-    std::vector<int> cls((size_t)n), order((size_t)n);
+    /* class 0: every node in a part <= pivot, 1: every node beyond it, 2: straddles.
+     * The stable 3-way order (reference: DC_create_permutation with 3 parts) is computed
+     * chunk-wise so that large ranges near the root are processed by all threads. */
+    std::vector<int> order((size_t)n);
     const int *rows = isSep ? sepToNode + (int64_t)sepOffset * dimElem
                             : conn + (int64_t)firstElem * dimElem;
-    int nbLeft = 0, nbSep = 0;
-    for (int e = 0; e < n; e++) {
-        int onLeft = 0;
-        for (int j = 0; j < dimElem; j++) onLeft += (nodePart[rows[(int64_t)e * dimElem + j]] <= pivot);
-        int c = (onLeft == dimElem) ? 0 : (onLeft == 0 ? 1 : 2);
-        cls[e] = c;
-        nbLeft += (c == 0);
-        nbSep  += (c == 2);
+    const int chunk = 1 << 16;
+    const int nbChunks = (n + chunk - 1) / chunk;
+    std::vector<int> hist((size_t)nbChunks * 3, 0);
+    {
+        std::vector<unsigned char> cls((size_t)n);
+        #pragma omp taskloop default(shared) grainsize(1) if (nbChunks > 4)
+        for (int c = 0; c < nbChunks; c++) {
+            const int e0 = c * chunk, e1 = std::min(n, e0 + chunk);
+            int h[3] = {0, 0, 0};
+            for (int e = e0; e < e1; e++) {
+                int onLeft = 0;
+                for (int j = 0; j < dimElem; j++) onLeft += (nodePart[rows[(int64_t)e * dimElem + j]] <= pivot);
+                const int k = (onLeft == dimElem) ? 0 : (onLeft == 0 ? 1 : 2);
+                cls[(size_t)e] = (unsigned char)k;
+                h[k]++;
+            }
+            hist[(size_t)c * 3] = h[0]; hist[(size_t)c * 3 + 1] = h[1]; hist[(size_t)c * 3 + 2] = h[2];
+        }
+        int total[3] = {0, 0, 0};
+        for (int c = 0; c < nbChunks; c++)
+            for (int k = 0; k < 3; k++) total[k] += hist[(size_t)c * 3 + k];
+        int base[3] = {0, total[0], total[0] + total[1]};
+        for (int c = 0; c < nbChunks; c++)
+            for (int k = 0; k < 3; k++) {
+                const int cnt = hist[(size_t)c * 3 + k];
+                hist[(size_t)c * 3 + k] = base[k];
+                base[k] += cnt;
+            }
+        #pragma omp taskloop default(shared) grainsize(1) if (nbChunks > 4)
+        for (int c = 0; c < nbChunks; c++) {
+            const int e0 = c * chunk, e1 = std::min(n, e0 + chunk);
+            int next[3] = {hist[(size_t)c * 3], hist[(size_t)c * 3 + 1], hist[(size_t)c * 3 + 2]};
+            for (int e = e0; e < e1; e++) order[(size_t)e] = next[cls[(size_t)e]]++;
+        }
+        nbLeftOut = total[0];
+        nbSepOut = total[2];
     }
-    stable_partition_perm(order.data(), cls.data(), n, 3);
+    const int nbLeft = nbLeftOut, nbSep = nbSepOut;
 
-    scatter_rows_inplace<int>(conn + (int64_t)firstElem * dimElem, order.data(), n, dimElem);
-    scatter_rows_inplace<int>(posToOrig + firstElem, order.data(), n, 1);
-    if (isSep) scatter_rows_inplace<int>(sepToNode + (int64_t)sepOffset * dimElem, order.data(), n, dimElem);
-    std::vector<int>().swap(cls);
+    task_scatter_rows(conn + (int64_t)firstElem * dimElem, order.data(), n, dimElem);
+    task_scatter_rows(posToOrig + firstElem, order.data(), n, 1);
+    if (isSep) task_scatter_rows(sepToNode + (int64_t)sepOffset * dimElem, order.data(), n, dimElem);
     std::vector<int>().swap(order);
 
     tree = new_tree_node(firstElem, lastElem, nbSep, firstNode, lastNode, isSep, false);
+    /* the three subtrees work on disjoint element ranges: build them concurrently (the
+     * reference builds the separator after its siblings, but nothing it reads is written
+     * by them) */
+    #pragma omp task default(shared) if (n > 4096)
     tree_creation(tree->right, sepToNode, nodePart, nodePartSize, pivot + 1, lastPart,
                   firstElem + nbLeft, lastElem - nbSep, firstNode + nbLeftNodes, lastNode,
                   sepOffset + nbLeft, isSep);
+    #pragma omp task default(shared) if (n > 4096)
     tree_creation(tree->left, sepToNode, nodePart, nodePartSize, firstPart, pivot, firstElem,
                   firstElem + nbLeft - 1, firstNode, lastNode - nbRightNodes, sepOffset, isSep);
     if (nbSep > 0)
         sep_partitioning(tree->sep, lastElem - nbSep + 1, lastElem, firstNode, lastNode);
+    #pragma omp taskwait
 }
 
 /* reference: partitioning.cc:115-164 (+ create_sepToNode 89-112) */
@@ -194,23 +315,22 @@ void TreeBuilder::sep_partitioning(tree_t *&tree, int firstSepElem, int lastSepE
         return;
     }
     /* separator-local node numbers in order of first appearance */
-    std::vector<int> sepToNode((size_t)n * dimElem);
+    std::vector<int> sepToNode((size_t)n * dimElem), localToGlobal;
     std::unordered_map<int, int> localId;
     localId.reserve((size_t)n * 2);
     const int *rows = conn + (int64_t)firstSepElem * dimElem;
     for (int64_t k = 0; k < (int64_t)n * dimElem; k++) {
         auto it = localId.find(rows[k]);
-        if (it == localId.end()) it = localId.emplace(rows[k], (int)localId.size()).first;
+        if (it == localId.end()) {
+            it = localId.emplace(rows[k], (int)localId.size()).first;
+            localToGlobal.push_back(rows[k]);
+        }
         sepToNode[(size_t)k] = it->second;
     }
     const int nbSepNodes = (int)localId.size();
 
-    std::vector<int64_t> xadj, adjncy;
     std::vector<int> nodePart;
-    build_nodal_graph(xadj, adjncy, sepToNode.data(), n, dimElem, nbSepNodes);
-    metis_recursive(nodePart, xadj, adjncy, nbSepNodes, nbSepPart);
-    std::vector<int64_t>().swap(xadj);
-    std::vector<int64_t>().swap(adjncy);
+    partition_nodes(nodePart, sepToNode.data(), n, nbSepNodes, nbSepPart, localToGlobal.data());
 
     tree_creation(tree, sepToNode.data(), nodePart.data(), nullptr, 0, nbSepPart - 1,
                   firstSepElem, lastSepElem, firstNode, lastNode, 0, true);
@@ -219,7 +339,8 @@ void TreeBuilder::sep_partitioning(tree_t *&tree, int firstSepElem, int lastSepE
 }  // namespace dc
 
 /* reference: tree_creation.cc:482-501 + partitioning.cc:167-228 */
-void DC_create_tree (int *elemToNode, int nbElem, int dimElem, int nbNodes)
+static void create_tree_impl(int *elemToNode, int nbElem, int dimElem, int nbNodes, const double *coord,
+                             int dimNode)
 {
     using namespace dc;
     DC_free_tree();
@@ -227,35 +348,59 @@ void DC_create_tree (int *elemToNode, int nbElem, int dimElem, int nbNodes)
     nodePerm = new int[nbNodes > 0 ? nbNodes : 1];
     const int maxElem = options().maxElemPerPart;
     const int64_t nbConn = (int64_t)nbElem * dimElem;
+    const int nt = options().nbThreads > 0 ? options().nbThreads : omp_get_max_threads();
 
     #pragma omp parallel for schedule(static) if (nbConn > (1 << 16))
     for (int64_t k = 0; k < nbConn; k++) elemToNode[k]--;
 
     int nbPart = (int)ceil(nbElem / (double)maxElem);
+    std::vector<int> posToOrig((size_t)(nbElem > 0 ? nbElem : 1));
+    for (int i = 0; i < nbElem; i++) posToOrig[i] = i;
+    TreeBuilder b{elemToNode, posToOrig.data(), dimElem, maxElem, coord, dimNode};
+
+    const bool verbose = getenv("DC_PLAN_VERBOSE") != nullptr;
+    double t0 = omp_get_wtime();
+    auto lap = [&](const char *what) {
+        if (verbose) { double t1 = omp_get_wtime(); fprintf(stderr, "[dc_tree] %-12s %.2fs\n", what, t1 - t0); t0 = t1; }
+    };
     std::vector<int> nodePart;
-    {
-        std::vector<int64_t> xadj, adjncy;
-        build_nodal_graph(xadj, adjncy, elemToNode, nbElem, dimElem, nbNodes);
-        metis_recursive(nodePart, xadj, adjncy, nbNodes, nbPart);
-    }
+    #pragma omp parallel num_threads(nt)
+    #pragma omp single
+    b.partition_nodes(nodePart, elemToNode, nbElem, nbNodes, nbPart, nullptr);
+    lap("partition");
     stable_partition_perm(nodePerm, nodePart.data(), nbNodes, nbPart);
     std::vector<int> nodePartSize((size_t)(nbPart > 0 ? nbPart : 1), 0);
     for (int i = 0; i < nbNodes; i++) nodePartSize[nodePart[i]]++;
 
-    std::vector<int> posToOrig((size_t)(nbElem > 0 ? nbElem : 1));
-    for (int i = 0; i < nbElem; i++) posToOrig[i] = i;
-
-    TreeBuilder b{elemToNode, posToOrig.data(), dimElem, maxElem};
+    #pragma omp parallel num_threads(nt)
+    #pragma omp single
     b.tree_creation(treeHead, nullptr, nodePart.data(), nodePartSize.data(), 0, nbPart - 1, 0,
                     nbElem - 1, 0, nbNodes - 1, 0, false);
 
+    lap("recursion");
     #pragma omp parallel for schedule(static) if (nbConn > (1 << 16))
     for (int64_t k = 0; k < nbConn; k++) elemToNode[k]++;
 
     if (options().vecSize > 0)
         color_leaves(elemToNode, nbElem, dimElem, nbNodes, options().vecSize, posToOrig.data());
 
+    #pragma omp parallel for schedule(static) if (nbElem > (1 << 16))
     for (int pos = 0; pos < nbElem; pos++) elemPerm[posToOrig[pos]] = pos;
+}
+
+void DC_create_tree (int *elemToNode, int nbElem, int dimElem, int nbNodes)
+{
+    create_tree_impl(elemToNode, nbElem, dimElem, nbNodes, nullptr, 3);
+}
+
+/* Same contract as DC_create_tree, with the node partitions cut by recursive coordinate
+ * bisection of `coord` ([nbNodes][dimNode], ORIGINAL node numbering) instead of METIS.
+ * For meshes where METIS is too slow; the resulting tree obeys the same invariants. */
+void DC_create_tree_geometric (int *elemToNode, int nbElem, int dimElem, int nbNodes,
+                               const double *coord, int dimNode)
+{
+    if (!coord) dc::fatal("Error: DC_create_tree_geometric needs node coordinates.");
+    create_tree_impl(elemToNode, nbElem, dimElem, nbNodes, coord, dimNode);
 }
 
 /* reference: tree_creation.cc:176-239 (BULK_SYNCHRONOUS, no STATS): every leaf,

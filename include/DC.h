@@ -135,6 +135,10 @@ int  DC_get_vec_size ();
 /* Leaf capacity used by DC_create_tree (reference constant MAX_ELEM_PER_PART). */
 void DC_set_max_elem_per_part (int maxElem);
 int  DC_get_max_elem_per_part ();
+/* DC_create_tree with recursive coordinate bisection of the nodes (coord: [nbNodes][dimNode],
+ * original numbering) in place of METIS -- same tree invariants, usable at 10^8 elements. */
+void DC_create_tree_geometric (int *elemToNode, int nbElem, int dimElem, int nbNodes,
+                               const double *coord, int dimNode);
 /* Worker threads for DC_tree_traversal / DC_assembly host callbacks (0 = all). */
 void DC_set_num_threads (int nbThreads);
 /* Root of the current tree (nullptr before create/read). */

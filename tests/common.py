@@ -166,13 +166,17 @@ class RefLib:
 class MineLib:
     """Same driver surface over the product's host library."""
 
-    def __init__(self, vec=0):
+    def __init__(self, vec=0, geometric=False):
         self.vec = vec
+        self.geometric = geometric
         dc.DC_set_vec_size(vec)
 
-    def create_tree(self, conn, E, N):
+    def create_tree(self, conn, E, N, coord=None):
         dc.DC_set_vec_size(self.vec)
-        dc.DC_create_tree(conn, E, 4, N)
+        if self.geometric:
+            dc.DC_create_tree_geometric(conn, E, 4, N, coord)
+        else:
+            dc.DC_create_tree(conn, E, 4, N)
 
     def permute_double_2d(self, tab, n, dim):
         dc.DC_permute_double_2d_array(tab, n, dim)
@@ -207,7 +211,10 @@ def prepare_mesh(lib, n, tmp_path, hub=False, tag="t"):
     if hub:
         conn, coord, N = dc.hub_collapse(conn, coord, n)
     E = conn.shape[0]
-    lib.create_tree(conn, E, N)
+    if getattr(lib, "geometric", False):
+        lib.create_tree(conn, E, N, coord)
+    else:
+        lib.create_tree(conn, E, N)
     lib.permute_double_2d(coord, N, 3)
     flat = conn.reshape(-1)
     lib.renumber(flat, 4 * E)

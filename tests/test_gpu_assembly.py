@@ -93,6 +93,14 @@ def test_all_modes_against_oracle(tmp_path, n, vec, dim, slots, hub):
         assert plan.c.big.nbEdges > 0           # the fallback really ran
 
 
+@pytest.mark.parametrize("n,dim", [(12, 3), (20, 1)])
+def test_geometric_tree_bit_exact(tmp_path, n, dim):
+    """Trees cut by coordinate bisection (the at-scale builder) feed the same device path."""
+    mesh = prepare_mesh(MineLib(0, geometric=True), n, tmp_path)
+    ctx, _ = _ctx(mesh, slots=288)
+    assert _run(ctx, mesh, dim, dc.MODE_DETERMINISTIC).tobytes() == oracle_serial(mesh, dim).tobytes()
+
+
 def test_plan_without_tree_is_still_bit_exact(tmp_path):
     mesh = prepare_mesh(MineLib(0), 10, tmp_path)
     ctx, _ = _ctx(mesh, slots=400, with_tree=False)

@@ -124,3 +124,37 @@ def test_tiny_meshes(tmp_path):
         if mesh["E"] <= 200:
             assert cnt == 1 and nodes[0].isLeaf
             assert (nodes[0].firstEdge, nodes[0].lastEdge) == (0, mesh["nnz"] - 1)
+
+
+@pytest.mark.parametrize("n,vec", [(6, 0), (12, 0), (12, 4), (20, 0)])
+def test_geometric_tree_is_a_valid_dc_tree(tmp_path, n, vec):
+    """DC_create_tree_geometric (coordinate bisection instead of METIS) must obey the D&C
+    invariants the traversal relies on: leaves cover every element once; the elements of a
+    non-separator node only touch that node's node interval; left/right node intervals split
+    the parent's; a separator subtree inherits its parent's node interval."""
+    mesh = prepare_mesh(MineLib(vec, geometric=True), n, tmp_path)
+    nodes, cnt, elemPerm, nodePerm = parse_tree(mesh["tree"], mesh["E"], mesh["N"])
+    assert sorted(elemPerm.tolist()) == list(range(mesh["E"]))
+    assert sorted(nodePerm.tolist()) == list(range(mesh["N"]))
+    conn = mesh["conn"] - 1
+    covered = np.zeros(mesh["E"], dtype=np.int32)
+    for i in range(cnt):
+        t = nodes[i]
+        if t.isLeaf:
+            covered[t.firstElem:t.lastElem + 1] += 1
+            assert t.lastElem - t.firstElem + 1 <= 200 or t.lastSep == t.lastElem
+        if t.lastSep >= t.firstElem:
+            sub = conn[t.firstElem:t.lastSep + 1]
+            assert sub.min() >= t.firstNode and sub.max() <= t.lastNode
+        if not t.isLeaf:
+            l, r = nodes[t.left], nodes[t.right]
+            if not t.isSep:
+                assert (l.firstNode, r.lastNode) == (t.firstNode, t.lastNode) and l.lastNode + 1 == r.firstNode
+            if t.sep >= 0:
+                s = nodes[t.sep]
+                assert s.isSep and (s.firstNode, s.lastNode) == (t.firstNode, t.lastNode)
+                assert (s.firstElem, s.lastSep) == (t.lastElem + 1, t.lastSep)
+    assert (covered == 1).all()
+    # the reference's traversal semantics hold on it: restated walk == ascending loop
+    walk = common.oracle_traverse(mesh, 1, nodes, split=vec > 0)
+    assert walk.tobytes() == common.oracle_serial(mesh, 1).tobytes()
