@@ -163,37 +163,40 @@ def main():
     import numpy as np
     import torch
     import dc_lib_b200 as dc
+    from dc_lib_b200 import multigpu
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; dc-b200 has no CPU path")
     torch.cuda.set_device(local)
+    dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        os.environ.setdefault("OMP_NUM_THREADS", str(max(1, (os.cpu_count() or 1))))
+    device = f"cuda:{local}"
 
-    w = build_workload(dc, n, vec, builder, rank)
-    E, N, nnz = w["E"], w["N"], w["nnz"]
-    t0 = time.time()
-    plan = dc.HostPlan(w["conn"], N, w["row"], w["col"], 0, w["rec"], args.slots)
-    plan_s = time.time() - t0
-    ctx = dc.Context(local)
-    ctx.set_mesh(w["conn"], w["coord"], w["row"], w["col"], 0)
-    ctx.upload_plan(plan)
-    st = plan.stats()
-    del plan
-    w["conn"] = w["row"] = w["col"] = w["rec"] = None          # host copies no longer needed
+    # one slab (cube) per GPU; rank 0 builds tree / CSR / schedule, the others get them over NCCL
+    ctx, info = multigpu.setup_device_slabs(n, rank, world, device, builder=builder, vec=vec, slots=args.slots, dist=dist)
+    E, N, nnz, st = info["E"], info["N"], info["nnz"], info["stats"]
     op, prm = (dc.OP_ELASTICITY, [LAMBDA, MU]) if dim == 3 else (dc.OP_LAPLACIAN, None)
-    vals = torch.empty(nnz * dim * dim, dtype=torch.float64, device="cuda")
+    per = dim * dim
+    vals = torch.empty(nnz * per, dtype=torch.float64, device=device)
     stream = torch.cuda.current_stream().cuda_stream
+    exch = multigpu.DeviceInterfaceExchange(info["intf"], per, device, dist) if world > 1 else None
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def step():
+        ctx.assemble(op, prm, dc.MODE_DETERMINISTIC, vals, stream)
+        if exch:
+            exch.run(vals, stream)           # NCCL send/recv of interface partial sums + unpack-add
+
     # ---- device-resident timing -------------------------------------------------------
     for _ in range(args.warmup):
-        ctx.assemble(op, prm, dc.MODE_DETERMINISTIC, vals, stream)
+        step()
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
@@ -201,61 +204,87 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        ctx.assemble(op, prm, dc.MODE_DETERMINISTIC, vals, stream)
+        step()
     e1.record()
     barrier()
-    launches = ctx.launch_count() - l0
+    launches = ctx.launch_count() - l0 + (exch.launches_per_step * args.steps if exch else 0)
     ms = e0.elapsed_time(e1) / args.steps
+    # the assembly kernel alone (what the roofline line describes)
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for _ in range(args.steps):
+        ctx.assemble(op, prm, dc.MODE_DETERMINISTIC, vals, stream)
+    k1.record()
+    torch.cuda.synchronize()
+    kernel_ms = k0.elapsed_time(k1) / args.steps
     sampler.stop_flag = True
     sampler.join()
 
-    # ---- end to end through the host-array entry point ---------------------------------
-    h_coord = torch.from_numpy(w["coord"]).pin_memory()
-    h_vals = torch.empty(nnz * dim * dim, dtype=torch.float64, pin_memory=True)
-    e2e_steps = max(2, min(args.steps, 5 if nnz * dim * dim < 5e8 else 2))
-    for _ in range(1):
+    # ---- end to end through the host-array entry points ---------------------------------
+    # per step: host coordinates -> device, assembly (+ interface exchange), values -> host.
+    # Matrices above 16 GB stream through a 2 GiB pinned ring (the host consumer sees every byte).
+    h_coord = info["coord"].cpu().pin_memory()
+    total = nnz * per
+    ring = total if total * 8 <= 16e9 else (1 << 28)
+    h_vals = torch.empty(ring, dtype=torch.float64, pin_memory=True)
+    e2e_steps = max(2, min(args.steps, 5 if total < 5e8 else 2))
+
+    def e2e_step():
         ctx.update_coords(h_coord.numpy(), stream)
-        ctx.assemble_to_host(op, prm, dc.MODE_DETERMINISTIC, h_vals.numpy(), stream)
+        step()
+        for first in range(0, total, ring):
+            cnt = min(ring, total - first)
+            ctx.download_range(vals, first, cnt, h_vals.numpy(), stream)
+        ctx.sync(stream)
+
+    e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        ctx.update_coords(h_coord.numpy(), stream)
-        ctx.assemble_to_host(op, prm, dc.MODE_DETERMINISTIC, h_vals.numpy(), stream)
+        e2e_step()
     barrier()
     e2e_ms = 1e3 * (time.perf_counter() - t0) / e2e_steps
     checksum = float(h_vals.numpy()[:: max(1, h_vals.numel() // 1000003)].sum())
 
     if world > 1:
-        t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device="cuda")
+        t = torch.tensor([ms, e2e_ms, kernel_ms], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_ms = float(t[0]), float(t[1])
+        ms, e2e_ms, kernel_ms = float(t[0]), float(t[1]), float(t[2])
         dist.barrier()
     if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
         return
 
     peak, peak_src = measured_peak()
-    b_alg = 16 * E + 24 * N + 4 * (N + 1) + 4 * nnz + 8 * dim * dim * nnz
-    achieved = b_alg / (ms * 1e-3) / 1e9
+    b_alg = 16 * E + 24 * N + 4 * (N + 1) + 4 * nnz + 8 * per * nnz
+    achieved = b_alg / (kernel_ms * 1e-3) / 1e9
     line = {
         "metric": "assembled elements/s (fp64, CSR scatter-add)", "value": world * E / (ms * 1e-3), "unit": "elements/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "kernel": "gather_units",
+                     "traffic": None, "peak_source": peak_src, "kernel": "gather_units", "kernel_ms": kernel_ms,
                      "algorithmic_bytes_per_launch": b_alg, "bytes_per_element": b_alg / E},
         "e2e": {"value": world * E / (e2e_ms * 1e-3), "unit": "elements/s", "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": 24 * N, "d2h_bytes_per_step": 8 * dim * dim * nnz, "steps": e2e_steps,
-                "checksum": checksum},
+                "h2d_bytes_per_step": 24 * N, "d2h_bytes_per_step": 8 * per * nnz, "steps": e2e_steps,
+                "host_buffer": "full-size pinned array" if ring == total else "2 GiB pinned ring", "checksum": checksum},
         "gpu_launches": launches, "clocks": sampler.summary(),
-        "setup": {"tree_s": w["tree_s"], "tree_and_csr_s": w["setup_s"], "plan_s": plan_s, "units": st["units"],
-                  "element_setups_per_element": st["slots_total"] / E,
+        "setup": {"tree_and_csr_s": info["tree_s"], "plan_s": info["plan_s"], "total_s": info["setup_s"],
+                  "units": st["units"], "element_setups_per_element": st["slots_total"] / E,
                   "item_padding_efficiency": st["items_useful"] / max(st["items"], 1), "host_cores": os.cpu_count()},
     }
+    if world > 1:
+        line["config"]["parallelism"] = (f"{world} slabs (one cube per GPU, stacked along x), interface-edge partial sums "
+                                         "exchanged with NCCL send/recv and added by the unpack-add kernel")
+        line["interface_bytes_per_step_per_gpu"] = exch.bytes_per_step
     if not args.no_cpu_baseline:
         base = cpu_reference(dim, 5, 1)
         base.pop("ms_per_step")
         line["cpu_baseline"] = base
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

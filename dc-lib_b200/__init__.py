@@ -84,6 +84,8 @@ def _declare(L):
     L.dc_cuda_set_mesh_device.argtypes = [vp, vp, vp, vp, vp, c_int, c_int, c_int64, c_int]
     L.dc_cuda_update_coords.argtypes = [vp, vp, vp]
     L.dc_cuda_upload_plan.argtypes = [vp, POINTER(Plan)]
+    L.dc_cuda_set_plan_device.argtypes = [vp, vp, vp, vp, vp, vp, c_int64, c_int, c_int, c_int, c_int]
+    L.dc_cuda_download_range.argtypes = [vp, c_int64, c_int64, vp, vp]
     L.dc_cuda_upload_lists.argtypes = [vp, vp, vp, vp, c_int64, c_int64]
     L.dc_cuda_assemble.argtypes = [vp, c_int, vp, c_int, c_int, vp, vp]
     L.dc_cuda_values.argtypes = [vp, c_int, POINTER(c_void_p)]
@@ -104,6 +106,12 @@ def _declare(L):
     L.dc_contrib_free.restype = None
     L.dcx_kuhn_cube.argtypes = [c_int, vp, vp, c_double, c_int]
     L.dcx_kuhn_cube.restype = None
+    L.dcx_kuhn_slab.argtypes = [c_int, vp, vp, c_double, c_int, c_int]
+    L.dcx_kuhn_slab.restype = None
+    L.dc_get_node_perm.argtypes = [vp, c_int]
+    L.dc_get_elem_perm.argtypes = [vp, c_int]
+    L.dc_cuda_pack_edges.argtypes = [vp, vp, c_int64, c_int, vp, vp]
+    L.dc_cuda_unpack_add_edges.argtypes = [vp, vp, c_int64, c_int, vp, vp]
     L.dcx_build_csr.argtypes = [vp, c_int, c_int, vp, vp, c_int]
     L.dcx_build_csr.restype = c_int64
     L.dc_flatten_tree.argtypes = [vp, c_int64]
@@ -244,6 +252,26 @@ class HostPlan:
         if rc:
             raise RuntimeError(f"dc_plan_build failed with code {rc}")
 
+    def arrays(self):
+        """Zero-copy numpy views of the schedule arrays (valid while this object lives)."""
+        c = self.c
+        as_np = np.ctypeslib.as_array
+
+        def view(ptr, count, dtype, width=1):
+            if count == 0:
+                return np.zeros((0,) if width == 1 else (0, width), dtype=dtype)
+            a = as_np(ctypes.cast(ptr, POINTER(ctypes.c_uint8)), shape=(count * width * np.dtype(dtype).itemsize,))
+            a = a.view(dtype)
+            return a if width == 1 else a.reshape(count, width)
+
+        return dict(units=view(c.units, c.nbUnits, np.uint8, 64), tasks=view(c.tasks, c.nbTasks, np.uint8, 16),
+                    items=view(c.items, c.nbItems, np.uint16), halo=view(c.haloElems, c.nbHalo, np.int32),
+                    nbUnits=int(c.nbUnits), maxSlots=int(c.maxSlots), maxHalo=int(c.maxHalo),
+                    maxTasks=int(c.maxTasks), maxItems=int(c.maxItems), bigEdges=int(c.big.nbEdges))
+
+    def diag_rel(self, nbNodes):
+        return np.ctypeslib.as_array(self.c.diagRel, shape=(max(nbNodes, 1),))[:nbNodes]
+
     def stats(self):
         c = self.c
         return dict(units=c.nbUnits, tasks=c.nbTasks, items=c.nbItems, items_useful=c.nbItemsUseful,
@@ -289,6 +317,19 @@ class Context:
 
     def upload_plan(self, plan):
         self._ck(lib().dc_cuda_upload_plan(self.h, byref(plan.c)), "dc_cuda_upload_plan")
+
+    def set_plan_device(self, t):
+        """t: dict of torch CUDA tensors {units,tasks,items,halo,diagRel} + ints {nbUnits,maxSlots,maxHalo,maxTasks,maxItems}."""
+        self._keep_plan = t
+        self._ck(lib().dc_cuda_set_plan_device(self.h, _p(t["units"]), _p(t["tasks"]), _p(t["items"]), _p(t["halo"]),
+                                               _p(t["diagRel"]), t["nbUnits"], t["maxSlots"], t["maxHalo"],
+                                               t["maxTasks"], t["maxItems"]), "dc_cuda_set_plan_device")
+
+    def download_range(self, d_values, first, count, h_buf, stream=None):
+        self._ck(lib().dc_cuda_download_range(_p(d_values), first, count, _p(h_buf), stream), "dc_cuda_download_range")
+
+    def sync(self, stream=None):
+        self._ck(lib().dc_cuda_sync(stream), "dc_cuda_sync")
 
     def upload_lists(self, conn, nbNodes, row, col, colBase=0):
         cl = ContribList()
@@ -362,13 +403,33 @@ def reset_edges(d_values, firstEdge, lastEdge, perEdge, stream=None):
         raise RuntimeError(lib().dc_cuda_last_error().decode())
 
 
-def kuhn_cube_fast(n, amplitude=0.3, seed=12345):
-    """C++/OpenMP version of kuhn_cube + jitter_coords (identical arrays)."""
+def kuhn_cube_fast(n, amplitude=0.3, seed=12345, x_offset=0, coords_only=False):
+    """C++/OpenMP version of kuhn_cube + jitter_coords (identical arrays).  x_offset places
+    the cube that many cells along x inside a bar of cubes (shared planes get equal nodes)."""
     E, N = 6 * n ** 3, (n + 1) ** 3
-    conn = np.empty((E, 4), dtype=np.int32)
+    conn = None if coords_only else np.empty((E, 4), dtype=np.int32)
     coord = np.empty((N, 3), dtype=np.float64)
-    lib().dcx_kuhn_cube(n, _p(conn), _p(coord), amplitude, seed)
+    lib().dcx_kuhn_slab(n, _p(conn), _p(coord), amplitude, seed, x_offset)
     return conn, coord, N
+
+
+def get_node_perm(nbNodes):
+    out = np.empty(nbNodes, dtype=np.int32)
+    if lib().dc_get_node_perm(_p(out), nbNodes):
+        raise RuntimeError("no node permutation (call between DC_create_tree/DC_read_tree and DC_store_tree)")
+    return out
+
+
+def pack_edges(d_values, d_edge, perEdge, d_buf, stream=None):
+    rc = lib().dc_cuda_pack_edges(_p(d_values), _p(d_edge), d_edge.numel(), perEdge, _p(d_buf), stream)
+    if rc:
+        raise RuntimeError(lib().dc_cuda_last_error().decode())
+
+
+def unpack_add_edges(d_values, d_edge, perEdge, d_buf, stream=None):
+    rc = lib().dc_cuda_unpack_add_edges(_p(d_values), _p(d_edge), d_edge.numel(), perEdge, _p(d_buf), stream)
+    if rc:
+        raise RuntimeError(lib().dc_cuda_last_error().decode())
 
 
 def build_csr_fast(conn, nbNodes, colBase=0):

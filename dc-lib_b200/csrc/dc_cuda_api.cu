@@ -40,6 +40,7 @@ struct dc_cuda_ctx {
     int maxSlots = 0, maxHalo = 0, maxTasks = 0, maxItems = 0;
     int threads = 256;       /* CTA size of the unit kernel (128 or 256) */
     int64_t nbUnits = 0, nbBigEdges = 0;
+    bool ownsPlan = true;
     dc_unit_t *d_units = nullptr;
     dc_task_t *d_tasks = nullptr;
     uint16_t *d_items = nullptr;
@@ -95,6 +96,10 @@ static void free_mesh(dc_cuda_ctx *c)
 }
 static void free_plan(dc_cuda_ctx *c)
 {
+    if (!c->ownsPlan) {
+        c->d_units = nullptr; c->d_tasks = nullptr; c->d_items = nullptr; c->d_halo = c->d_diagRel = nullptr;
+        c->ownsPlan = true;
+    }
     cudaFree(c->d_units); cudaFree(c->d_tasks); cudaFree(c->d_items); cudaFree(c->d_halo);
     cudaFree(c->d_diagRel); cudaFree(c->d_bigEdge); cudaFree(c->d_bigPtr); cudaFree(c->d_bigItem);
     c->d_units = nullptr; c->d_tasks = nullptr; c->d_items = nullptr; c->d_halo = c->d_diagRel = nullptr;
@@ -192,6 +197,28 @@ extern "C" int dc_cuda_upload_plan(dc_cuda_ctx *c, const struct dc_plan_s *p)
     c->maxHalo = p->maxHalo;
     c->maxTasks = p->maxTasks;
     c->maxItems = p->maxItems;
+    return 0;
+}
+
+extern "C" int dc_cuda_set_plan_device(dc_cuda_ctx *c, const void *d_units, const void *d_tasks,
+                                       const void *d_items, const int *d_halo, const int *d_diagRel,
+                                       int64_t nbUnits, int maxSlots, int maxHalo, int maxTasks, int maxItems)
+{
+    if (!c) return fail(-1, "dc_cuda_set_plan_device: null context");
+    if ((reinterpret_cast<uintptr_t>(d_units) | reinterpret_cast<uintptr_t>(d_tasks) |
+         reinterpret_cast<uintptr_t>(d_items) | reinterpret_cast<uintptr_t>(d_halo)) & 15)
+        return fail(-5, "dc_cuda_set_plan_device: arrays must be 16-byte aligned");
+    CK(cudaSetDevice(c->device));
+    free_plan(c);
+    c->ownsPlan = false;
+    c->d_units = (dc_unit_t *)d_units;
+    c->d_tasks = (dc_task_t *)d_tasks;
+    c->d_items = (uint16_t *)d_items;
+    c->d_halo = const_cast<int *>(d_halo);
+    c->d_diagRel = const_cast<int *>(d_diagRel);
+    c->nbUnits = nbUnits;
+    c->nbBigEdges = 0;
+    c->maxSlots = maxSlots; c->maxHalo = maxHalo; c->maxTasks = maxTasks; c->maxItems = maxItems;
     return 0;
 }
 
@@ -302,6 +329,15 @@ extern "C" int dc_cuda_download_values(dc_cuda_ctx *c, int dim, double *h_values
     return 0;
 }
 
+extern "C" int dc_cuda_download_range(const double *d_values, int64_t first, int64_t count, double *h_buf,
+                                      void *stream)
+{
+    if (count <= 0) return 0;
+    CK(cudaMemcpyAsync(h_buf, d_values + first, sizeof(double) * (size_t)count, cudaMemcpyDeviceToHost,
+                       (cudaStream_t)stream));
+    return 0;
+}
+
 static unsigned grid_for(int64_t work, int perBlock)
 {
     int64_t b = (work + perBlock - 1) / perBlock;
@@ -350,6 +386,26 @@ extern "C" int dc_cuda_reset_edges(double *d_values, int64_t firstEdge, int64_t 
     if (lastEdge < firstEdge) return 0;
     const int64_t n = (lastEdge - firstEdge + 1) * perEdge;
     reset_values<<<grid_for(n / 2 + 1, 256), 256, 0, (cudaStream_t)stream>>>(d_values + firstEdge * perEdge, n);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int dc_cuda_pack_edges(const double *d_values, const int64_t *d_edge, int64_t nbEdges, int perEdge,
+                                  double *d_buf, void *stream)
+{
+    if (nbEdges <= 0) return 0;
+    pack_edges<<<grid_for(nbEdges * perEdge, 256), 256, 0, (cudaStream_t)stream>>>(d_values, d_edge, nbEdges,
+                                                                                   perEdge, d_buf);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int dc_cuda_unpack_add_edges(double *d_values, const int64_t *d_edge, int64_t nbEdges, int perEdge,
+                                        const double *d_buf, void *stream)
+{
+    if (nbEdges <= 0) return 0;
+    unpack_add_edges<<<grid_for(nbEdges * perEdge, 256), 256, 0, (cudaStream_t)stream>>>(d_values, d_edge, nbEdges,
+                                                                                         perEdge, d_buf);
     CK(cudaGetLastError());
     return 0;
 }

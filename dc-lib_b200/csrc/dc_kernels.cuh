@@ -373,5 +373,30 @@ __global__ void __launch_bounds__(256) renumber(int *__restrict__ tab, const int
         tab[i] = __ldg(perm + (tab[i] - base)) + base;
 }
 
+/* ---- interface exchange (multi-GPU) ------------------------------------------ */
+
+/* buf[k][:] = values[edge[k]][:]  (perEdge doubles per edge) */
+__global__ void __launch_bounds__(256) pack_edges(const double *__restrict__ values, const int64_t *__restrict__ edge,
+                                                  int64_t nbEdges, int perEdge, double *__restrict__ buf)
+{
+    const int64_t total = nbEdges * perEdge, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += stride) {
+        const int64_t k = w / perEdge;
+        buf[w] = values[__ldg(edge + k) * perEdge + (w - k * perEdge)];
+    }
+}
+
+/* values[edge[k]][:] += buf[k][:]; buf may be a peer GPU's buffer mapped over NVLink */
+__global__ void __launch_bounds__(256) unpack_add_edges(double *__restrict__ values, const int64_t *__restrict__ edge,
+                                                        int64_t nbEdges, int perEdge, const double *__restrict__ buf)
+{
+    const int64_t total = nbEdges * perEdge, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += stride) {
+        const int64_t k = w / perEdge;
+        double *dst = values + __ldg(edge + k) * perEdge + (w - k * perEdge);
+        *dst = __dadd_rn(*dst, buf[w]);
+    }
+}
+
 }  // namespace dcdev
 #endif

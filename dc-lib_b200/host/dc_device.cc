@@ -45,6 +45,20 @@ extern "C" int64_t dc_flatten_tree (int *out, int64_t maxNodes)
     return n;
 }
 
+/* copies of the library-owned permutations (valid between create/read and store) */
+extern "C" int dc_get_node_perm (int *out, int nbNodes)
+{
+    if (!nodePerm) return -1;
+    std::copy(nodePerm, nodePerm + nbNodes, out);
+    return 0;
+}
+extern "C" int dc_get_elem_perm (int *out, int nbElem)
+{
+    if (!elemPerm) return -1;
+    std::copy(elemPerm, elemPerm + nbElem, out);
+    return 0;
+}
+
 void DC_device_init (int device)
 {
     if (g_ctx) { dc_cuda_destroy(g_ctx); g_ctx = nullptr; }

@@ -12,8 +12,18 @@
 
 extern "C" {
 
-/* conn: [6 n^3][4] 1-based; coord: [(n+1)^3][3] */
+/* conn: [6 n^3][4] 1-based; coord: [(n+1)^3][3].  xOffset shifts the cube by that many
+ * cells along x inside a longer bar of cubes: coordinates and the jitter hash then use the
+ * GLOBAL node id ((i+xOffset)*(n+1)+j)*(n+1)+k, so that neighbouring slabs agree on the
+ * nodes of their common plane (multi-GPU decomposition). */
+void dcx_kuhn_slab(int n, int *conn, double *coord, double amplitude, int seed, int xOffset);
+
 void dcx_kuhn_cube(int n, int *conn, double *coord, double amplitude, int seed)
+{
+    dcx_kuhn_slab(n, conn, coord, amplitude, seed, 0);
+}
+
+void dcx_kuhn_slab(int n, int *conn, double *coord, double amplitude, int seed, int xOffset)
 {
     static const int order[6][3] = {{0, 1, 2}, {0, 2, 1}, {1, 0, 2}, {1, 2, 0}, {2, 0, 1}, {2, 1, 0}};
     const int64_t m = n + 1, cells = (int64_t)n * n * n;
@@ -36,9 +46,10 @@ void dcx_kuhn_cube(int n, int *conn, double *coord, double amplitude, int seed)
         const int64_t N = m * m * m;
         #pragma omp parallel for schedule(static)
         for (int64_t id = 0; id < N; id++) {
-            const double grid[3] = {(double)(id / (m * m)), (double)((id / m) % m), (double)(id % m)};
+            const double grid[3] = {(double)(id / (m * m) + xOffset), (double)((id / m) % m), (double)(id % m)};
+            const int64_t gid = id + (int64_t)xOffset * m * m;
             for (int comp = 0; comp < 3; comp++) {
-                int64_t h = (id * 3 + comp + seed) & 0x7FFFFFFF;
+                int64_t h = (gid * 3 + comp + seed) & 0x7FFFFFFF;
                 for (int r = 0; r < 3; r++) {
                     h = (h * 1103515245LL + 12345) & 0x7FFFFFFF;
                     h ^= h >> 13;

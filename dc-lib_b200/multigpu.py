@@ -1,0 +1,190 @@
+"""Multi-GPU decomposition of the assembly: one process per GPU, each owns a
+slab of the mesh with its own D&C tree and device schedule; the only exchange per assembly is
+the sum of the partial values of the CSR edges whose two nodes lie on a plane shared with a
+neighbouring slab.  The per-neighbour edge lists play the role of the reference's
+intfIndex / intfNodes / intfDst triple (include/DC.h:51-53, 141-143), at edge granularity, and
+are ordered identically on both sides of a plane so that buffers can be added position by
+position.  Transport is torch.distributed send/recv (NCCL over NVLink on GPUs, gloo in the
+CPU tests); packing and the unpack-add are the kernels behind dc_cuda_pack_edges /
+dc_cuda_unpack_add_edges.
+"""
+import numpy as np
+
+from . import (DC_create_tree, DC_create_tree_geometric, DC_finalize_tree, DC_permute_double_2d_array,
+               DC_renumber_int_array, DC_set_vec_size, build_csr_fast, flatten_tree, get_node_perm,
+               kuhn_cube_fast, pack_edges, unpack_add_edges)
+
+
+def global_node_ids(n, rank):
+    """Global id of every local (original-numbering) node of slab `rank`."""
+    m = n + 1
+    ids = np.arange(m ** 3, dtype=np.int64)
+    return ids + np.int64(rank) * n * m * m
+
+
+def plane_edges(node_perm, row, col, n, side):
+    """Local CSR edges whose two nodes lie on the plane x = side (0 or n) of the cube, ordered by
+    (plane index of the row node, plane index of the column node) -- the same on both slabs."""
+    m = n + 1
+    N = node_perm.shape[0]
+    plane_old = side * m * m + np.arange(m * m, dtype=np.int64)          # plane index p = j*(n+1)+k
+    plane_new = node_perm[plane_old].astype(np.int64)
+    plane_of = -np.ones(N, dtype=np.int64)
+    plane_of[plane_new] = np.arange(m * m)
+    starts, lens = row[plane_new].astype(np.int64), (row[plane_new + 1] - row[plane_new]).astype(np.int64)
+    owner = np.repeat(np.arange(m * m), lens)
+    idx = np.repeat(starts - np.concatenate(([0], np.cumsum(lens)[:-1])), lens) + np.arange(lens.sum())
+    other = plane_of[col[idx]]
+    keep = other >= 0
+    key = owner[keep] * (m * m) + other[keep]
+    return np.ascontiguousarray(idx[keep][np.argsort(key, kind="stable")], dtype=np.int64)
+
+
+def build_slab(n, rank, world, builder="geometric", vec=0, seed=12345):
+    """Appendix-A driver for slab `rank` of a bar of `world` jittered Kuhn cubes stacked along x.
+    Returns the user-side arrays, the flattened tree and, per neighbour, the local CSR edges
+    shared with it (both nodes on the common plane) in an order both sides agree on."""
+    conn, coord, N = kuhn_cube_fast(n, seed=seed, x_offset=rank * n)
+    E = conn.shape[0]
+    DC_set_vec_size(vec)
+    if builder == "geometric":
+        DC_create_tree_geometric(conn, E, 4, N, coord)
+    else:
+        DC_create_tree(conn, E, 4, N)
+    node_perm = get_node_perm(N)
+    DC_permute_double_2d_array(coord, N, 3)
+    DC_renumber_int_array(conn.reshape(-1), 4 * E)
+    row, col = build_csr_fast(conn, N)
+    DC_finalize_tree(row, conn, E, 4)
+    rec = flatten_tree()
+
+    intf = {}
+    for side, nb in ((0, rank - 1), (n, rank + 1)):
+        if 0 <= nb < world:
+            intf[nb] = plane_edges(node_perm, row, col, n, side)
+    gid_of_new = np.empty(N, dtype=np.int64)
+    gid_of_new[node_perm] = global_node_ids(n, rank)
+    return dict(conn=conn, coord=coord, row=row, col=col, E=E, N=N, nnz=int(row[-1]), rec=rec, n=n,
+                intf=intf, gid_of_new=gid_of_new, node_perm=node_perm, rank=rank, world=world)
+
+
+class InterfaceExchange:
+    """Sums the interface-edge partial values with the neighbouring ranks."""
+
+    def __init__(self, intf, per_edge, device, dist=None):
+        import torch
+        self.torch, self.dist, self.per = torch, dist, per_edge
+        self.on_gpu = torch.device(device).type == "cuda"
+        self.nbs = sorted(intf)
+        self.edges = {nb: torch.from_numpy(intf[nb]).to(device) for nb in self.nbs}
+        self.send = {nb: torch.empty(intf[nb].shape[0] * per_edge, dtype=torch.float64, device=device) for nb in self.nbs}
+        self.recv = {nb: torch.empty_like(self.send[nb]) for nb in self.nbs}
+        self.bytes_per_step = sum(2 * 8 * self.send[nb].numel() for nb in self.nbs)
+        self.launches_per_step = 2 * len(self.nbs) if self.on_gpu else 0
+
+    def _pack(self, values, nb, stream):
+        if self.on_gpu:
+            pack_edges(values, self.edges[nb], self.per, self.send[nb], stream)
+        else:
+            self.send[nb].copy_(values.view(-1, self.per)[self.edges[nb]].reshape(-1))
+
+    def _unpack_add(self, values, nb, stream):
+        if self.on_gpu:
+            unpack_add_edges(values, self.edges[nb], self.per, self.recv[nb], stream)
+        else:
+            values.view(-1, self.per)[self.edges[nb]] += self.recv[nb].view(-1, self.per)
+
+    def run(self, values, stream=None):
+        if not self.nbs:
+            return
+        dist = self.dist
+        ops = []
+        for nb in self.nbs:
+            self._pack(values, nb, stream)
+            ops.append(dist.P2POp(dist.isend, self.send[nb], nb))
+            ops.append(dist.P2POp(dist.irecv, self.recv[nb], nb))
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        for nb in self.nbs:
+            self._unpack_add(values, nb, stream)
+
+
+def setup_device_slabs(n, rank, world, device, builder="geometric", vec=0, slots=400, dist=None, seed=12345):
+    """Device-resident slab for this rank.  Every slab of the bar has the same topology, so
+    rank 0 builds tree, CSR pattern and schedule once on its host cores and broadcasts the
+    arrays GPU-to-GPU (NCCL over NVLink); each rank generates its own coordinates and permutes
+    them on the device.  Returns (ctx, info) with the context ready for dc_cuda_assemble."""
+    import time
+
+    import torch
+
+    from . import Context, HostPlan, permute_double_2d
+
+    names = ["conn", "row", "col", "node_perm", "units", "tasks", "items", "halo", "diagRel", "intf_left", "intf_right"]
+    t0 = time.time()
+    tensors, meta = {}, None
+    if rank == 0:
+        slab = build_slab(n, 0, 1, builder=builder, vec=vec, seed=seed)
+        node_perm = slab["node_perm"]
+        t_tree = time.time() - t0
+        t1 = time.time()
+        plan = HostPlan(slab["conn"], slab["N"], slab["row"], slab["col"], 0, slab["rec"], slots)
+        t_plan = time.time() - t1
+        arr = plan.arrays()
+        if arr["bigEdges"]:
+            raise RuntimeError("setup_device_slabs: rows exceeding the unit budget are not supported on this path")
+        host = dict(conn=slab["conn"], row=slab["row"], col=slab["col"], node_perm=node_perm, units=arr["units"],
+                    tasks=arr["tasks"], items=arr["items"].view(np.int16), halo=arr["halo"],
+                    diagRel=plan.diag_rel(slab["N"]),
+                    intf_left=plane_edges(node_perm, slab["row"], slab["col"], n, 0) if world > 1 else np.zeros(0, np.int64),
+                    intf_right=plane_edges(node_perm, slab["row"], slab["col"], n, n) if world > 1 else np.zeros(0, np.int64))
+        for k in names:
+            tensors[k] = torch.from_numpy(np.ascontiguousarray(host[k])).to(device)
+        st = plan.stats()
+        meta = dict(shapes={k: (tuple(tensors[k].shape), str(tensors[k].dtype)) for k in names},
+                    ints={k: arr[k] for k in ("nbUnits", "maxSlots", "maxHalo", "maxTasks", "maxItems")},
+                    E=slab["E"], N=slab["N"], nnz=slab["nnz"], stats=st, tree_s=t_tree, plan_s=t_plan)
+        del plan, slab, host, arr
+    if world > 1:
+        box = [meta]
+        dist.broadcast_object_list(box, src=0)
+        meta = box[0]
+        for k in names:
+            shape, dtype = meta["shapes"][k]
+            if rank != 0:
+                tensors[k] = torch.empty(shape, dtype=getattr(torch, dtype.split(".")[1]), device=device)
+            if tensors[k].numel():
+                dist.broadcast(tensors[k], src=0)
+    # own coordinates: generated in the original numbering, permuted on the device
+    _, coord_old, _ = kuhn_cube_fast(n, seed=seed, x_offset=rank * n, coords_only=True)
+    d_old = torch.from_numpy(coord_old).to(device)
+    d_coord = torch.empty_like(d_old)
+    permute_double_2d(d_old, d_coord, tensors["node_perm"], 3, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    del d_old, coord_old
+    ctx = Context(torch.device(device).index or 0)
+    ctx.set_mesh_device(tensors["conn"], d_coord, tensors["row"], tensors["col"], meta["nnz"], 0)
+    plan_t = dict(units=tensors["units"], tasks=tensors["tasks"], items=tensors["items"], halo=tensors["halo"],
+                  diagRel=tensors["diagRel"], **meta["ints"])
+    ctx.set_plan_device(plan_t)
+    intf = {}
+    if rank > 0:
+        intf[rank - 1] = tensors["intf_left"]
+    if rank < world - 1:
+        intf[rank + 1] = tensors["intf_right"]
+    info = dict(meta, coord=d_coord, intf=intf, setup_s=time.time() - t0)
+    return ctx, info
+
+
+class DeviceInterfaceExchange(InterfaceExchange):
+    """InterfaceExchange over edge lists that already live on the device."""
+
+    def __init__(self, intf, per_edge, device, dist):
+        import torch
+        self.torch, self.dist, self.per, self.on_gpu = torch, dist, per_edge, True
+        self.nbs = sorted(intf)
+        self.edges = {nb: intf[nb] for nb in self.nbs}
+        self.send = {nb: torch.empty(intf[nb].numel() * per_edge, dtype=torch.float64, device=device) for nb in self.nbs}
+        self.recv = {nb: torch.empty_like(self.send[nb]) for nb in self.nbs}
+        self.bytes_per_step = sum(2 * 8 * self.send[nb].numel() for nb in self.nbs)
+        self.launches_per_step = 2 * len(self.nbs)

@@ -57,6 +57,9 @@ extern "C" {
      * {firstElem,lastElem,lastSep,firstNode,lastNode,isSep,isLeaf,hasSep};
      * returns the node count (call with out = NULL to size the buffer) */
     int64_t dc_flatten_tree (int *out, int64_t maxNodes);
+    /* copies of the library-owned permutations (between create/read and store); 0 on success */
+    int dc_get_node_perm (int *out, int nbNodes);
+    int dc_get_elem_perm (int *out, int nbElem);
 }
 
 #endif

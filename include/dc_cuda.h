@@ -53,6 +53,11 @@ int  dc_cuda_update_coords(dc_cuda_ctx *ctx, const double *h_coord, void *stream
 
 /* Schedule built by dc_plan_build() (host); copied to the device. */
 int  dc_cuda_upload_plan(dc_cuda_ctx *ctx, const struct dc_plan_s *plan);
+/* Same, adopting schedule arrays that already live in device memory (e.g. received from
+ * another rank over NCCL); not copied, not freed.  No big-row fallback list on this path. */
+int  dc_cuda_set_plan_device(dc_cuda_ctx *ctx, const void *d_units, const void *d_tasks,
+                             const void *d_items, const int *d_halo, const int *d_diagRel,
+                             int64_t nbUnits, int maxSlots, int maxHalo, int maxTasks, int maxItems);
 /* Explicit contribution lists for DC_MODE_LIST (all edges). */
 int  dc_cuda_upload_lists(dc_cuda_ctx *ctx, const int64_t *h_edge, const int64_t *h_ptr,
                           const uint32_t *h_item, int64_t nbEdges, int64_t nbItems);
@@ -65,6 +70,11 @@ int  dc_cuda_assemble(dc_cuda_ctx *ctx, int op, const double *h_params, int nbPa
 int  dc_cuda_values(dc_cuda_ctx *ctx, int dim, double **d_values);
 int  dc_cuda_download_values(dc_cuda_ctx *ctx, int dim, double *h_values, void *stream);
 
+/* Device -> host copy of d_values[first, first+count) (asynchronous; for streaming a matrix
+ * larger than the host's pinned buffer). */
+int  dc_cuda_download_range(const double *d_values, int64_t first, int64_t count, double *h_buf,
+                            void *stream);
+
 /* Permutation family on device arrays: d_out[perm[i]] = d_in[i] (rows of dimItem). */
 int  dc_cuda_permute_double_2d(const double *d_in, double *d_out, const int *d_perm,
                                int64_t nbItem, int dimItem, void *stream);
@@ -74,6 +84,16 @@ int  dc_cuda_renumber(int *d_tab, const int *d_perm, int64_t size, int isFortran
 /* Zero d_values[first*perEdge, (last+1)*perEdge) -- the reset of one edge interval. */
 int  dc_cuda_reset_edges(double *d_values, int64_t firstEdge, int64_t lastEdge, int perEdge,
                          void *stream);
+
+/* Interface exchange between GPUs (the reference leaves halo exchange to the user's
+ * MPI/GASPI code through userCommFct, src/tree_traversal.cc:65-73; the data layout follows
+ * its intfIndex/intfNodes/intfDst triple, include/DC.h:51-53, at edge granularity):
+ * pack gathers the partial sums of the listed CSR edges into a contiguous send buffer,
+ * unpack_add adds a received buffer (local, or a peer GPU's buffer mapped over NVLink). */
+int  dc_cuda_pack_edges(const double *d_values, const int64_t *d_edge, int64_t nbEdges, int perEdge,
+                        double *d_buf, void *stream);
+int  dc_cuda_unpack_add_edges(double *d_values, const int64_t *d_edge, int64_t nbEdges, int perEdge,
+                              const double *d_buf, void *stream);
 
 /* Tuning knobs: "unit_threads" = CTA size of the unit kernel (128 or 256, default 256). */
 int  dc_cuda_set_option(dc_cuda_ctx *ctx, const char *name, int value);
