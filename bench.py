@@ -130,7 +130,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="dc_b200", choices=["dc_b200", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("DC_BENCH_WORKLOAD", "m100"))
+    ap.add_argument("--workload", default=os.environ.get("DC_BENCH_WORKLOAD", "target350"))
     ap.add_argument("--slots", type=int, default=int(os.environ.get("DC_BENCH_SLOTS", "400")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

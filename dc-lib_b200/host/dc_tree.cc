@@ -438,7 +438,12 @@ void DC_set_vec_size (int vecSize) { dc::options().vecSize = vecSize; }
 int  DC_get_vec_size () { return dc::options().vecSize; }
 void DC_set_max_elem_per_part (int maxElem) { if (maxElem > 0) dc::options().maxElemPerPart = maxElem; }
 int  DC_get_max_elem_per_part () { return dc::options().maxElemPerPart; }
-void DC_set_num_threads (int nbThreads) { dc::options().nbThreads = nbThreads; }
+void DC_set_num_threads (int nbThreads)
+{
+    /* 0 = every processor, whatever OMP_NUM_THREADS said at start-up (torchrun exports 1) */
+    dc::options().nbThreads = nbThreads > 0 ? nbThreads : omp_get_num_procs();
+    omp_set_num_threads(dc::options().nbThreads);
+}
 tree_t *DC_get_tree () { return treeHead; }
 
 void DC_free_tree ()

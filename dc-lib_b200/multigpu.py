@@ -11,7 +11,7 @@ dc_cuda_unpack_add_edges.
 import numpy as np
 
 from . import (DC_create_tree, DC_create_tree_geometric, DC_finalize_tree, DC_permute_double_2d_array,
-               DC_renumber_int_array, DC_set_vec_size, build_csr_fast, flatten_tree, get_node_perm,
+               DC_renumber_int_array, DC_set_num_threads, DC_set_vec_size, build_csr_fast, flatten_tree, get_node_perm,
                kuhn_cube_fast, pack_edges, unpack_add_edges)
 
 
@@ -124,6 +124,7 @@ def setup_device_slabs(n, rank, world, device, builder="geometric", vec=0, slots
     t0 = time.time()
     tensors, meta = {}, None
     if rank == 0:
+        DC_set_num_threads(0)                      # all host cores (torchrun exports OMP_NUM_THREADS=1)
         slab = build_slab(n, 0, 1, builder=builder, vec=vec, seed=seed)
         node_perm = slab["node_perm"]
         t_tree = time.time() - t0
@@ -154,7 +155,7 @@ def setup_device_slabs(n, rank, world, device, builder="geometric", vec=0, slots
             if rank != 0:
                 tensors[k] = torch.empty(shape, dtype=getattr(torch, dtype.split(".")[1]), device=device)
             if tensors[k].numel():
-                dist.broadcast(tensors[k], src=0)
+                dist.broadcast(tensors[k].view(torch.uint8), src=0)       # raw bytes: NCCL has no int16
     # own coordinates: generated in the original numbering, permuted on the device
     _, coord_old, _ = kuhn_cube_fast(n, seed=seed, x_offset=rank * n, coords_only=True)
     d_old = torch.from_numpy(coord_old).to(device)
