@@ -52,7 +52,8 @@ class Unit(ctypes.Structure):
     _fields_ = [("edgeFirst", c_int64), ("itemFirst", c_int64), ("haloFirst", c_int64),
                 ("edgeCount", c_int32), ("nodeFirst", c_int32), ("nodeCount", c_int32),
                 ("ownElemFirst", c_int32), ("ownElemCount", c_int32), ("haloCount", c_int32),
-                ("taskFirst", c_int32), ("taskCount", c_int32), ("itemCount", c_int32)]
+                ("taskFirst", c_int32), ("taskCount", c_int32), ("itemCount", c_int32),
+                ("tgtFirst", c_int64), ("tgtCount", c_int32), ("pad_", c_int32)]
 
 
 class Task(ctypes.Structure):
@@ -62,11 +63,12 @@ class Task(ctypes.Structure):
 
 class ContribList(ctypes.Structure):
     _fields_ = [("nbEdges", c_int64), ("nbItems", c_int64), ("edge", POINTER(c_int64)),
-                ("ptr", POINTER(c_int64)), ("item", POINTER(c_uint32))]
+                ("ptr", POINTER(c_int64)), ("item", POINTER(c_uint32)), ("edgeT", POINTER(c_int64))]
 
 
 class Plan(ctypes.Structure):
     _fields_ = [("maxSlots", c_int32), ("maxHalo", c_int32), ("maxTasks", c_int32), ("maxItems", c_int32),
+                ("maxTgt", c_int32), ("symmetric", c_int32), ("nbTgt", c_int64), ("tgt", POINTER(c_int32)),
                 ("nbUnits", c_int64), ("nbTasks", c_int64),
                 ("nbItems", c_int64), ("nbHalo", c_int64), ("units", POINTER(Unit)),
                 ("tasks", POINTER(Task)), ("items", POINTER(c_uint16)),
@@ -84,7 +86,7 @@ def _declare(L):
     L.dc_cuda_set_mesh_device.argtypes = [vp, vp, vp, vp, vp, c_int, c_int, c_int64, c_int]
     L.dc_cuda_update_coords.argtypes = [vp, vp, vp]
     L.dc_cuda_upload_plan.argtypes = [vp, POINTER(Plan)]
-    L.dc_cuda_set_plan_device.argtypes = [vp, vp, vp, vp, vp, vp, c_int64, c_int, c_int, c_int, c_int]
+    L.dc_cuda_set_plan_device.argtypes = [vp, vp, vp, vp, vp, vp, vp, c_int64, c_int, c_int, c_int, c_int, c_int, c_int]
     L.dc_cuda_download_range.argtypes = [vp, c_int64, c_int64, vp, vp]
     L.dc_cuda_upload_lists.argtypes = [vp, vp, vp, vp, c_int64, c_int64]
     L.dc_cuda_assemble.argtypes = [vp, c_int, vp, c_int, c_int, vp, vp]
@@ -98,8 +100,8 @@ def _declare(L):
     L.dc_cuda_launch_count.restype = c_int64
     L.dc_cuda_sync.argtypes = [vp]
     L.dc_cuda_set_option.argtypes = [vp, c_char_p, c_int]
-    L.dc_plan_build.argtypes = [POINTER(Plan), vp, c_int, c_int, vp, vp, c_int, vp, c_int64, c_int, c_int]
-    L.dc_contrib_build.argtypes = [POINTER(ContribList), vp, c_int, c_int, vp, vp, c_int, vp, c_int64]
+    L.dc_plan_build.argtypes = [POINTER(Plan), vp, c_int, c_int, vp, vp, c_int, vp, c_int64, c_int, c_int, c_int]
+    L.dc_contrib_build.argtypes = [POINTER(ContribList), vp, c_int, c_int, vp, vp, c_int, vp, c_int64, c_int]
     L.dc_plan_free.argtypes = [POINTER(Plan)]
     L.dc_plan_free.restype = None
     L.dc_contrib_free.argtypes = [POINTER(ContribList)]
@@ -243,12 +245,15 @@ def flatten_tree():
 class HostPlan:
     """Owns a dc_plan_t built by dc_plan_build()."""
 
-    def __init__(self, conn, nbNodes, row, col, colBase, treeRec, maxSlots=832, nbThreads=0):
+    def __init__(self, conn, nbNodes, row, col, colBase, treeRec, maxSlots=400, nbThreads=0, symmetric=True):
+        """symmetric=True: every off-diagonal block is computed once, by the lane of the upper edge
+        (row < col), which also stores its transpose (operators with bitwise symmetric element
+        matrices); False: one lane per edge, every unit writes exactly its own edge interval."""
         self.c = Plan()
         conn = np.ascontiguousarray(conn, dtype=np.int32)
         nrec = 0 if treeRec is None else treeRec.shape[0]
         rc = lib().dc_plan_build(byref(self.c), _p(conn), conn.shape[0], nbNodes, _p(row), _p(col), colBase,
-                                 _p(treeRec), nrec, maxSlots, nbThreads)
+                                 _p(treeRec), nrec, maxSlots, nbThreads, 1 if symmetric else 0)
         if rc:
             raise RuntimeError(f"dc_plan_build failed with code {rc}")
 
@@ -264,17 +269,19 @@ class HostPlan:
             a = a.view(dtype)
             return a if width == 1 else a.reshape(count, width)
 
-        return dict(units=view(c.units, c.nbUnits, np.uint8, 64), tasks=view(c.tasks, c.nbTasks, np.uint8, 16),
+        return dict(units=view(c.units, c.nbUnits, np.uint8, 80), tasks=view(c.tasks, c.nbTasks, np.uint8, 16),
                     items=view(c.items, c.nbItems, np.uint16), halo=view(c.haloElems, c.nbHalo, np.int32),
+                    tgt=view(c.tgt, c.nbTgt, np.int32, 2),
                     nbUnits=int(c.nbUnits), maxSlots=int(c.maxSlots), maxHalo=int(c.maxHalo),
-                    maxTasks=int(c.maxTasks), maxItems=int(c.maxItems), bigEdges=int(c.big.nbEdges))
+                    maxTasks=int(c.maxTasks), maxItems=int(c.maxItems), maxTgt=int(c.maxTgt),
+                    symmetric=int(c.symmetric), bigEdges=int(c.big.nbEdges))
 
     def diag_rel(self, nbNodes):
         return np.ctypeslib.as_array(self.c.diagRel, shape=(max(nbNodes, 1),))[:nbNodes]
 
     def stats(self):
         c = self.c
-        return dict(units=c.nbUnits, tasks=c.nbTasks, items=c.nbItems, items_useful=c.nbItemsUseful,
+        return dict(units=c.nbUnits, tasks=c.nbTasks, items=c.nbItems, items_useful=c.nbItemsUseful, symmetric=c.symmetric,
                     halo=c.nbHalo, slots_total=c.nbSlotsTotal, max_slots=c.maxSlots, big_edges=c.big.nbEdges)
 
     def __del__(self):
@@ -322,8 +329,9 @@ class Context:
         """t: dict of torch CUDA tensors {units,tasks,items,halo,diagRel} + ints {nbUnits,maxSlots,maxHalo,maxTasks,maxItems}."""
         self._keep_plan = t
         self._ck(lib().dc_cuda_set_plan_device(self.h, _p(t["units"]), _p(t["tasks"]), _p(t["items"]), _p(t["halo"]),
-                                               _p(t["diagRel"]), t["nbUnits"], t["maxSlots"], t["maxHalo"],
-                                               t["maxTasks"], t["maxItems"]), "dc_cuda_set_plan_device")
+                                               _p(t["diagRel"]), _p(t["tgt"]), t["nbUnits"], t["maxSlots"],
+                                               t["maxHalo"], t["maxTasks"], t["maxItems"], t["maxTgt"],
+                                               t["symmetric"]), "dc_cuda_set_plan_device")
 
     def download_range(self, d_values, first, count, h_buf, stream=None):
         self._ck(lib().dc_cuda_download_range(_p(d_values), first, count, _p(h_buf), stream), "dc_cuda_download_range")
@@ -334,7 +342,7 @@ class Context:
     def upload_lists(self, conn, nbNodes, row, col, colBase=0):
         cl = ContribList()
         conn = np.ascontiguousarray(conn, dtype=np.int32)
-        rc = lib().dc_contrib_build(byref(cl), _p(conn), conn.shape[0], nbNodes, _p(row), _p(col), colBase, None, 0)
+        rc = lib().dc_contrib_build(byref(cl), _p(conn), conn.shape[0], nbNodes, _p(row), _p(col), colBase, None, 0, 0)
         if rc:
             raise RuntimeError(f"dc_contrib_build failed with code {rc}")
         try:

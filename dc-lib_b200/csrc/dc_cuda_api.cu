@@ -37,7 +37,9 @@ struct dc_cuda_ctx {
     int *d_conn = nullptr, *d_row = nullptr, *d_col = nullptr;
     double *d_coord = nullptr;
     /* plan */
-    int maxSlots = 0, maxHalo = 0, maxTasks = 0, maxItems = 0;
+    int maxSlots = 0, maxHalo = 0, maxTasks = 0, maxItems = 0, maxTgt = 0, symmetric = 0;
+    int *d_tgt = nullptr;
+    int64_t *d_bigEdgeT = nullptr;
     int threads = 256;       /* CTA size of the unit kernel (128 or 256) */
     int64_t nbUnits = 0, nbBigEdges = 0;
     bool ownsPlan = true;
@@ -97,9 +99,11 @@ static void free_mesh(dc_cuda_ctx *c)
 static void free_plan(dc_cuda_ctx *c)
 {
     if (!c->ownsPlan) {
-        c->d_units = nullptr; c->d_tasks = nullptr; c->d_items = nullptr; c->d_halo = c->d_diagRel = nullptr;
+        c->d_units = nullptr; c->d_tasks = nullptr; c->d_items = nullptr; c->d_halo = c->d_diagRel = c->d_tgt = nullptr;
         c->ownsPlan = true;
     }
+    cudaFree(c->d_tgt); cudaFree(c->d_bigEdgeT);
+    c->d_tgt = nullptr; c->d_bigEdgeT = nullptr;
     cudaFree(c->d_units); cudaFree(c->d_tasks); cudaFree(c->d_items); cudaFree(c->d_halo);
     cudaFree(c->d_diagRel); cudaFree(c->d_bigEdge); cudaFree(c->d_bigPtr); cudaFree(c->d_bigItem);
     c->d_units = nullptr; c->d_tasks = nullptr; c->d_items = nullptr; c->d_halo = c->d_diagRel = nullptr;
@@ -186,6 +190,9 @@ extern "C" int dc_cuda_upload_plan(dc_cuda_ctx *c, const struct dc_plan_s *p)
     if ((rc = upload(&c->d_items, p->items, p->nbItems))) return rc;
     if ((rc = upload(&c->d_halo, p->haloElems, p->nbHalo))) return rc;
     if ((rc = upload(&c->d_diagRel, p->diagRel, (int64_t)c->nbNodes))) return rc;
+    if ((rc = upload(&c->d_tgt, p->tgt, 2 * p->nbTgt))) return rc;
+    if (p->big.nbEdges > 0 && p->big.edgeT)
+        if ((rc = upload(&c->d_bigEdgeT, p->big.edgeT, p->big.nbEdges))) return rc;
     if (p->big.nbEdges > 0) {
         if ((rc = upload(&c->d_bigEdge, p->big.edge, p->big.nbEdges))) return rc;
         if ((rc = upload(&c->d_bigPtr, p->big.ptr, p->big.nbEdges + 1))) return rc;
@@ -197,12 +204,15 @@ extern "C" int dc_cuda_upload_plan(dc_cuda_ctx *c, const struct dc_plan_s *p)
     c->maxHalo = p->maxHalo;
     c->maxTasks = p->maxTasks;
     c->maxItems = p->maxItems;
+    c->maxTgt = p->maxTgt;
+    c->symmetric = p->symmetric;
     return 0;
 }
 
 extern "C" int dc_cuda_set_plan_device(dc_cuda_ctx *c, const void *d_units, const void *d_tasks,
                                        const void *d_items, const int *d_halo, const int *d_diagRel,
-                                       int64_t nbUnits, int maxSlots, int maxHalo, int maxTasks, int maxItems)
+                                       const int *d_tgt, int64_t nbUnits, int maxSlots, int maxHalo,
+                                       int maxTasks, int maxItems, int maxTgt, int symmetric)
 {
     if (!c) return fail(-1, "dc_cuda_set_plan_device: null context");
     if ((reinterpret_cast<uintptr_t>(d_units) | reinterpret_cast<uintptr_t>(d_tasks) |
@@ -216,9 +226,11 @@ extern "C" int dc_cuda_set_plan_device(dc_cuda_ctx *c, const void *d_units, cons
     c->d_items = (uint16_t *)d_items;
     c->d_halo = const_cast<int *>(d_halo);
     c->d_diagRel = const_cast<int *>(d_diagRel);
+    c->d_tgt = const_cast<int *>(d_tgt);
     c->nbUnits = nbUnits;
     c->nbBigEdges = 0;
     c->maxSlots = maxSlots; c->maxHalo = maxHalo; c->maxTasks = maxTasks; c->maxItems = maxItems;
+    c->maxTgt = maxTgt; c->symmetric = symmetric;
     return 0;
 }
 
@@ -236,15 +248,16 @@ extern "C" int dc_cuda_upload_lists(dc_cuda_ctx *c, const int64_t *h_edge, const
     return 0;
 }
 
-template <class Op, int THREADS, int MINB>
+template <class Op, int THREADS, int MINB, bool SYM>
 static int launch_units(dc_cuda_ctx *c, double *d_values, cudaStream_t s)
 {
-    const UnitLayout L = UnitSmem<Op>::layout(c->maxSlots, c->maxHalo, c->maxTasks, c->maxItems, THREADS);
+    const UnitLayout L = UnitSmem<Op>::layout(c->maxSlots, c->maxHalo, c->maxTasks, c->maxItems, c->maxTgt, THREADS);
     if (L.total > 227 * 1024) return fail(-11, "dc_cuda_assemble: unit does not fit in shared memory");
-    auto kern = gather_units<Op, THREADS, MINB>;
+    auto kern = gather_units<Op, THREADS, MINB, SYM>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
     kern<<<(unsigned)c->nbUnits, THREADS, (size_t)L.total, s>>>(c->d_units, c->d_tasks, c->d_items, c->d_halo,
-                                                                 c->d_diagRel, c->d_conn, c->d_coord, d_values, L);
+                                                                 c->d_diagRel, reinterpret_cast<const int2 *>(c->d_tgt),
+                                                                 c->d_conn, c->d_coord, d_values, L);
     return 0;
 }
 
@@ -255,14 +268,21 @@ static int assemble_t(dc_cuda_ctx *c, int mode, double *d_values, cudaStream_t s
     if (mode == DC_MODE_DETERMINISTIC) {
         if (!c->d_units && c->nbBigEdges == 0) return fail(-6, "dc_cuda_assemble: no plan uploaded");
         if (c->nbUnits > 0) {
-            int rc = (c->threads == 128) ? launch_units<Op, 128, 4>(c, d_values, s)
-                                         : launch_units<Op, 256, 2>(c, d_values, s);
+            if (c->symmetric && !Op::SYMMETRIC)
+                return fail(-13, "dc_cuda_assemble: symmetric schedule with a non-symmetric operator");
+            int rc;
+            if (c->symmetric)
+                rc = (c->threads == 128) ? launch_units<Op, 128, 4, true>(c, d_values, s)
+                                         : launch_units<Op, 256, 2, true>(c, d_values, s);
+            else
+                rc = (c->threads == 128) ? launch_units<Op, 128, 4, false>(c, d_values, s)
+                                         : launch_units<Op, 256, 2, false>(c, d_values, s);
             if (rc) return rc;
             c->launches++;
         }
         if (c->nbBigEdges > 0) {
             gather_lists<Op><<<(unsigned)((c->nbBigEdges + 127) / 128), 128, 0, s>>>(
-                c->d_bigEdge, c->d_bigPtr, c->d_bigItem, c->nbBigEdges, c->d_conn, c->d_coord, d_values);
+                c->d_bigEdge, c->d_bigPtr, c->d_bigItem, c->d_bigEdgeT, c->nbBigEdges, c->d_conn, c->d_coord, d_values);
             c->launches++;
         }
     } else if (mode == DC_MODE_ATOMIC) {
@@ -274,7 +294,8 @@ static int assemble_t(dc_cuda_ctx *c, int mode, double *d_values, cudaStream_t s
     } else if (mode == DC_MODE_LIST) {
         if (!c->d_listPtr) return fail(-6, "dc_cuda_assemble: no contribution lists uploaded");
         gather_lists<Op><<<(unsigned)((c->nbListEdges + 127) / 128), 128, 0, s>>>(
-            c->d_listEdge, c->d_listPtr, c->d_listItem, c->nbListEdges, c->d_conn, c->d_coord, d_values);
+            c->d_listEdge, c->d_listPtr, c->d_listItem, (const int64_t *)nullptr, c->nbListEdges, c->d_conn, c->d_coord,
+            d_values);
         c->launches++;
     } else {
         return fail(-7, "dc_cuda_assemble: unknown mode");

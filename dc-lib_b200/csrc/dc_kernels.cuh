@@ -91,6 +91,7 @@ struct UnitLayout {
     int offStage;    /* region A: own connectivity (TMA target), later per-warp output staging */
     int offHalo;     /* halo element ids                                                     */
     int offTasks;    /* dc_task_t records                                                    */
+    int offTgt;      /* symmetric schedule: (edge, transposed edge) pairs                    */
     int offItems;    /* uint16 items                                                         */
     int offRecs;     /* element records                                                      */
     int total;
@@ -102,27 +103,46 @@ struct UnitSmem {
     /* record stride in doubles: an odd number of 8-byte words keeps 64-bit accesses of
      * different slots spread over the banks */
     static constexpr int RS = (Op::NS % 2 == 0) ? Op::NS + 1 : Op::NS;
-    static UnitLayout layout(int maxSlots, int maxHalo, int maxTasks, int maxItems, int threads)
+    /* per-warp staging: 32 blocks + 32 target edges */
+    static constexpr int STAGE = 32 * DD * 8 + 32 * 4;
+    static UnitLayout layout(int maxSlots, int maxHalo, int maxTasks, int maxItems, int maxTgt, int threads)
     {
         auto up = [](int v) { return (v + 15) & ~15; };
         UnitLayout L;
-        const int a = maxSlots * 16, b = (threads / 32) * 32 * DD * 8;
+        const int a = maxSlots * 16, b = (threads / 32) * STAGE;
         L.offStage = 32;
         L.offHalo = L.offStage + up(a > b ? a : b);
         L.offTasks = L.offHalo + up(maxHalo * 4);
-        L.offItems = L.offTasks + up(maxTasks * 16);
+        L.offTgt = L.offTasks + up(maxTasks * 16);
+        L.offItems = L.offTgt + up(maxTgt * 8);
         L.offRecs = L.offItems + up(maxItems * 2);
         L.total = L.offRecs + maxSlots * RS * 8;
         return L;
     }
 };
 
-template <class Op, int THREADS, int MINB>
+/* store the 32 staged blocks of a warp: idx runs over the 32*DD doubles so that consecutive
+ * lanes write consecutive addresses inside a block (and across blocks of consecutive edges) */
+template <int DD>
+__device__ __forceinline__ void flush_stage(double *__restrict__ values, const double *stage, const int *tgt,
+                                            int lane)
+{
+#pragma unroll
+    for (int r = 0; r < DD; r++) {
+        const int idx = r * 32 + lane;
+        const int ent = idx / DD;
+        const int t = tgt[ent];
+        if (t >= 0) st_stream_f64(values + (int64_t)t * DD + (idx - ent * DD), stage[idx]);
+    }
+}
+
+template <class Op, int THREADS, int MINB, bool SYM>
 __global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *__restrict__ units,
                                                               const dc_task_t *__restrict__ tasks,
                                                               const uint16_t *__restrict__ items,
                                                               const int *__restrict__ haloElems,
                                                               const int *__restrict__ diagRel,
+                                                              const int2 *__restrict__ tgtPairs,
                                                               const int *__restrict__ conn,
                                                               const double *__restrict__ coord,
                                                               double *__restrict__ values, const UnitLayout L)
@@ -133,9 +153,9 @@ __global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *_
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);          /* bar[0]: mesh data, bar[1]: schedule */
     int4 *connS = reinterpret_cast<int4 *>(smem_raw + L.offStage);
-    double *stage = reinterpret_cast<double *>(smem_raw + L.offStage);
     int *haloS = reinterpret_cast<int *>(smem_raw + L.offHalo);
     dc_task_t *taskS = reinterpret_cast<dc_task_t *>(smem_raw + L.offTasks);
+    int2 *tgtS = reinterpret_cast<int2 *>(smem_raw + L.offTgt);
     uint16_t *itemS = reinterpret_cast<uint16_t *>(smem_raw + L.offItems);
     double *recs = reinterpret_cast<double *>(smem_raw + L.offRecs);
 
@@ -144,7 +164,7 @@ __global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *_
     const int nSlots = u.ownElemCount + u.haloCount;
 
     /* P0: everything the unit reads that is contiguous in HBM comes in as TMA bulk copies:
-     * own connectivity rows (tree order makes them one range), halo ids, tasks, items */
+     * own connectivity rows (tree order makes them one range), halo ids, tasks, items, targets */
     if (tid == 0) {
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
@@ -157,9 +177,11 @@ __global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *_
         if (ownBytes) tma_bulk_g2s(connS, reinterpret_cast<const int4 *>(conn) + u.ownElemFirst, ownBytes, &bar[0]);
         if (haloBytes) tma_bulk_g2s(haloS, haloElems + u.haloFirst, haloBytes, &bar[0]);
         const uint32_t taskBytes = (uint32_t)u.taskCount * 16u, itemBytes = (uint32_t)u.itemCount * 2u;
-        mbar_expect_tx(&bar[1], taskBytes + itemBytes);
+        const uint32_t tgtBytes = SYM ? (uint32_t)((u.tgtCount + 1) & ~1) * 8u : 0u;
+        mbar_expect_tx(&bar[1], taskBytes + itemBytes + tgtBytes);
         if (taskBytes) tma_bulk_g2s(taskS, tasks + u.taskFirst, taskBytes, &bar[1]);
         if (itemBytes) tma_bulk_g2s(itemS, items + u.itemFirst, itemBytes, &bar[1]);
+        if (tgtBytes) tma_bulk_g2s(tgtS, tgtPairs + u.tgtFirst, tgtBytes, &bar[1]);
     }
     mbar_wait(&bar[0], 0);
 
@@ -198,65 +220,63 @@ __global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *_
     mbar_wait(&bar[1], 0);
     __syncthreads();   /* records complete; region A is free for staging from here on */
 
-    /* P2: tasks round-robin over warps; a lane owns one CSR edge and sums its
-     * contributions in ascending element order (the order of the item rows) */
-    double *myStage = stage + warp * 32 * DD;
-    double *out = values + u.edgeFirst * DD;
+    /* P2: tasks round-robin over warps; a lane owns one CSR edge and adds its contributions
+     * in ascending element order (the order of the item rows) */
+    double *myStage = reinterpret_cast<double *>(smem_raw + L.offStage + warp * UnitSmem<Op>::STAGE);
+    int *myTgt = reinterpret_cast<int *>(myStage + 32 * DD);
     for (int t = warp; t < u.taskCount; t += NW) {
         const dc_task_t task = taskS[t];
         const uint16_t *it = itemS + task.itemRel + lane;
         double acc[DD];
 #pragma unroll
         for (int c = 0; c < DD; c++) acc[c] = 0.0;
-        /* two contributions in flight per lane: the blocks are independent, only the
-         * final adds into acc are ordered (ascending element = item row order) */
-        int i = 0;
-        for (; i + 1 < task.iters; i += 2) {
-            const uint32_t cur0 = it[i * 32], cur1 = it[(i + 1) * 32];
-            double blk0[DD], blk1[DD];
-            if (cur0 != DC_ITEM_NULL) Op::block(recs + (cur0 >> 4) * RS, c_params, cur0 & 15u, blk0);
-            if (cur1 != DC_ITEM_NULL) Op::block(recs + (cur1 >> 4) * RS, c_params, cur1 & 15u, blk1);
-            if (cur0 != DC_ITEM_NULL) {
-#pragma unroll
-                for (int c = 0; c < DD; c++) acc[c] = __dadd_rn(acc[c], blk0[c]);
-            }
-            if (cur1 != DC_ITEM_NULL) {
-#pragma unroll
-                for (int c = 0; c < DD; c++) acc[c] = __dadd_rn(acc[c], blk1[c]);
-            }
-        }
-        if (i < task.iters) {
+        for (int i = 0; i < task.iters; i++) {
             const uint32_t cur = it[i * 32];
-            if (cur != DC_ITEM_NULL) {
-                double blk[DD];
-                Op::block(recs + (cur >> 4) * RS, c_params, cur & 15u, blk);
-#pragma unroll
-                for (int c = 0; c < DD; c++) acc[c] = __dadd_rn(acc[c], blk[c]);
-            }
+            if (cur != DC_ITEM_NULL) Op::accumulate(recs + (cur >> 4) * RS, c_params, cur & 15u, acc);
         }
-        if (task.kind == DC_TASK_EDGES) {
-            if (DD == 1) {
-                const int e = (int)task.first + lane;
-                if (e < u.edgeCount && !((task.mask >> lane) & 1u)) st_stream_f64(out + e, acc[0]);
-            } else {
-#pragma unroll
-                for (int c = 0; c < DD; c++) myStage[lane * DD + c] = acc[c];
-                __syncwarp();
-                const int remaining = u.edgeCount - (int)task.first;   /* edges of this task that exist */
-#pragma unroll
-                for (int r = 0; r < DD; r++) {
-                    const int idx = r * 32 + lane;
-                    const int ent = idx / DD;
-                    if (ent < remaining && !((task.mask >> ent) & 1u))
-                        st_stream_f64(out + (int64_t)task.first * DD + idx, myStage[idx]);
-                }
-                __syncwarp();
-            }
-        } else {
+        if (task.kind == DC_TASK_DIAG) {
             if ((task.mask >> lane) & 1u) {
                 const int d = __ldg(diagRel + u.nodeFirst + (int)task.first + lane);
 #pragma unroll
-                for (int c = 0; c < DD; c++) st_stream_f64(out + (int64_t)d * DD + c, acc[c]);
+                for (int c = 0; c < DD; c++) st_stream_f64(values + (u.edgeFirst + d) * DD + c, acc[c]);
+            }
+        } else if (SYM) {
+            /* upper edge: block to (row,col), transposed block to (col,row) */
+            const bool valid = (task.mask >> lane) & 1u;
+            int2 tg = make_int2(-1, -1);
+            if (valid) tg = tgtS[(int)task.first + lane];
+            if (DD == 1) {
+                if (valid) {
+                    st_stream_f64(values + tg.x, acc[0]);
+                    st_stream_f64(values + tg.y, acc[0]);
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < DD; c++) myStage[lane * DD + c] = acc[c];
+                myTgt[lane] = tg.x;
+                __syncwarp();
+                flush_stage<DD>(values, myStage, myTgt, lane);
+                __syncwarp();
+#pragma unroll
+                for (int c = 0; c < DD; c++) myStage[lane * DD + (c % Op::D) * Op::D + c / Op::D] = acc[c];
+                myTgt[lane] = tg.y;
+                __syncwarp();
+                flush_stage<DD>(values, myStage, myTgt, lane);
+                __syncwarp();
+            }
+        } else {
+            /* 32 consecutive edges of the unit's own interval (diagonal lanes skipped) */
+            const int e = (int)task.first + lane;
+            const bool valid = e < u.edgeCount && !((task.mask >> lane) & 1u);
+            if (DD == 1) {
+                if (valid) st_stream_f64(values + u.edgeFirst + e, acc[0]);
+            } else {
+#pragma unroll
+                for (int c = 0; c < DD; c++) myStage[lane * DD + c] = acc[c];
+                myTgt[lane] = valid ? (int)(u.edgeFirst + e) : -1;
+                __syncwarp();
+                flush_stage<DD>(values, myStage, myTgt, lane);
+                __syncwarp();
             }
         }
     }
@@ -267,7 +287,8 @@ __global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *_
 template <class Op>
 __global__ void __launch_bounds__(128) gather_lists(const int64_t *__restrict__ edge,
                                                     const int64_t *__restrict__ ptr,
-                                                    const uint32_t *__restrict__ item, int64_t nbEdges,
+                                                    const uint32_t *__restrict__ item,
+                                                    const int64_t *__restrict__ edgeT, int64_t nbEdges,
                                                     const int *__restrict__ conn,
                                                     const double *__restrict__ coord,
                                                     double *__restrict__ values)
@@ -280,15 +301,18 @@ __global__ void __launch_bounds__(128) gather_lists(const int64_t *__restrict__ 
     for (int c = 0; c < DD; c++) acc[c] = 0.0;
     for (int64_t q = ptr[i]; q < ptr[i + 1]; q++) {
         const uint32_t it = __ldg(item + q);
-        double rec[Op::NS], blk[DD];
+        double rec[Op::NS];
         load_element<Op>(conn, coord, (int64_t)(it >> 4), rec);
-        Op::block(rec, c_params, it & 15u, blk);
-#pragma unroll
-        for (int c = 0; c < DD; c++) acc[c] = __dadd_rn(acc[c], blk[c]);
+        Op::accumulate(rec, c_params, it & 15u, acc);
     }
     double *dst = values + edge[i] * DD;
 #pragma unroll
     for (int c = 0; c < DD; c++) dst[c] = acc[c];
+    if (edgeT && edgeT[i] >= 0) {          /* symmetric lists: the transposed block goes to (col,row) */
+        double *dt = values + edgeT[i] * DD;
+#pragma unroll
+        for (int c = 0; c < DD; c++) dt[(c % Op::D) * Op::D + c / Op::D] = acc[c];
+    }
 }
 
 /* ---- fast mode: one thread per element, red.global.add.f64 --------------- */
@@ -317,7 +341,9 @@ __global__ void __launch_bounds__(128) scatter_atomic(const int *__restrict__ co
             while (k < r1 && __ldg(col + k) != target) k++;
             if (k == r1) continue;
             double blk[DD];
-            Op::block(rec, c_params, (uint32_t)(4 * a + b), blk);
+#pragma unroll
+            for (int q = 0; q < DD; q++) blk[q] = 0.0;
+            Op::accumulate(rec, c_params, (uint32_t)(4 * a + b), blk);   /* = K_e[a][b] */
             double *dst = values + (int64_t)k * DD;
 #pragma unroll
             for (int q = 0; q < DD; q++) red_add_f64(dst + q, blk[q]);

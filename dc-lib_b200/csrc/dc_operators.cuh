@@ -5,9 +5,13 @@
  * and `+=`s it into nodeToNodeValue.  Host function pointers cannot run on the
  * GPU, so the callbacks are replaced by device operators with this contract:
  *
- *   setup(x[4][3], params, rec)        once per element: whatever the operator wants
- *                                      to keep for its 16 blocks, NS doubles;
- *   block(rec, params, 4*a+b, out[D*D]) the D x D block K_e[a][b] from that record.
+ *   setup(x[4][3], params, rec)         once per element: whatever the operator wants
+ *                                       to keep for its 16 blocks, NS doubles;
+ *   accumulate(rec, params, 4*a+b, acc) acc[D*D] += K_e[a][b], the `+=` of the host
+ *                                       callback, in the operator's own fixed sequence;
+ *   SYMMETRIC                           K_e[b][a] == transpose(K_e[a][b]) bit for bit and
+ *                                       accumulate keeps that, so the symmetric schedule
+ *                                       may compute (a,b) once and store the transpose.
  *
  * Every product / fma / sum is written with an explicit rounding intrinsic so
  * that nvcc cannot contract or reassociate: the sequence is the operator's
@@ -77,19 +81,24 @@ struct OpLaplacian {
                 rec[q++] = __dmul_rn(vol, d);
             }
     }
+    static constexpr bool SYMMETRIC = true;
     /* ab = 4*a+b */
     template <typename R>
-    __device__ __forceinline__ static void block(R rec, const double *, uint32_t ab, double (&out)[1])
+    __device__ __forceinline__ static void accumulate(R rec, const double *, uint32_t ab, double (&acc)[1])
     {
         const uint32_t q = (uint32_t)(0x9863875265413210ULL >> (4 * ab)) & 15u;
-        out[0] = rec[q];
+        acc[0] = __dadd_rn(acc[0], rec[q]);
     }
 };
 
 /* Isotropic linear elasticity, 3x3 blocks, volume folded symmetrically into the gradients:
- * h_a = g_a * sqrt(vol); p[i][j] = ha_i*hb_j; dot = (p00+p11)+p22;
- * K[a][b][i][j] = fma(mu, p[j][i], lambda*p[i][j]), diagonal: fma(mu, dot, that).
- * params = {lambda, mu}.  The record is the 12 scaled gradient components. */
+ * h_a = g_a * sqrt(vol); p[i][j] = ha_i*hb_j; dot = (p00+p11)+p22; the scatter-add of block
+ * (a,b) into its CSR entry v is, per component,
+ *     v[i][j] = fma(lambda, p[i][j], v[i][j]);  v[i][j] = fma(mu, p[j][i], v[i][j]);
+ *     and for i == j:  v[i][i] = fma(mu, dot, v[i][i]);
+ * (= v += vol*(lambda ga_i gb_j + mu ga_j gb_i + delta_ij mu ga.gb), three fused updates).
+ * Swapping a and b transposes p bit for bit, so block (b,a) receives exactly the transposed
+ * updates.  params = {lambda, mu}.  The record is the 12 scaled gradient components. */
 struct OpElasticity {
     static constexpr int D = 3;
     static constexpr int NS = 12;
@@ -102,8 +111,9 @@ struct OpElasticity {
 #pragma unroll
         for (int i = 0; i < 12; i++) rec[i] = __dmul_rn(rec[i], s);
     }
+    static constexpr bool SYMMETRIC = true;
     template <typename R>
-    __device__ __forceinline__ static void block(R rec, const double *params, uint32_t ab, double (&out)[9])
+    __device__ __forceinline__ static void accumulate(R rec, const double *params, uint32_t ab, double (&acc)[9])
     {
         const uint32_t a = ab >> 2, b = ab & 3u;
         const double ga[3] = {rec[3 * a], rec[3 * a + 1], rec[3 * a + 2]};
@@ -119,9 +129,10 @@ struct OpElasticity {
         for (int i = 0; i < 3; i++)
 #pragma unroll
             for (int j = 0; j < 3; j++) {
-                double v = __fma_rn(mu, p[j][i], __dmul_rn(lam, p[i][j]));
+                double v = __fma_rn(lam, p[i][j], acc[i * 3 + j]);
+                v = __fma_rn(mu, p[j][i], v);
                 if (i == j) v = __fma_rn(mu, dot, v);
-                out[i * 3 + j] = v;
+                acc[i * 3 + j] = v;
             }
     }
 };

@@ -22,8 +22,10 @@
 
 #define DC_ITEM_NULL   0xFFFFu      /* padding entry of an item row              */
 #define DC_SLOT_LIMIT  4095         /* slots are 12-bit: item = slot<<4 | a<<2 | b */
-#define DC_TASK_EDGES  0            /* 32 consecutive edges of the unit            */
-#define DC_TASK_DIAG   1            /* the diagonal edges of 32 consecutive nodes  */
+#define DC_TASK_EDGES  0            /* 32 consecutive edges of the unit (general schedule)   */
+#define DC_TASK_DIAG   1            /* the diagonal edges of 32 consecutive nodes            */
+#define DC_TASK_UPPER  2            /* 32 upper edges (col > row): symmetric schedule, the    */
+                                    /* lane also writes the transposed block to (col,row)   */
 
 typedef struct {
     int64_t edgeFirst;      /* first CSR edge of the unit                          */
@@ -35,7 +37,10 @@ typedef struct {
     int32_t haloCount;                    /* slots [ownElemCount, +haloCount)       */
     int32_t taskFirst, taskCount;
     int32_t itemCount;                    /* uint16 items of the unit (multiple of 32) */
-} dc_unit_t;                /* 64 bytes */
+    int64_t tgtFirst;                     /* symmetric schedule: first (edge, transposed edge) pair */
+    int32_t tgtCount;                     /* upper edges of the unit                               */
+    int32_t pad_;
+} dc_unit_t;                /* 80 bytes */
 
 typedef struct {
     uint32_t itemRel;       /* items of this task start at unit.itemFirst+itemRel  */
@@ -43,7 +48,8 @@ typedef struct {
     uint16_t kind;          /* DC_TASK_EDGES / DC_TASK_DIAG                        */
     uint32_t mask;          /* EDGES: lanes that are diagonal edges (skipped);     */
                             /* DIAG : lanes that hold a node                       */
-    uint32_t first;         /* EDGES: edge offset in unit; DIAG: node offset       */
+    uint32_t first;         /* EDGES: edge offset in unit; DIAG: node offset;      */
+                            /* UPPER: index of the first upper edge of the unit    */
 } dc_task_t;                /* 16 bytes */
 
 /* Fallback list for rows too large for a unit (and for generic operators):
@@ -54,6 +60,8 @@ typedef struct {
     int64_t *edge;          /* [nbEdges]   CSR edge index                          */
     int64_t *ptr;           /* [nbEdges+1] offsets into item                       */
     uint32_t *item;         /* [nbItems]                                           */
+    int64_t *edgeT;         /* [nbEdges] symmetric lists: edge that receives the   */
+                            /* transposed block, -1 for none; NULL otherwise       */
 } dc_contrib_list_t;
 
 typedef struct dc_plan_s {
@@ -61,6 +69,10 @@ typedef struct dc_plan_s {
     int32_t  maxHalo;       /* largest halo list (entries, padded to 4)            */
     int32_t  maxTasks;      /* most tasks in one unit                              */
     int32_t  maxItems;      /* most uint16 items in one unit                       */
+    int32_t  maxTgt;        /* most upper edges in one unit (symmetric schedule)   */
+    int32_t  symmetric;     /* 1: UPPER tasks + tgt pairs, 0: EDGES tasks          */
+    int64_t  nbTgt;         /* pairs in tgt                                        */
+    int32_t *tgt;           /* [nbTgt][2] (edge of (row,col), edge of (col,row))   */
     int64_t  nbUnits, nbTasks, nbItems, nbHalo;
     dc_unit_t *units;
     dc_task_t *tasks;
@@ -83,10 +95,10 @@ extern "C" {
  * dc_plan_build_from_tree for the pointer-tree front end.  Returns 0 on success. */
 int  dc_plan_build(dc_plan_t *plan, const int *conn, int nbElem, int nbNodes, const int *row,
                    const int *col, int colBase, const int *treeRec, int64_t nbTreeRec,
-                   int maxSlots, int nbThreads);
+                   int maxSlots, int nbThreads, int symmetric);
 int  dc_contrib_build(dc_contrib_list_t *out, const int *conn, int nbElem, int nbNodes,
                       const int *row, const int *col, int colBase, const int *rows,
-                      int64_t nbRows);
+                      int64_t nbRows, int symmetric);
 void dc_plan_free(dc_plan_t *plan);
 void dc_contrib_free(dc_contrib_list_t *c);
 #ifdef __cplusplus

@@ -13,7 +13,8 @@ namespace {
 
 dc_cuda_ctx *g_ctx = nullptr;
 int g_mode = DC_DEVICE_DETERMINISTIC;
-int g_maxSlots = 832;
+int g_maxSlots = 400;
+int g_symmetric = 1;     /* both built-in operators have bitwise symmetric element matrices */
 
 [[noreturn]] void die(const char *what)
 {
@@ -79,7 +80,7 @@ void DC_device_set_mesh (const double *coord, const int *elemToNode, const int *
     flatten(treeHead, rec);
     dc_plan_t plan;
     int rc = dc_plan_build(&plan, elemToNode, nbElem, nbNodes, nodeToNodeRow, nodeToNodeColumn, colBase,
-                           rec.data(), (int64_t)rec.size() / 8, g_maxSlots, dc::options().nbThreads);
+                           rec.data(), (int64_t)rec.size() / 8, g_maxSlots, dc::options().nbThreads, g_symmetric);
     if (rc) {
         fprintf(stderr, "Error: DC_device_set_mesh: cannot build the device schedule (code %d).\n", rc);
         exit(EXIT_FAILURE);

@@ -161,8 +161,18 @@ struct Selector {
 struct UnitOut {
     std::vector<dc_task_t> tasks;
     std::vector<uint16_t> items;
+    std::vector<int32_t> tgt;      /* symmetric schedule: (edge, transposed edge) per upper edge */
     int64_t useful = 0;
 };
+
+/* edge index of (rowNode, colNode) */
+inline int find_edge(const Mesh &m, int rowNode, int colNode)
+{
+    const int target = colNode + m.colBase;
+    for (int k = m.row[rowNode]; k < m.row[rowNode + 1]; k++)
+        if (m.col[k] == target) return k;
+    return -1;
+}
 
 inline int slot_of(const UnitSeed &s, int e)
 {
@@ -172,7 +182,7 @@ inline int slot_of(const UnitSeed &s, int e)
 
 /* items of every edge of the unit, grouped per edge in ascending element order */
 void build_unit(const Mesh &m, const UnitSeed &s, int32_t *diagRel, UnitOut &out,
-                std::vector<std::vector<uint16_t>> &perEdge, int &error)
+                std::vector<std::vector<uint16_t>> &perEdge, int &error, bool symmetric)
 {
     const int64_t edgeFirst = m.row[s.nodeFirst];
     const int edgeCount = m.row[s.nodeFirst + s.nodeCount] - (int)edgeFirst;
@@ -195,6 +205,7 @@ void build_unit(const Mesh &m, const UnitSeed &s, int32_t *diagRel, UnitOut &out
             while (a < 4 && c[a] - 1 != n) a++;
             const int slot = slot_of(s, e);
             for (int b = 0; b < 4; b++) {
+                if (symmetric && c[b] - 1 < n) continue;  /* lower edges are written as transposes */
                 const int target = c[b] - 1 + m.colBase;
                 int k = r0;
                 while (k < r1 && m.col[k] != target) k++;
@@ -203,9 +214,45 @@ void build_unit(const Mesh &m, const UnitSeed &s, int32_t *diagRel, UnitOut &out
             }
         }
     }
+    if (symmetric) {
+        /* upper-edge tasks: the unit's edges with col > row in (row, position) order, 32 per task;
+         * each lane also owns the transposed edge (col,row), wherever that row lives */
+        std::vector<int> upper;
+        for (int n = s.nodeFirst; n < s.nodeFirst + s.nodeCount; n++)
+            for (int k = m.row[n]; k < m.row[n + 1]; k++) {
+                const int c = m.col[k] - m.colBase;
+                if (c <= n) continue;
+                const int kt = find_edge(m, c, n);
+                if (kt < 0) { error = 1; continue; }      /* pattern is not structurally symmetric */
+                upper.push_back((int)(k - edgeFirst));
+                out.tgt.push_back(k);
+                out.tgt.push_back(kt);
+            }
+        for (size_t base = 0; base < upper.size(); base += 32) {
+            dc_task_t t;
+            t.kind = DC_TASK_UPPER;
+            t.first = (uint32_t)base;
+            t.mask = 0;
+            t.itemRel = (uint32_t)out.items.size();
+            size_t iters = 0;
+            for (size_t l = 0; l < 32 && base + l < upper.size(); l++) {
+                t.mask |= 1u << l;
+                iters = std::max(iters, perEdge[(size_t)upper[base + l]].size());
+            }
+            t.iters = (uint16_t)iters;
+            out.items.resize(out.items.size() + iters * 32, (uint16_t)DC_ITEM_NULL);
+            uint16_t *dst = out.items.data() + t.itemRel;
+            for (size_t l = 0; l < 32 && base + l < upper.size(); l++) {
+                const std::vector<uint16_t> &v = perEdge[(size_t)upper[base + l]];
+                for (size_t i = 0; i < v.size(); i++) dst[i * 32 + l] = v[i];
+                out.useful += (int64_t)v.size();
+            }
+            out.tasks.push_back(t);
+        }
+    }
     /* edge tasks: 32 consecutive edges, item rows [iter][lane]; diagonal lanes are
      * left to the diagonal tasks */
-    for (int base = 0; base < edgeCount; base += 32) {
+    for (int base = 0; !symmetric && base < edgeCount; base += 32) {
         dc_task_t t;
         t.kind = DC_TASK_EDGES;
         t.first = (uint32_t)base;
@@ -268,11 +315,11 @@ T *dup(const std::vector<T> &v)
 
 extern "C" int dc_contrib_build(dc_contrib_list_t *out, const int *conn, int nbElem, int nbNodes,
                                 const int *row, const int *col, int colBase, const int *rows,
-                                int64_t nbRows)
+                                int64_t nbRows, int symmetric)
 {
     Mesh m{conn, nbElem, nbNodes, row, col, colBase, {}, {}};
     build_node_to_elem(m);
-    std::vector<int64_t> edge, ptr;
+    std::vector<int64_t> edge, ptr, edgeT;
     std::vector<uint32_t> item;
     ptr.push_back(0);
     int error = 0;
@@ -287,6 +334,7 @@ extern "C" int dc_contrib_build(dc_contrib_list_t *out, const int *conn, int nbE
             int a = 0;
             while (a < 4 && c[a] - 1 != n) a++;
             for (int b = 0; b < 4; b++) {
+                if (symmetric && c[b] - 1 < n) continue;
                 int k = r0;
                 while (k < r1 && col[k] != c[b] - 1 + colBase) k++;
                 if (k == r1) { error = 1; continue; }
@@ -294,7 +342,17 @@ extern "C" int dc_contrib_build(dc_contrib_list_t *out, const int *conn, int nbE
             }
         }
         for (int k = r0; k < r1; k++) {
+            const int c = col[k] - colBase;
+            if (symmetric && c < n) continue;            /* written as a transpose by the owner of c */
             edge.push_back(k);
+            if (symmetric) {
+                int64_t kt = -1;
+                if (c > n) {
+                    kt = find_edge(m, c, n);
+                    if (kt < 0) error = 1;
+                }
+                edgeT.push_back(kt);
+            }
             item.insert(item.end(), perEdge[(size_t)(k - r0)].begin(), perEdge[(size_t)(k - r0)].end());
             ptr.push_back((int64_t)item.size());
         }
@@ -304,12 +362,13 @@ extern "C" int dc_contrib_build(dc_contrib_list_t *out, const int *conn, int nbE
     out->edge = dup(edge);
     out->ptr = dup(ptr);
     out->item = dup(item);
+    out->edgeT = symmetric ? dup(edgeT) : nullptr;
     return error ? -2 : 0;
 }
 
 extern "C" int dc_plan_build(dc_plan_t *plan, const int *conn, int nbElem, int nbNodes,
                              const int *row, const int *col, int colBase, const int *treeRec,
-                             int64_t nbTreeRec, int maxSlots, int nbThreads)
+                             int64_t nbTreeRec, int maxSlots, int nbThreads, int symmetric)
 {
     memset(plan, 0, sizeof *plan);
     const bool verbose = getenv("DC_PLAN_VERBOSE") != nullptr;
@@ -361,6 +420,7 @@ extern "C" int dc_plan_build(dc_plan_t *plan, const int *conn, int nbElem, int n
     std::vector<int32_t> diagRel((size_t)nbNodes, -1);
     std::vector<std::vector<dc_task_t>> tTasks((size_t)nt);
     std::vector<std::vector<uint16_t>> tItems((size_t)nt);
+    std::vector<std::vector<int32_t>> tTgt((size_t)nt);
     std::vector<int> unitThread((size_t)nbUnits);
     int error = 0;
     int64_t useful = 0;
@@ -375,8 +435,11 @@ extern "C" int dc_plan_build(dc_plan_t *plan, const int *conn, int nbElem, int n
             const UnitSeed &s = seeds[(size_t)u];
             out.tasks.clear();
             out.items.clear();
+            out.tgt.clear();
             out.useful = 0;
-            build_unit(m, s, diagRel.data(), out, perEdge, error);
+            build_unit(m, s, diagRel.data(), out, perEdge, error, symmetric != 0);
+            const int32_t nbUpper = (int32_t)(out.tgt.size() / 2);
+            while (out.tgt.size() % 4) out.tgt.push_back(0);      /* 16-byte granules for the bulk copy */
             dc_unit_t &d = units[(size_t)u];
             memset(&d, 0, sizeof d);
             d.edgeFirst = row[s.nodeFirst];
@@ -390,6 +453,9 @@ extern "C" int dc_plan_build(dc_plan_t *plan, const int *conn, int nbElem, int n
             d.taskCount = (int32_t)out.tasks.size();
             d.itemFirst = (int64_t)tItems[tid].size();
             d.itemCount = (int32_t)out.items.size();
+            d.tgtFirst = (int64_t)(tTgt[tid].size() / 2);
+            d.tgtCount = nbUpper;
+            tTgt[tid].insert(tTgt[tid].end(), out.tgt.begin(), out.tgt.end());
             unitThread[(size_t)u] = tid;
             tTasks[tid].insert(tTasks[tid].end(), out.tasks.begin(), out.tasks.end());
             tItems[tid].insert(tItems[tid].end(), out.items.begin(), out.items.end());
@@ -399,10 +465,18 @@ extern "C" int dc_plan_build(dc_plan_t *plan, const int *conn, int nbElem, int n
     if (error) return -2;
     lap("units");
 
-    std::vector<int64_t> taskBase((size_t)nt + 1, 0), itemBase((size_t)nt + 1, 0);
+    std::vector<int64_t> taskBase((size_t)nt + 1, 0), itemBase((size_t)nt + 1, 0), tgtBase((size_t)nt + 1, 0);
     for (int t = 0; t < nt; t++) {
         taskBase[(size_t)t + 1] = taskBase[t] + (int64_t)tTasks[t].size();
         itemBase[(size_t)t + 1] = itemBase[t] + (int64_t)tItems[t].size();
+        tgtBase[(size_t)t + 1] = tgtBase[t] + (int64_t)(tTgt[t].size() / 2);
+    }
+    plan->symmetric = symmetric ? 1 : 0;
+    plan->nbTgt = tgtBase[nt];
+    plan->tgt = (int32_t *)malloc(sizeof(int32_t) * 2 * (size_t)(plan->nbTgt ? plan->nbTgt : 1));
+    for (int t = 0; t < nt; t++) {
+        if (!tTgt[t].empty()) memcpy(plan->tgt + 2 * tgtBase[t], tTgt[t].data(), sizeof(int32_t) * tTgt[t].size());
+        std::vector<int32_t>().swap(tTgt[t]);
     }
     if (taskBase[nt] >= INT32_MAX) return -4;
     plan->nbTasks = taskBase[nt];
@@ -416,12 +490,14 @@ extern "C" int dc_plan_build(dc_plan_t *plan, const int *conn, int nbElem, int n
         std::vector<uint16_t>().swap(tItems[t]);
     }
     int64_t haloTotal = 0, slotsTotal = 0;
-    int maxUsed = 0, maxHalo = 0, maxTasks = 0, maxItems = 0;
+    int maxUsed = 0, maxHalo = 0, maxTasks = 0, maxItems = 0, maxTgt = 0;
     for (int64_t u = 0; u < nbUnits; u++) {
         dc_unit_t &d = units[(size_t)u];
         const int t = unitThread[(size_t)u];
         d.taskFirst += (int32_t)taskBase[t];
         d.itemFirst += itemBase[t];
+        d.tgtFirst += tgtBase[t];
+        maxTgt = std::max(maxTgt, (d.tgtCount + 1) & ~1);
         d.haloFirst = haloTotal;                       /* multiple of 4: bulk copies need 16-byte sources */
         haloTotal += (d.haloCount + 3) & ~3;
         slotsTotal += d.ownElemCount + d.haloCount;
@@ -433,6 +509,7 @@ extern "C" int dc_plan_build(dc_plan_t *plan, const int *conn, int nbElem, int n
     plan->maxHalo = maxHalo;
     plan->maxTasks = maxTasks;
     plan->maxItems = maxItems;
+    plan->maxTgt = maxTgt;
     plan->haloElems = (int32_t *)calloc((size_t)(haloTotal ? haloTotal : 1), sizeof(int32_t));
     for (int64_t u = 0; u < nbUnits; u++) {
         const std::vector<int> &h = seeds[(size_t)u].halo;
@@ -448,7 +525,7 @@ extern "C" int dc_plan_build(dc_plan_t *plan, const int *conn, int nbElem, int n
     plan->nbItemsUseful = useful;
     if (!bigRows.empty()) {
         int rc = dc_contrib_build(&plan->big, conn, nbElem, nbNodes, row, col, colBase,
-                                  bigRows.data(), (int64_t)bigRows.size());
+                                  bigRows.data(), (int64_t)bigRows.size(), symmetric);
         if (rc) return rc;
     }
     return 0;
@@ -456,13 +533,14 @@ extern "C" int dc_plan_build(dc_plan_t *plan, const int *conn, int nbElem, int n
 
 extern "C" void dc_contrib_free(dc_contrib_list_t *c)
 {
-    free(c->edge); free(c->ptr); free(c->item);
+    free(c->edge); free(c->ptr); free(c->item); free(c->edgeT);
     memset(c, 0, sizeof *c);
 }
 
 extern "C" void dc_plan_free(dc_plan_t *plan)
 {
     free(plan->units); free(plan->tasks); free(plan->items); free(plan->haloElems); free(plan->diagRel);
+    free(plan->tgt);
     dc_contrib_free(&plan->big);
     memset(plan, 0, sizeof *plan);
 }

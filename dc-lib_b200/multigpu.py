@@ -109,7 +109,8 @@ class InterfaceExchange:
             self._unpack_add(values, nb, stream)
 
 
-def setup_device_slabs(n, rank, world, device, builder="geometric", vec=0, slots=400, dist=None, seed=12345):
+def setup_device_slabs(n, rank, world, device, builder="geometric", vec=0, slots=400, dist=None, seed=12345,
+                       symmetric=True):
     """Device-resident slab for this rank.  Every slab of the bar has the same topology, so
     rank 0 builds tree, CSR pattern and schedule once on its host cores and broadcasts the
     arrays GPU-to-GPU (NCCL over NVLink); each rank generates its own coordinates and permutes
@@ -120,7 +121,7 @@ def setup_device_slabs(n, rank, world, device, builder="geometric", vec=0, slots
 
     from . import Context, HostPlan, permute_double_2d
 
-    names = ["conn", "row", "col", "node_perm", "units", "tasks", "items", "halo", "diagRel", "intf_left", "intf_right"]
+    names = ["conn", "row", "col", "node_perm", "units", "tasks", "items", "halo", "diagRel", "tgt", "intf_left", "intf_right"]
     t0 = time.time()
     tensors, meta = {}, None
     if rank == 0:
@@ -129,21 +130,21 @@ def setup_device_slabs(n, rank, world, device, builder="geometric", vec=0, slots
         node_perm = slab["node_perm"]
         t_tree = time.time() - t0
         t1 = time.time()
-        plan = HostPlan(slab["conn"], slab["N"], slab["row"], slab["col"], 0, slab["rec"], slots)
+        plan = HostPlan(slab["conn"], slab["N"], slab["row"], slab["col"], 0, slab["rec"], slots, symmetric=symmetric)
         t_plan = time.time() - t1
         arr = plan.arrays()
         if arr["bigEdges"]:
             raise RuntimeError("setup_device_slabs: rows exceeding the unit budget are not supported on this path")
         host = dict(conn=slab["conn"], row=slab["row"], col=slab["col"], node_perm=node_perm, units=arr["units"],
                     tasks=arr["tasks"], items=arr["items"].view(np.int16), halo=arr["halo"],
-                    diagRel=plan.diag_rel(slab["N"]),
+                    diagRel=plan.diag_rel(slab["N"]), tgt=arr["tgt"],
                     intf_left=plane_edges(node_perm, slab["row"], slab["col"], n, 0) if world > 1 else np.zeros(0, np.int64),
                     intf_right=plane_edges(node_perm, slab["row"], slab["col"], n, n) if world > 1 else np.zeros(0, np.int64))
         for k in names:
             tensors[k] = torch.from_numpy(np.ascontiguousarray(host[k])).to(device)
         st = plan.stats()
         meta = dict(shapes={k: (tuple(tensors[k].shape), str(tensors[k].dtype)) for k in names},
-                    ints={k: arr[k] for k in ("nbUnits", "maxSlots", "maxHalo", "maxTasks", "maxItems")},
+                    ints={k: arr[k] for k in ("nbUnits", "maxSlots", "maxHalo", "maxTasks", "maxItems", "maxTgt", "symmetric")},
                     E=slab["E"], N=slab["N"], nnz=slab["nnz"], stats=st, tree_s=t_tree, plan_s=t_plan)
         del plan, slab, host, arr
     if world > 1:
@@ -166,7 +167,7 @@ def setup_device_slabs(n, rank, world, device, builder="geometric", vec=0, slots
     ctx = Context(torch.device(device).index or 0)
     ctx.set_mesh_device(tensors["conn"], d_coord, tensors["row"], tensors["col"], meta["nnz"], 0)
     plan_t = dict(units=tensors["units"], tasks=tensors["tasks"], items=tensors["items"], halo=tensors["halo"],
-                  diagRel=tensors["diagRel"], **meta["ints"])
+                  diagRel=tensors["diagRel"], tgt=tensors["tgt"], **meta["ints"])
     ctx.set_plan_device(plan_t)
     intf = {}
     if rank > 0:

@@ -57,7 +57,8 @@ int  dc_cuda_upload_plan(dc_cuda_ctx *ctx, const struct dc_plan_s *plan);
  * another rank over NCCL); not copied, not freed.  No big-row fallback list on this path. */
 int  dc_cuda_set_plan_device(dc_cuda_ctx *ctx, const void *d_units, const void *d_tasks,
                              const void *d_items, const int *d_halo, const int *d_diagRel,
-                             int64_t nbUnits, int maxSlots, int maxHalo, int maxTasks, int maxItems);
+                             const int *d_tgt, int64_t nbUnits, int maxSlots, int maxHalo,
+                             int maxTasks, int maxItems, int maxTgt, int symmetric);
 /* Explicit contribution lists for DC_MODE_LIST (all edges). */
 int  dc_cuda_upload_lists(dc_cuda_ctx *ctx, const int64_t *h_edge, const int64_t *h_ptr,
                           const uint32_t *h_item, int64_t nbEdges, int64_t nbItems);

@@ -85,28 +85,45 @@ void dco_laplacian_ke(const double x[4][3], double ke[16])
 }
 
 /* Isotropic elasticity with the volume folded symmetrically into the gradients:
- * h_a = g_a * sqrt(vol);  p[i][j] = ha_i*hb_j;  dot = (p00+p11)+p22;
- * ke[a*4+b][i*3+j] = fma(mu, p[j][i], lambda*p[i][j]), and on the diagonal
- * fma(mu, dot, that).  (= vol * (lambda ga_i gb_j + mu ga_j gb_i + delta_ij mu ga.gb)) */
-void dco_elasticity_ke(const double x[4][3], double lambda, double mu, double ke[16][9])
+ * h_a = g_a * sqrt(vol);  p[i][j] = ha_i*hb_j;  dot = (p00+p11)+p22.  The scatter-add of
+ * block (a,b) into its CSR entry v is three fused updates per component,
+ *     v[i][j] = fma(lambda, p[i][j], v[i][j]);  v[i][j] = fma(mu, p[j][i], v[i][j]);
+ *     i == j:  v[i][i] = fma(mu, dot, v[i][i]);
+ * i.e. v += vol*(lambda ga_i gb_j + mu ga_j gb_i + delta_ij mu ga.gb).  dco_elasticity_h
+ * computes the h_a; dco_elasticity_add performs the update of one block. */
+void dco_elasticity_h(const double x[4][3], double h[4][3])
 {
-    double g[4][3], h[4][3], vol;
+    double g[4][3], vol;
     dco_tet_gradients(x, g, &vol);
     double s = sqrt(vol);
     for (int a = 0; a < 4; a++)
         for (int k = 0; k < 3; k++) h[a][k] = g[a][k] * s;
+}
+
+void dco_elasticity_add(const double ha[3], const double hb[3], double lambda, double mu, double v[9])
+{
+    double p[3][3];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) p[i][j] = ha[i] * hb[j];
+    double dot = (p[0][0] + p[1][1]) + p[2][2];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            double t = fma(lambda, p[i][j], v[i * 3 + j]);
+            t = fma(mu, p[j][i], t);
+            if (i == j) t = fma(mu, dot, t);
+            v[i * 3 + j] = t;
+        }
+}
+
+/* the element matrix itself (what the updates add up to), for reference */
+void dco_elasticity_ke(const double x[4][3], double lambda, double mu, double ke[16][9])
+{
+    double h[4][3];
+    dco_elasticity_h(x, h);
     for (int a = 0; a < 4; a++)
         for (int b = 0; b < 4; b++) {
-            double p[3][3];
-            for (int i = 0; i < 3; i++)
-                for (int j = 0; j < 3; j++) p[i][j] = h[a][i] * h[b][j];
-            double dot = (p[0][0] + p[1][1]) + p[2][2];
-            for (int i = 0; i < 3; i++)
-                for (int j = 0; j < 3; j++) {
-                    double v = fma(mu, p[j][i], lambda * p[i][j]);
-                    if (i == j) v = fma(mu, dot, v);
-                    ke[a * 4 + b][i * 3 + j] = v;
-                }
+            for (int k = 0; k < 9; k++) ke[a * 4 + b][k] = 0.0;
+            dco_elasticity_add(h[a], h[b], lambda, mu, ke[a * 4 + b]);
         }
 }
 
@@ -137,13 +154,11 @@ void dco_assemble_range(const dco_user_t *u, int firstElem, int lastElem)
                 for (int b = 0; b < 4; b++)
                     u->values[find_edge(u, n[a], n[b])] += ke[a * 4 + b];
         } else {
-            double ke[16][9];
-            dco_elasticity_ke(x, u->lambda, u->mu, ke);
+            double h[4][3];
+            dco_elasticity_h(x, h);
             for (int a = 0; a < 4; a++)
-                for (int b = 0; b < 4; b++) {
-                    double *dst = u->values + find_edge(u, n[a], n[b]) * d2;
-                    for (int k = 0; k < 9; k++) dst[k] += ke[a * 4 + b][k];
-                }
+                for (int b = 0; b < 4; b++)
+                    dco_elasticity_add(h[a], h[b], u->lambda, u->mu, u->values + find_edge(u, n[a], n[b]) * d2);
         }
     }
 }

@@ -41,6 +41,8 @@ typedef struct {
 /* element kernels (the numeric contract shared with the device operators) */
 void dco_tet_gradients(const double x[4][3], double g[4][3], double *vol);
 void dco_laplacian_ke(const double x[4][3], double ke[16]);
+void dco_elasticity_h(const double x[4][3], double h[4][3]);
+void dco_elasticity_add(const double ha[3], const double hb[3], double lambda, double mu, double v[9]);
 void dco_elasticity_ke(const double x[4][3], double lambda, double mu, double ke[16][9]);
 
 /* leaf callbacks with the reference's signature void(*)(void*, DCargs_t*) */

@@ -21,11 +21,11 @@ OPS = {1: (dc.OP_LAPLACIAN, None), 3: (dc.OP_ELASTICITY, [LAMBDA, MU])}
 REL_TOL = 1e-12
 
 
-def _ctx(mesh, slots=832, lists=False, with_tree=True):
+def _ctx(mesh, slots=832, lists=False, with_tree=True, sym=True):
     ctx = dc.Context(0)
     ctx.set_mesh(mesh["conn"], mesh["coord"], mesh["row"], mesh["col"], 0)
     rec = tree_records(mesh) if with_tree else None
-    plan = dc.HostPlan(mesh["conn"], mesh["N"], mesh["row"], mesh["col"], 0, rec, slots)
+    plan = dc.HostPlan(mesh["conn"], mesh["N"], mesh["row"], mesh["col"], 0, rec, slots, symmetric=sym)
     ctx.upload_plan(plan)
     if lists:
         ctx.upload_lists(mesh["conn"], mesh["N"], mesh["row"], mesh["col"], 0)
@@ -55,6 +55,8 @@ def test_deterministic_matches_reference_golden(tmp_path, key, dim):
     ctx, _ = _ctx(mesh)
     got = _run(ctx, mesh, dim, dc.MODE_DETERMINISTIC)
     assert md5(got) == g[f"values_md5_d{dim}"]
+    ctx2, _ = _ctx(mesh, slots=300, sym=False)                    # general (non-symmetric) schedule
+    assert _run(ctx2, mesh, dim, dc.MODE_DETERMINISTIC).tobytes() == got.tobytes()
     raw = os.path.join(GOLDEN, f"{key}_values_d1.npy")
     if dim == 1 and os.path.exists(raw):
         assert np.load(raw).tobytes() == got.tobytes()
@@ -73,16 +75,17 @@ def test_baseline_configs_c1_c2(tmp_path, key, dim):
     assert _rel_err(fast, got) <= REL_TOL
 
 
+@pytest.mark.parametrize("sym", [True, False])
 @pytest.mark.parametrize("n,vec,dim,slots,hub", [
     (8, 0, 1, 832, False), (8, 4, 3, 832, False), (12, 0, 3, 200, False), (12, 2, 1, 64, False),
-    (16, 8, 3, 832, False), (18, 0, 3, 832, True), (18, 4, 1, 100, True), (3, 0, 3, 832, False),
-    (1, 0, 1, 832, False)])
-def test_all_modes_against_oracle(tmp_path, n, vec, dim, slots, hub):
+    (16, 8, 3, 832, False), (18, 0, 3, 832, True), (18, 4, 1, 100, True), (18, 0, 3, 100, True),
+    (3, 0, 3, 832, False), (1, 0, 1, 832, False)])
+def test_all_modes_against_oracle(tmp_path, n, vec, dim, slots, hub, sym):
     """Small slot budgets force leaf splitting and the big-row fallback; hub meshes have
     nodes of valence ~100 (BASELINE config C5)."""
     mesh = prepare_mesh(MineLib(vec), n, tmp_path, hub=hub)
     want = oracle_serial(mesh, dim)
-    ctx, plan = _ctx(mesh, slots=slots, lists=True)
+    ctx, plan = _ctx(mesh, slots=slots, lists=True, sym=sym)
     det = _run(ctx, mesh, dim, dc.MODE_DETERMINISTIC)
     assert det.tobytes() == want.tobytes()
     lst = _run(ctx, mesh, dim, dc.MODE_LIST)
@@ -103,7 +106,7 @@ def test_geometric_tree_bit_exact(tmp_path, n, dim):
 
 def test_plan_without_tree_is_still_bit_exact(tmp_path):
     mesh = prepare_mesh(MineLib(0), 10, tmp_path)
-    ctx, _ = _ctx(mesh, slots=400, with_tree=False)
+    ctx, _ = _ctx(mesh, slots=400, with_tree=False, sym=False)
     for dim in (1, 3):
         assert _run(ctx, mesh, dim, dc.MODE_DETERMINISTIC).tobytes() == oracle_serial(mesh, dim).tobytes()
 

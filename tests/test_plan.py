@@ -18,13 +18,16 @@ def _plan_arrays(p):
     return units, tasks, items, halo
 
 
+@pytest.mark.parametrize("sym", [True, False])
 @pytest.mark.parametrize("n,vec,slots,hub", [(8, 0, 832, False), (10, 4, 832, False), (10, 0, 200, False),
                                              (12, 0, 64, False), (18, 0, 832, True), (18, 0, 120, True)])
-def test_plan_covers_every_contribution_once(tmp_path, n, vec, slots, hub):
+def test_plan_covers_every_contribution_once(tmp_path, n, vec, slots, hub, sym):
     mesh = prepare_mesh(MineLib(vec), n, tmp_path, hub=hub)
     rec = tree_records(mesh)
-    plan = dc.HostPlan(mesh["conn"], mesh["N"], mesh["row"], mesh["col"], 0, rec, slots)
+    plan = dc.HostPlan(mesh["conn"], mesh["N"], mesh["row"], mesh["col"], 0, rec, slots, symmetric=sym)
     units, tasks, items, halo = _plan_arrays(plan)
+    tgt = np.ctypeslib.as_array(plan.c.tgt, shape=(max(plan.c.nbTgt, 1), 2))
+    rows_of = np.repeat(np.arange(mesh["N"]), np.diff(mesh["row"]))
     E, N, nnz = mesh["E"], mesh["N"], mesh["nnz"]
     conn = mesh["conn"].astype(np.int64) - 1
     row, col = mesh["row"], mesh["col"]
@@ -49,12 +52,22 @@ def test_plan_covers_every_contribution_once(tmp_path, n, vec, slots, hub):
             halo[u.haloFirst:u.haloFirst + u.haloCount].tolist()
         for t in tasks[u.taskFirst:u.taskFirst + u.taskCount]:
             block = items[u.itemFirst + t.itemRel:u.itemFirst + t.itemRel + 32 * t.iters].reshape(t.iters, 32)
+            assert t.kind == 1 or (t.kind == 2) == sym
             for lane in range(32):
+                kT = -1
                 if t.kind == 0:
                     if (t.mask >> lane) & 1 or t.first + lane >= u.edgeCount:
                         assert (block[:, lane] == 0xFFFF).all()
                         continue
                     k = u.edgeFirst + t.first + lane
+                elif t.kind == 2:
+                    if not (t.mask >> lane) & 1:
+                        assert (block[:, lane] == 0xFFFF).all()
+                        continue
+                    assert t.first + lane < u.tgtCount
+                    k, kT = (int(v) for v in tgt[u.tgtFirst + t.first + lane])
+                    assert u.edgeFirst <= k < u.edgeFirst + u.edgeCount and col[k] > rows_of[k]
+                    assert rows_of[kT] == col[k] and col[kT] == rows_of[k]      # the transposed edge
                 else:
                     if not (t.mask >> lane) & 1:
                         assert (block[:, lane] == 0xFFFF).all()
@@ -73,20 +86,23 @@ def test_plan_covers_every_contribution_once(tmp_path, n, vec, slots, hub):
                     assert e > last                      # ascending element order inside an edge
                     last = e
                     got[k] += 1
+                    if kT >= 0:
+                        got[kT] += 1
     big = plan.c.big
     for q in range(big.nbEdges):
         k = big.edge[q]
-        rows_seen[int(np.searchsorted(row, k, side="right") - 1)] += 0
         got[k] += big.ptr[q + 1] - big.ptr[q]
+        if sym and big.edgeT[q] >= 0:
+            got[big.edgeT[q]] += big.ptr[q + 1] - big.ptr[q]
     covered = rows_seen.copy()
     for q in range(big.nbEdges):
         covered[int(np.searchsorted(row, big.edge[q], side="right") - 1)] = 1
     assert (covered == 1).all()
     assert np.array_equal(got, want)
-    assert plan.c.nbItemsUseful + big.nbItems == 16 * E
+    assert plan.c.nbItemsUseful + big.nbItems == (10 if sym else 16) * E
 
 
 def test_plan_without_tree_uses_row_blocks(tmp_path):
     mesh = prepare_mesh(MineLib(0), 8, tmp_path)
-    plan = dc.HostPlan(mesh["conn"], mesh["N"], mesh["row"], mesh["col"], 0, None, 300)
+    plan = dc.HostPlan(mesh["conn"], mesh["N"], mesh["row"], mesh["col"], 0, None, 300, symmetric=False)
     assert plan.c.nbUnits > 1 and plan.c.nbItemsUseful == 16 * mesh["E"]

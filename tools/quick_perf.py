@@ -9,6 +9,7 @@ import common
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 slots_list = [int(s) for s in sys.argv[2].split(",")] if len(sys.argv) > 2 else [832]
 threads_list = [int(s) for s in sys.argv[3].split(",")] if len(sys.argv) > 3 else [128, 256]
+sym_list = [int(s) for s in sys.argv[4].split(",")] if len(sys.argv) > 4 else [1, 0]
 vec = 0
 t0 = time.time()
 with tempfile.TemporaryDirectory() as tmp:
@@ -17,11 +18,11 @@ print(f"mesh n={n} E={mesh['E']} N={mesh['N']} nnz={mesh['nnz']} prep {time.time
 rec = common.tree_records(mesh)
 E, N, nnz = mesh["E"], mesh["N"], mesh["nnz"]
 first = True
-for slots in slots_list:
+for slots, sym in [(a, b) for a in slots_list for b in sym_list]:
     t0 = time.time()
-    plan = dc.HostPlan(mesh["conn"], N, mesh["row"], mesh["col"], 0, rec, slots)
+    plan = dc.HostPlan(mesh["conn"], N, mesh["row"], mesh["col"], 0, rec, slots, symmetric=bool(sym))
     st = plan.stats()
-    print(f"slots={slots} plan {time.time()-t0:.2f}s units={st['units']} pad_eff={st['items_useful']/max(st['items'],1):.3f} slots/elem={st['slots_total']/E:.3f} maxItems={plan.c.maxItems} maxTasks={plan.c.maxTasks} maxHalo={plan.c.maxHalo}", flush=True)
+    print(f"slots={slots} sym={sym} plan {time.time()-t0:.2f}s units={st['units']} pad_eff={st['items_useful']/max(st['items'],1):.3f} slots/elem={st['slots_total']/E:.3f} maxItems={plan.c.maxItems} maxTasks={plan.c.maxTasks} maxHalo={plan.c.maxHalo}", flush=True)
     for threads in threads_list:
         ctx = dc.Context(0)
         ctx.set_mesh(mesh["conn"], mesh["coord"], mesh["row"], mesh["col"], 0)
