@@ -241,14 +241,14 @@ __global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *_
                 for (int c = 0; c < DD; c++) st_stream_f64(values + (u.edgeFirst + d) * DD + c, acc[c]);
             }
         } else if (SYM) {
-            /* upper edge: block to (row,col), transposed block to (col,row) */
+            /* owned edge: block to (row,col); upper edges also store the transpose at (col,row) */
             const bool valid = (task.mask >> lane) & 1u;
             int2 tg = make_int2(-1, -1);
             if (valid) tg = tgtS[(int)task.first + lane];
             if (DD == 1) {
                 if (valid) {
                     st_stream_f64(values + tg.x, acc[0]);
-                    st_stream_f64(values + tg.y, acc[0]);
+                    if (tg.y >= 0) st_stream_f64(values + tg.y, acc[0]);
                 }
             } else {
 #pragma unroll

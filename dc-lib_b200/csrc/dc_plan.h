@@ -24,8 +24,9 @@
 #define DC_SLOT_LIMIT  4095         /* slots are 12-bit: item = slot<<4 | a<<2 | b */
 #define DC_TASK_EDGES  0            /* 32 consecutive edges of the unit (general schedule)   */
 #define DC_TASK_DIAG   1            /* the diagonal edges of 32 consecutive nodes            */
-#define DC_TASK_UPPER  2            /* 32 upper edges (col > row): symmetric schedule, the    */
-                                    /* lane also writes the transposed block to (col,row)   */
+#define DC_TASK_UPPER  2            /* symmetric schedule: 32 owned edges (diagonal or col > row) */
+                                    /* listed in tgt; an upper-edge lane also writes the        */
+                                    /* transposed block to (col,row)                            */
 
 typedef struct {
     int64_t edgeFirst;      /* first CSR edge of the unit                          */
@@ -72,7 +73,7 @@ typedef struct dc_plan_s {
     int32_t  maxTgt;        /* most upper edges in one unit (symmetric schedule)   */
     int32_t  symmetric;     /* 1: UPPER tasks + tgt pairs, 0: EDGES tasks          */
     int64_t  nbTgt;         /* pairs in tgt                                        */
-    int32_t *tgt;           /* [nbTgt][2] (edge of (row,col), edge of (col,row))   */
+    int32_t *tgt;           /* [nbTgt][2] (edge of (row,col), edge of (col,row) or -1) */
     int64_t  nbUnits, nbTasks, nbItems, nbHalo;
     dc_unit_t *units;
     dc_task_t *tasks;

@@ -215,44 +215,56 @@ void build_unit(const Mesh &m, const UnitSeed &s, int32_t *diagRel, UnitOut &out
         }
     }
     if (symmetric) {
-        /* upper-edge tasks: the unit's edges with col > row in (row, position) order, 32 per task;
-         * each lane also owns the transposed edge (col,row), wherever that row lives */
-        std::vector<int> upper;
+        /* owned edges = diagonal + upper edges (col > row) of the unit's rows.  Each becomes one
+         * lane; an upper-edge lane also owns the transposed edge (col,row), wherever that row
+         * lives.  Lanes are grouped 32 per task after a stable sort by contribution count
+         * (descending), so that the lanes of a task run the same number of iterations --
+         * diagonals (one contribution per incident element) end up in tasks of their own. */
+        struct Owned { int rel; int k; int kt; int count; };
+        std::vector<Owned> owned;
         for (int n = s.nodeFirst; n < s.nodeFirst + s.nodeCount; n++)
             for (int k = m.row[n]; k < m.row[n + 1]; k++) {
                 const int c = m.col[k] - m.colBase;
-                if (c <= n) continue;
-                const int kt = find_edge(m, c, n);
-                if (kt < 0) { error = 1; continue; }      /* pattern is not structurally symmetric */
-                upper.push_back((int)(k - edgeFirst));
-                out.tgt.push_back(k);
-                out.tgt.push_back(kt);
+                if (c < n) continue;
+                int kt = -1;
+                if (c > n) {
+                    kt = find_edge(m, c, n);
+                    if (kt < 0) { error = 1; continue; }      /* pattern is not structurally symmetric */
+                }
+                const int rel = (int)(k - edgeFirst);
+                owned.push_back(Owned{rel, k, kt, (int)perEdge[(size_t)rel].size()});
             }
-        for (size_t base = 0; base < upper.size(); base += 32) {
+        std::stable_sort(owned.begin(), owned.end(), [](const Owned &x, const Owned &y) { return x.count > y.count; });
+        for (const Owned &o : owned) {
+            out.tgt.push_back(o.k);
+            out.tgt.push_back(o.kt);
+        }
+        for (size_t base = 0; base < owned.size(); base += 32) {
             dc_task_t t;
             t.kind = DC_TASK_UPPER;
             t.first = (uint32_t)base;
             t.mask = 0;
             t.itemRel = (uint32_t)out.items.size();
             size_t iters = 0;
-            for (size_t l = 0; l < 32 && base + l < upper.size(); l++) {
+            for (size_t l = 0; l < 32 && base + l < owned.size(); l++) {
                 t.mask |= 1u << l;
-                iters = std::max(iters, perEdge[(size_t)upper[base + l]].size());
+                iters = std::max(iters, (size_t)owned[base + l].count);
             }
             t.iters = (uint16_t)iters;
             out.items.resize(out.items.size() + iters * 32, (uint16_t)DC_ITEM_NULL);
             uint16_t *dst = out.items.data() + t.itemRel;
-            for (size_t l = 0; l < 32 && base + l < upper.size(); l++) {
-                const std::vector<uint16_t> &v = perEdge[(size_t)upper[base + l]];
+            for (size_t l = 0; l < 32 && base + l < owned.size(); l++) {
+                const std::vector<uint16_t> &v = perEdge[(size_t)owned[base + l].rel];
                 for (size_t i = 0; i < v.size(); i++) dst[i * 32 + l] = v[i];
                 out.useful += (int64_t)v.size();
             }
             out.tasks.push_back(t);
         }
+        return;
     }
     /* edge tasks: 32 consecutive edges, item rows [iter][lane]; diagonal lanes are
      * left to the diagonal tasks */
-    for (int base = 0; !symmetric && base < edgeCount; base += 32) {
+    for (int base = 0; base < edgeCount; base += 32) {
         dc_task_t t;
         t.kind = DC_TASK_EDGES;
         t.first = (uint32_t)base;

@@ -52,7 +52,7 @@ def test_plan_covers_every_contribution_once(tmp_path, n, vec, slots, hub, sym):
             halo[u.haloFirst:u.haloFirst + u.haloCount].tolist()
         for t in tasks[u.taskFirst:u.taskFirst + u.taskCount]:
             block = items[u.itemFirst + t.itemRel:u.itemFirst + t.itemRel + 32 * t.iters].reshape(t.iters, 32)
-            assert t.kind == 1 or (t.kind == 2) == sym
+            assert (t.kind == 2) == sym
             for lane in range(32):
                 kT = -1
                 if t.kind == 0:
@@ -66,8 +66,11 @@ def test_plan_covers_every_contribution_once(tmp_path, n, vec, slots, hub, sym):
                         continue
                     assert t.first + lane < u.tgtCount
                     k, kT = (int(v) for v in tgt[u.tgtFirst + t.first + lane])
-                    assert u.edgeFirst <= k < u.edgeFirst + u.edgeCount and col[k] > rows_of[k]
-                    assert rows_of[kT] == col[k] and col[kT] == rows_of[k]      # the transposed edge
+                    assert u.edgeFirst <= k < u.edgeFirst + u.edgeCount and col[k] >= rows_of[k]
+                    if col[k] == rows_of[k]:
+                        assert kT == -1                                          # a diagonal edge
+                    else:
+                        assert rows_of[kT] == col[k] and col[kT] == rows_of[k]  # the transposed edge
                 else:
                     if not (t.mask >> lane) & 1:
                         assert (block[:, lane] == 0xFFFF).all()
