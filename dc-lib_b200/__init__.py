@@ -49,11 +49,12 @@ def lib():
 
 
 class Unit(ctypes.Structure):
-    _fields_ = [("edgeFirst", c_int64), ("itemFirst", c_int64), ("haloFirst", c_int64),
+    _fields_ = [("edgeFirst", c_int64), ("itemFirst", c_int64), ("tgtFirst", c_int64), ("slotFirst", c_int64),
+                ("hnodeFirst", c_int64), ("haloFirst", c_int64),
                 ("edgeCount", c_int32), ("nodeFirst", c_int32), ("nodeCount", c_int32),
                 ("ownElemFirst", c_int32), ("ownElemCount", c_int32), ("haloCount", c_int32),
                 ("taskFirst", c_int32), ("taskCount", c_int32), ("itemCount", c_int32),
-                ("tgtFirst", c_int64), ("tgtCount", c_int32), ("pad_", c_int32)]
+                ("tgtCount", c_int32), ("hnodeCount", c_int32), ("pad_", c_int32)]
 
 
 class Task(ctypes.Structure):
@@ -67,12 +68,13 @@ class ContribList(ctypes.Structure):
 
 
 class Plan(ctypes.Structure):
-    _fields_ = [("maxSlots", c_int32), ("maxHalo", c_int32), ("maxTasks", c_int32), ("maxItems", c_int32),
+    _fields_ = [("maxSlots", c_int32), ("maxHalo", c_int32), ("maxNodes", c_int32), ("maxTasks", c_int32), ("maxItems", c_int32),
                 ("maxTgt", c_int32), ("symmetric", c_int32), ("nbTgt", c_int64), ("tgt", POINTER(c_int32)),
                 ("nbUnits", c_int64), ("nbTasks", c_int64),
                 ("nbItems", c_int64), ("nbHalo", c_int64), ("units", POINTER(Unit)),
                 ("tasks", POINTER(Task)), ("items", POINTER(c_uint16)),
-                ("haloElems", POINTER(c_int32)), ("diagRel", POINTER(c_int32)),
+                ("haloElems", POINTER(c_int32)), ("nbSlotNodes", c_int64), ("slotNodes", POINTER(c_uint16)),
+                ("nbHaloNodes", c_int64), ("haloNodes", POINTER(c_int32)), ("diagRel", POINTER(c_int32)),
                 ("big", ContribList), ("nbSlotsTotal", c_int64), ("nbItemsUseful", c_int64)]
 
 
@@ -86,7 +88,7 @@ def _declare(L):
     L.dc_cuda_set_mesh_device.argtypes = [vp, vp, vp, vp, vp, c_int, c_int, c_int64, c_int]
     L.dc_cuda_update_coords.argtypes = [vp, vp, vp]
     L.dc_cuda_upload_plan.argtypes = [vp, POINTER(Plan)]
-    L.dc_cuda_set_plan_device.argtypes = [vp, vp, vp, vp, vp, vp, vp, c_int64, c_int, c_int, c_int, c_int, c_int, c_int]
+    L.dc_cuda_set_plan_device.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int]
     L.dc_cuda_download_range.argtypes = [vp, c_int64, c_int64, vp, vp]
     L.dc_cuda_upload_lists.argtypes = [vp, vp, vp, vp, c_int64, c_int64]
     L.dc_cuda_assemble.argtypes = [vp, c_int, vp, c_int, c_int, vp, vp]
@@ -269,10 +271,10 @@ class HostPlan:
             a = a.view(dtype)
             return a if width == 1 else a.reshape(count, width)
 
-        return dict(units=view(c.units, c.nbUnits, np.uint8, 80), tasks=view(c.tasks, c.nbTasks, np.uint8, 16),
-                    items=view(c.items, c.nbItems, np.uint16), halo=view(c.haloElems, c.nbHalo, np.int32),
-                    tgt=view(c.tgt, c.nbTgt, np.int32, 2),
-                    nbUnits=int(c.nbUnits), maxSlots=int(c.maxSlots), maxHalo=int(c.maxHalo),
+        return dict(units=view(c.units, c.nbUnits, np.uint8, 96), tasks=view(c.tasks, c.nbTasks, np.uint8, 16),
+                    items=view(c.items, c.nbItems, np.uint16), slotNodes=view(c.slotNodes, c.nbSlotNodes, np.uint16),
+                    haloNodes=view(c.haloNodes, c.nbHaloNodes, np.int32), tgt=view(c.tgt, c.nbTgt, np.int32, 2),
+                    nbUnits=int(c.nbUnits), maxSlots=int(c.maxSlots), maxHalo=int(c.maxHalo), maxNodes=int(c.maxNodes),
                     maxTasks=int(c.maxTasks), maxItems=int(c.maxItems), maxTgt=int(c.maxTgt),
                     symmetric=int(c.symmetric), bigEdges=int(c.big.nbEdges))
 
@@ -326,12 +328,12 @@ class Context:
         self._ck(lib().dc_cuda_upload_plan(self.h, byref(plan.c)), "dc_cuda_upload_plan")
 
     def set_plan_device(self, t):
-        """t: dict of torch CUDA tensors {units,tasks,items,halo,diagRel} + ints {nbUnits,maxSlots,maxHalo,maxTasks,maxItems}."""
+        """t: dict of torch CUDA tensors {units,tasks,items,slotNodes,haloNodes,diagRel,tgt} + the plan's ints."""
         self._keep_plan = t
-        self._ck(lib().dc_cuda_set_plan_device(self.h, _p(t["units"]), _p(t["tasks"]), _p(t["items"]), _p(t["halo"]),
-                                               _p(t["diagRel"]), _p(t["tgt"]), t["nbUnits"], t["maxSlots"],
-                                               t["maxHalo"], t["maxTasks"], t["maxItems"], t["maxTgt"],
-                                               t["symmetric"]), "dc_cuda_set_plan_device")
+        self._ck(lib().dc_cuda_set_plan_device(self.h, _p(t["units"]), _p(t["tasks"]), _p(t["items"]),
+                                               _p(t["slotNodes"]), _p(t["haloNodes"]), _p(t["diagRel"]), _p(t["tgt"]),
+                                               t["nbUnits"], t["maxSlots"], t["maxHalo"], t["maxNodes"], t["maxTasks"],
+                                               t["maxItems"], t["maxTgt"], t["symmetric"]), "dc_cuda_set_plan_device")
 
     def download_range(self, d_values, first, count, h_buf, stream=None):
         self._ck(lib().dc_cuda_download_range(_p(d_values), first, count, _p(h_buf), stream), "dc_cuda_download_range")

@@ -37,7 +37,8 @@ struct dc_cuda_ctx {
     int *d_conn = nullptr, *d_row = nullptr, *d_col = nullptr;
     double *d_coord = nullptr;
     /* plan */
-    int maxSlots = 0, maxHalo = 0, maxTasks = 0, maxItems = 0, maxTgt = 0, symmetric = 0;
+    int maxSlots = 0, maxHalo = 0, maxNodes = 0, maxTasks = 0, maxItems = 0, maxTgt = 0, symmetric = 0;
+    uint16_t *d_slotNodes = nullptr;
     int *d_tgt = nullptr;
     int64_t *d_bigEdgeT = nullptr;
     int threads = 256;       /* CTA size of the unit kernel (128 or 256) */
@@ -100,8 +101,10 @@ static void free_plan(dc_cuda_ctx *c)
 {
     if (!c->ownsPlan) {
         c->d_units = nullptr; c->d_tasks = nullptr; c->d_items = nullptr; c->d_halo = c->d_diagRel = c->d_tgt = nullptr;
+        c->d_slotNodes = nullptr;
         c->ownsPlan = true;
     }
+    cudaFree(c->d_slotNodes); c->d_slotNodes = nullptr;
     cudaFree(c->d_tgt); cudaFree(c->d_bigEdgeT);
     c->d_tgt = nullptr; c->d_bigEdgeT = nullptr;
     cudaFree(c->d_units); cudaFree(c->d_tasks); cudaFree(c->d_items); cudaFree(c->d_halo);
@@ -146,7 +149,11 @@ extern "C" int dc_cuda_set_mesh(dc_cuda_ctx *c, const int *h_conn, const double 
     c->nnz = h_row[nbNodes];
     int rc;
     if ((rc = upload(&c->d_conn, h_conn, (int64_t)nbElem * 4))) return rc;
-    if ((rc = upload(&c->d_coord, h_coord, (int64_t)nbNodes * 3))) return rc;
+    /* two spare nodes behind the array: the bulk copy of a unit's own coordinates is rounded up
+     * to a 48-byte granule */
+    CK(cudaMalloc((void **)&c->d_coord, sizeof(double) * 3 * ((size_t)nbNodes + 2)));
+    CK(cudaMemset(c->d_coord, 0, sizeof(double) * 3 * ((size_t)nbNodes + 2)));
+    CK(cudaMemcpy(c->d_coord, h_coord, sizeof(double) * 3 * (size_t)nbNodes, cudaMemcpyHostToDevice));
     if ((rc = upload(&c->d_row, h_row, (int64_t)nbNodes + 1))) return rc;
     if ((rc = upload(&c->d_col, h_col, c->nnz))) return rc;
     return 0;
@@ -188,7 +195,8 @@ extern "C" int dc_cuda_upload_plan(dc_cuda_ctx *c, const struct dc_plan_s *p)
     if ((rc = upload(&c->d_units, p->units, p->nbUnits))) return rc;
     if ((rc = upload(&c->d_tasks, p->tasks, p->nbTasks))) return rc;
     if ((rc = upload(&c->d_items, p->items, p->nbItems))) return rc;
-    if ((rc = upload(&c->d_halo, p->haloElems, p->nbHalo))) return rc;
+    if ((rc = upload(&c->d_halo, p->haloNodes, p->nbHaloNodes))) return rc;
+    if ((rc = upload(&c->d_slotNodes, p->slotNodes, p->nbSlotNodes))) return rc;
     if ((rc = upload(&c->d_diagRel, p->diagRel, (int64_t)c->nbNodes))) return rc;
     if ((rc = upload(&c->d_tgt, p->tgt, 2 * p->nbTgt))) return rc;
     if (p->big.nbEdges > 0 && p->big.edgeT)
@@ -202,6 +210,7 @@ extern "C" int dc_cuda_upload_plan(dc_cuda_ctx *c, const struct dc_plan_s *p)
     c->nbBigEdges = p->big.nbEdges;
     c->maxSlots = p->maxSlots;
     c->maxHalo = p->maxHalo;
+    c->maxNodes = p->maxNodes;
     c->maxTasks = p->maxTasks;
     c->maxItems = p->maxItems;
     c->maxTgt = p->maxTgt;
@@ -210,13 +219,15 @@ extern "C" int dc_cuda_upload_plan(dc_cuda_ctx *c, const struct dc_plan_s *p)
 }
 
 extern "C" int dc_cuda_set_plan_device(dc_cuda_ctx *c, const void *d_units, const void *d_tasks,
-                                       const void *d_items, const int *d_halo, const int *d_diagRel,
-                                       const int *d_tgt, int64_t nbUnits, int maxSlots, int maxHalo,
-                                       int maxTasks, int maxItems, int maxTgt, int symmetric)
+                                       const void *d_items, const void *d_slotNodes, const int *d_haloNodes,
+                                       const int *d_diagRel, const int *d_tgt, int64_t nbUnits, int maxSlots,
+                                       int maxHalo, int maxNodes, int maxTasks, int maxItems, int maxTgt,
+                                       int symmetric)
 {
     if (!c) return fail(-1, "dc_cuda_set_plan_device: null context");
     if ((reinterpret_cast<uintptr_t>(d_units) | reinterpret_cast<uintptr_t>(d_tasks) |
-         reinterpret_cast<uintptr_t>(d_items) | reinterpret_cast<uintptr_t>(d_halo)) & 15)
+         reinterpret_cast<uintptr_t>(d_items) | reinterpret_cast<uintptr_t>(d_haloNodes) |
+         reinterpret_cast<uintptr_t>(d_slotNodes) | reinterpret_cast<uintptr_t>(d_tgt)) & 15)
         return fail(-5, "dc_cuda_set_plan_device: arrays must be 16-byte aligned");
     CK(cudaSetDevice(c->device));
     free_plan(c);
@@ -224,13 +235,14 @@ extern "C" int dc_cuda_set_plan_device(dc_cuda_ctx *c, const void *d_units, cons
     c->d_units = (dc_unit_t *)d_units;
     c->d_tasks = (dc_task_t *)d_tasks;
     c->d_items = (uint16_t *)d_items;
-    c->d_halo = const_cast<int *>(d_halo);
+    c->d_halo = const_cast<int *>(d_haloNodes);
+    c->d_slotNodes = (uint16_t *)d_slotNodes;
     c->d_diagRel = const_cast<int *>(d_diagRel);
     c->d_tgt = const_cast<int *>(d_tgt);
     c->nbUnits = nbUnits;
     c->nbBigEdges = 0;
-    c->maxSlots = maxSlots; c->maxHalo = maxHalo; c->maxTasks = maxTasks; c->maxItems = maxItems;
-    c->maxTgt = maxTgt; c->symmetric = symmetric;
+    c->maxSlots = maxSlots; c->maxHalo = maxHalo; c->maxNodes = maxNodes; c->maxTasks = maxTasks;
+    c->maxItems = maxItems; c->maxTgt = maxTgt; c->symmetric = symmetric;
     return 0;
 }
 
@@ -251,13 +263,15 @@ extern "C" int dc_cuda_upload_lists(dc_cuda_ctx *c, const int64_t *h_edge, const
 template <class Op, int THREADS, int MINB, bool SYM>
 static int launch_units(dc_cuda_ctx *c, double *d_values, cudaStream_t s)
 {
-    const UnitLayout L = UnitSmem<Op>::layout(c->maxSlots, c->maxHalo, c->maxTasks, c->maxItems, c->maxTgt, THREADS);
+    const UnitLayout L = UnitSmem<Op>::layout(c->maxSlots, c->maxHalo, c->maxNodes, c->maxTasks, c->maxItems,
+                                              c->maxTgt, THREADS);
     if (L.total > 227 * 1024) return fail(-11, "dc_cuda_assemble: unit does not fit in shared memory");
     auto kern = gather_units<Op, THREADS, MINB, SYM>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-    kern<<<(unsigned)c->nbUnits, THREADS, (size_t)L.total, s>>>(c->d_units, c->d_tasks, c->d_items, c->d_halo,
-                                                                 c->d_diagRel, reinterpret_cast<const int2 *>(c->d_tgt),
-                                                                 c->d_conn, c->d_coord, d_values, L);
+    kern<<<(unsigned)c->nbUnits, THREADS, (size_t)L.total, s>>>(c->d_units, c->d_tasks, c->d_items, c->d_slotNodes,
+                                                                 c->d_halo, c->d_diagRel,
+                                                                 reinterpret_cast<const int2 *>(c->d_tgt), c->d_coord,
+                                                                 d_values, L);
     return 0;
 }
 

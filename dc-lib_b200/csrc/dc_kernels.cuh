@@ -88,8 +88,10 @@ __device__ __forceinline__ void load_element(const int *__restrict__ conn, const
 
 /* shared-memory geometry of a unit launch, computed on the host from the plan */
 struct UnitLayout {
-    int offStage;    /* region A: own connectivity (TMA target), later per-warp output staging */
-    int offHalo;     /* halo element ids                                                     */
+    int offStage;    /* per-warp output staging                                              */
+    int offSlotN;    /* per slot: 4 uint16 indices into the unit's node table (TMA target)    */
+    int offHnode;    /* halo node ids (TMA target)                                           */
+    int offCoord;    /* coordinates of the node table: own interval (TMA target) + halo nodes */
     int offTasks;    /* dc_task_t records                                                    */
     int offTgt;      /* symmetric schedule: (edge, transposed edge) pairs                    */
     int offItems;    /* uint16 items                                                         */
@@ -105,14 +107,16 @@ struct UnitSmem {
     static constexpr int RS = (Op::NS % 2 == 0) ? Op::NS + 1 : Op::NS;
     /* per-warp staging: 32 blocks + 32 target edges */
     static constexpr int STAGE = 32 * DD * 8 + 32 * 4;
-    static UnitLayout layout(int maxSlots, int maxHalo, int maxTasks, int maxItems, int maxTgt, int threads)
+    static UnitLayout layout(int maxSlots, int maxHalo, int maxNodes, int maxTasks, int maxItems, int maxTgt,
+                             int threads)
     {
         auto up = [](int v) { return (v + 15) & ~15; };
         UnitLayout L;
-        const int a = maxSlots * 16, b = (threads / 32) * STAGE;
         L.offStage = 32;
-        L.offHalo = L.offStage + up(a > b ? a : b);
-        L.offTasks = L.offHalo + up(maxHalo * 4);
+        L.offSlotN = L.offStage + up((threads / 32) * STAGE);
+        L.offHnode = L.offSlotN + up(((maxSlots + 1) & ~1) * 8);
+        L.offCoord = L.offHnode + up(maxHalo * 4);
+        L.offTasks = L.offCoord + up((maxNodes + maxHalo) * 24);
         L.offTgt = L.offTasks + up(maxTasks * 16);
         L.offItems = L.offTgt + up(maxTgt * 8);
         L.offRecs = L.offItems + up(maxItems * 2);
@@ -140,10 +144,10 @@ template <class Op, int THREADS, int MINB, bool SYM>
 __global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *__restrict__ units,
                                                               const dc_task_t *__restrict__ tasks,
                                                               const uint16_t *__restrict__ items,
-                                                              const int *__restrict__ haloElems,
+                                                              const uint16_t *__restrict__ slotNodes,
+                                                              const int *__restrict__ haloNodes,
                                                               const int *__restrict__ diagRel,
                                                               const int2 *__restrict__ tgtPairs,
-                                                              const int *__restrict__ conn,
                                                               const double *__restrict__ coord,
                                                               double *__restrict__ values, const UnitLayout L)
 {
@@ -152,8 +156,9 @@ __global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *_
     constexpr int NW = THREADS / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);          /* bar[0]: mesh data, bar[1]: schedule */
-    int4 *connS = reinterpret_cast<int4 *>(smem_raw + L.offStage);
-    int *haloS = reinterpret_cast<int *>(smem_raw + L.offHalo);
+    const uint2 *slotN = reinterpret_cast<const uint2 *>(smem_raw + L.offSlotN);
+    int *hnodeS = reinterpret_cast<int *>(smem_raw + L.offHnode);
+    double *coordS = reinterpret_cast<double *>(smem_raw + L.offCoord);
     dc_task_t *taskS = reinterpret_cast<dc_task_t *>(smem_raw + L.offTasks);
     int2 *tgtS = reinterpret_cast<int2 *>(smem_raw + L.offTgt);
     uint16_t *itemS = reinterpret_cast<uint16_t *>(smem_raw + L.offItems);
@@ -162,20 +167,26 @@ __global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *_
     const dc_unit_t u = units[blockIdx.x];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nSlots = u.ownElemCount + u.haloCount;
+    /* the unit's node table starts at the even node at or below nodeFirst and spans an even
+     * number of nodes: 48-byte granules, so the own coordinates are one aligned bulk copy */
+    const int alignedFirst = u.nodeFirst & ~1;
+    const int ownSpan = ((u.nodeFirst + u.nodeCount + 1) & ~1) - alignedFirst;
 
     /* P0: everything the unit reads that is contiguous in HBM comes in as TMA bulk copies:
-     * own connectivity rows (tree order makes them one range), halo ids, tasks, items, targets */
+     * slot -> node-table indices, halo node ids, own coordinates; tasks, items, targets */
     if (tid == 0) {
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
     }
     __syncthreads();
     if (tid == 0) {
-        const uint32_t ownBytes = (uint32_t)u.ownElemCount * 16u;
-        const uint32_t haloBytes = (uint32_t)((u.haloCount + 3) & ~3) * 4u;
-        mbar_expect_tx(&bar[0], ownBytes + haloBytes);
-        if (ownBytes) tma_bulk_g2s(connS, reinterpret_cast<const int4 *>(conn) + u.ownElemFirst, ownBytes, &bar[0]);
-        if (haloBytes) tma_bulk_g2s(haloS, haloElems + u.haloFirst, haloBytes, &bar[0]);
+        const uint32_t slotBytes = (uint32_t)((nSlots + 1) & ~1) * 8u;
+        const uint32_t hnodeBytes = (uint32_t)u.hnodeCount * 4u;
+        const uint32_t coordBytes = (uint32_t)ownSpan * 24u;
+        mbar_expect_tx(&bar[0], slotBytes + hnodeBytes + coordBytes);
+        if (slotBytes) tma_bulk_g2s(const_cast<uint2 *>(slotN), slotNodes + u.slotFirst * 4, slotBytes, &bar[0]);
+        if (hnodeBytes) tma_bulk_g2s(hnodeS, haloNodes + u.hnodeFirst, hnodeBytes, &bar[0]);
+        if (coordBytes) tma_bulk_g2s(coordS, coord + (int64_t)alignedFirst * 3, coordBytes, &bar[0]);
         const uint32_t taskBytes = (uint32_t)u.taskCount * 16u, itemBytes = (uint32_t)u.itemCount * 2u;
         const uint32_t tgtBytes = SYM ? (uint32_t)((u.tgtCount + 1) & ~1) * 8u : 0u;
         mbar_expect_tx(&bar[1], taskBytes + itemBytes + tgtBytes);
@@ -185,40 +196,32 @@ __global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *_
     }
     mbar_wait(&bar[0], 0);
 
-    /* P1: one record per touched element; two elements per thread in flight so that the
-     * (L2-latency) coordinate gathers of one overlap the arithmetic of the other */
-    for (int s0 = tid; s0 < nSlots; s0 += 2 * THREADS) {
-        const int s1 = s0 + THREADS;
-        const bool two = s1 < nSlots;
-        int4 c0, c1;
-        c0 = (s0 < u.ownElemCount) ? connS[s0]
-                                   : __ldg(reinterpret_cast<const int4 *>(conn) + haloS[s0 - u.ownElemCount]);
-        c1 = c0;
-        if (two)
-            c1 = (s1 < u.ownElemCount) ? connS[s1]
-                                       : __ldg(reinterpret_cast<const int4 *>(conn) + haloS[s1 - u.ownElemCount]);
-        const int n0[4] = {c0.x - 1, c0.y - 1, c0.z - 1, c0.w - 1};
-        const int n1[4] = {c1.x - 1, c1.y - 1, c1.z - 1, c1.w - 1};
-        double x0[4][3], x1[4][3];
+    /* P1a: coordinates of the halo nodes (one gather per node, not per element) */
+    for (int i = tid; i < u.hnodeCount; i += THREADS) {
+        const double *src = coord + (int64_t)hnodeS[i] * 3;
+        double *dst = coordS + (ownSpan + i) * 3;
+        dst[0] = __ldg(src);
+        dst[1] = __ldg(src + 1);
+        dst[2] = __ldg(src + 2);
+    }
+    __syncthreads();
+
+    /* P1b: one record per touched element, everything from shared memory */
+    for (int s = tid; s < nSlots; s += THREADS) {
+        const uint2 ln = slotN[s];
+        const uint32_t n[4] = {ln.x & 0xFFFFu, ln.x >> 16, ln.y & 0xFFFFu, ln.y >> 16};
+        double x[4][3];
 #pragma unroll
         for (int a = 0; a < 4; a++)
 #pragma unroll
-            for (int k = 0; k < 3; k++) {
-                x0[a][k] = __ldg(coord + (int64_t)n0[a] * 3 + k);
-                x1[a][k] = __ldg(coord + (int64_t)n1[a] * 3 + k);
-            }
+            for (int k = 0; k < 3; k++) x[a][k] = coordS[n[a] * 3 + k];
         double rec[Op::NS];
-        Op::setup(x0, c_params, rec);
+        Op::setup(x, c_params, rec);
 #pragma unroll
-        for (int i = 0; i < Op::NS; i++) recs[s0 * RS + i] = rec[i];
-        if (two) {
-            Op::setup(x1, c_params, rec);
-#pragma unroll
-            for (int i = 0; i < Op::NS; i++) recs[s1 * RS + i] = rec[i];
-        }
+        for (int i = 0; i < Op::NS; i++) recs[s * RS + i] = rec[i];
     }
     mbar_wait(&bar[1], 0);
-    __syncthreads();   /* records complete; region A is free for staging from here on */
+    __syncthreads();   /* records complete */
 
     /* P2: tasks round-robin over warps; a lane owns one CSR edge and adds its contributions
      * in ascending element order (the order of the item rows) */

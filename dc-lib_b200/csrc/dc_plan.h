@@ -10,7 +10,11 @@
  * (src/tree_creation.cc:185-186), and writes every value of that interval
  * exactly once -- the reset is fused into that single write.  The elements a unit
  * needs are its own contiguous range [firstElem, lastSep] plus the "halo":
- * elements of ancestor separators that touch one of its nodes.
+ * elements of ancestor separators that touch one of its nodes.  Each element gets a
+ * SLOT; slotNodes gives its 4 nodes as indices into the unit's node table (the own
+ * node interval, whose coordinates are one contiguous block of the coordinate array,
+ * followed by the halo nodes), so the kernel stages all coordinates in shared memory
+ * once instead of gathering them per element.
  *
  * Inside a unit every CSR edge is summed in ascending element index, which is the
  * order the reference's traversal produces (left < right < separator in element
@@ -31,17 +35,20 @@
 typedef struct {
     int64_t edgeFirst;      /* first CSR edge of the unit                          */
     int64_t itemFirst;      /* first uint16 item of the unit                       */
-    int64_t haloFirst;      /* first entry of haloElems                            */
+    int64_t tgtFirst;       /* symmetric schedule: first (edge, transposed edge) pair */
+    int64_t slotFirst;      /* first entry of slotNodes (4 uint16 per slot)        */
+    int64_t hnodeFirst;     /* first entry of haloNodes                            */
+    int64_t haloFirst;      /* first entry of haloElems (host-side bookkeeping)    */
     int32_t edgeCount;
     int32_t nodeFirst, nodeCount;
     int32_t ownElemFirst, ownElemCount;   /* slots [0, ownElemCount)                */
     int32_t haloCount;                    /* slots [ownElemCount, +haloCount)       */
     int32_t taskFirst, taskCount;
     int32_t itemCount;                    /* uint16 items of the unit (multiple of 32) */
-    int64_t tgtFirst;                     /* symmetric schedule: first (edge, transposed edge) pair */
-    int32_t tgtCount;                     /* upper edges of the unit                               */
+    int32_t tgtCount;                     /* owned edges of the unit (symmetric schedule) */
+    int32_t hnodeCount;                   /* nodes used by the unit outside its own interval */
     int32_t pad_;
-} dc_unit_t;                /* 80 bytes */
+} dc_unit_t;                /* 96 bytes */
 
 typedef struct {
     uint32_t itemRel;       /* items of this task start at unit.itemFirst+itemRel  */
@@ -67,7 +74,8 @@ typedef struct {
 
 typedef struct dc_plan_s {
     int32_t  maxSlots;      /* largest slot count of any unit                      */
-    int32_t  maxHalo;       /* largest halo list (entries, padded to 4)            */
+    int32_t  maxHalo;       /* largest halo-node list (entries, padded to 4)       */
+    int32_t  maxNodes;      /* most own nodes in one unit                          */
     int32_t  maxTasks;      /* most tasks in one unit                              */
     int32_t  maxItems;      /* most uint16 items in one unit                       */
     int32_t  maxTgt;        /* most upper edges in one unit (symmetric schedule)   */
@@ -78,7 +86,12 @@ typedef struct dc_plan_s {
     dc_unit_t *units;
     dc_task_t *tasks;
     uint16_t  *items;
-    int32_t   *haloElems;
+    int32_t   *haloElems;   /* element of every halo slot (not needed on the device) */
+    int64_t    nbSlotNodes; /* uint16 entries in slotNodes (4 per slot, units padded to 2 slots) */
+    uint16_t  *slotNodes;   /* per slot: the element's 4 nodes as indices into the unit's node table: */
+                            /* own nodes first (from nodeFirst & ~1), then haloNodes                */
+    int64_t    nbHaloNodes;
+    int32_t   *haloNodes;   /* node ids outside the unit's own interval            */
     int32_t   *diagRel;     /* [nbNodes] edge offset (in its unit) of node's diagonal, -1 if none */
     dc_contrib_list_t big;  /* rows that did not fit a unit                        */
     /* statistics */

@@ -161,6 +161,8 @@ struct Selector {
 struct UnitOut {
     std::vector<dc_task_t> tasks;
     std::vector<uint16_t> items;
+    std::vector<uint16_t> slotNodes;   /* 4 per slot */
+    std::vector<int32_t> haloNodes;
     std::vector<int32_t> tgt;      /* symmetric schedule: (edge, transposed edge) per upper edge */
     int64_t useful = 0;
 };
@@ -189,6 +191,39 @@ void build_unit(const Mesh &m, const UnitSeed &s, int32_t *diagRel, UnitOut &out
     if ((int)perEdge.size() < edgeCount) perEdge.resize((size_t)edgeCount);
     for (int k = 0; k < edgeCount; k++) perEdge[k].clear();
     std::vector<char> isDiag((size_t)edgeCount, 0);
+
+    /* node table: own interval (from the even node at or below nodeFirst, padded to an even
+     * count so that the block of coordinates is a 16-byte granule copy), then halo nodes */
+    {
+        const int alignedFirst = s.nodeFirst & ~1;
+        const int ownSpan = ((s.nodeFirst + s.nodeCount + 1) & ~1) - alignedFirst;
+        const int nSlots = s.ownCount + (int)s.halo.size();
+        std::vector<int> outside;
+        for (int sl = 0; sl < nSlots; sl++) {
+            const int e = sl < s.ownCount ? s.ownFirst + sl : s.halo[(size_t)(sl - s.ownCount)];
+            for (int j = 0; j < 4; j++) {
+                const int nd = m.conn[(int64_t)e * 4 + j] - 1;
+                if (nd < s.nodeFirst || nd >= s.nodeFirst + s.nodeCount) outside.push_back(nd);
+            }
+        }
+        std::sort(outside.begin(), outside.end());
+        outside.erase(std::unique(outside.begin(), outside.end()), outside.end());
+        if (ownSpan + (int)outside.size() > 65535) { error = 1; return; }
+        out.haloNodes.assign(outside.begin(), outside.end());
+        out.slotNodes.resize((size_t)nSlots * 4);
+        for (int sl = 0; sl < nSlots; sl++) {
+            const int e = sl < s.ownCount ? s.ownFirst + sl : s.halo[(size_t)(sl - s.ownCount)];
+            for (int j = 0; j < 4; j++) {
+                const int nd = m.conn[(int64_t)e * 4 + j] - 1;
+                int idx;
+                if (nd >= s.nodeFirst && nd < s.nodeFirst + s.nodeCount) idx = nd - alignedFirst;
+                else idx = ownSpan + (int)(std::lower_bound(outside.begin(), outside.end(), nd) - outside.begin());
+                out.slotNodes[(size_t)sl * 4 + j] = (uint16_t)idx;
+            }
+        }
+        while (out.slotNodes.size() % 8) out.slotNodes.push_back(0);    /* 16-byte granules */
+        while (out.haloNodes.size() % 4) out.haloNodes.push_back(0);
+    }
 
     for (int n = s.nodeFirst; n < s.nodeFirst + s.nodeCount; n++) {
         const int r0 = m.row[n], r1 = m.row[n + 1];
@@ -433,6 +468,8 @@ extern "C" int dc_plan_build(dc_plan_t *plan, const int *conn, int nbElem, int n
     std::vector<std::vector<dc_task_t>> tTasks((size_t)nt);
     std::vector<std::vector<uint16_t>> tItems((size_t)nt);
     std::vector<std::vector<int32_t>> tTgt((size_t)nt);
+    std::vector<std::vector<uint16_t>> tSlot((size_t)nt);
+    std::vector<std::vector<int32_t>> tHnode((size_t)nt);
     std::vector<int> unitThread((size_t)nbUnits);
     int error = 0;
     int64_t useful = 0;
@@ -448,6 +485,8 @@ extern "C" int dc_plan_build(dc_plan_t *plan, const int *conn, int nbElem, int n
             out.tasks.clear();
             out.items.clear();
             out.tgt.clear();
+            out.slotNodes.clear();
+            out.haloNodes.clear();
             out.useful = 0;
             build_unit(m, s, diagRel.data(), out, perEdge, error, symmetric != 0);
             const int32_t nbUpper = (int32_t)(out.tgt.size() / 2);
@@ -467,6 +506,14 @@ extern "C" int dc_plan_build(dc_plan_t *plan, const int *conn, int nbElem, int n
             d.itemCount = (int32_t)out.items.size();
             d.tgtFirst = (int64_t)(tTgt[tid].size() / 2);
             d.tgtCount = nbUpper;
+            d.slotFirst = (int64_t)(tSlot[tid].size() / 4);
+            d.hnodeFirst = (int64_t)tHnode[tid].size();
+            {
+                int hn = (int)out.haloNodes.size();          /* padded; the true count is recovered below */
+                d.hnodeCount = hn;
+            }
+            tSlot[tid].insert(tSlot[tid].end(), out.slotNodes.begin(), out.slotNodes.end());
+            tHnode[tid].insert(tHnode[tid].end(), out.haloNodes.begin(), out.haloNodes.end());
             tTgt[tid].insert(tTgt[tid].end(), out.tgt.begin(), out.tgt.end());
             unitThread[(size_t)u] = tid;
             tTasks[tid].insert(tTasks[tid].end(), out.tasks.begin(), out.tasks.end());
@@ -478,10 +525,23 @@ extern "C" int dc_plan_build(dc_plan_t *plan, const int *conn, int nbElem, int n
     lap("units");
 
     std::vector<int64_t> taskBase((size_t)nt + 1, 0), itemBase((size_t)nt + 1, 0), tgtBase((size_t)nt + 1, 0);
+    std::vector<int64_t> slotBase((size_t)nt + 1, 0), hnodeBase((size_t)nt + 1, 0);
     for (int t = 0; t < nt; t++) {
         taskBase[(size_t)t + 1] = taskBase[t] + (int64_t)tTasks[t].size();
         itemBase[(size_t)t + 1] = itemBase[t] + (int64_t)tItems[t].size();
         tgtBase[(size_t)t + 1] = tgtBase[t] + (int64_t)(tTgt[t].size() / 2);
+        slotBase[(size_t)t + 1] = slotBase[t] + (int64_t)(tSlot[t].size() / 4);
+        hnodeBase[(size_t)t + 1] = hnodeBase[t] + (int64_t)tHnode[t].size();
+    }
+    plan->nbSlotNodes = slotBase[nt] * 4;
+    plan->slotNodes = (uint16_t *)malloc(sizeof(uint16_t) * (size_t)(plan->nbSlotNodes ? plan->nbSlotNodes : 1));
+    plan->nbHaloNodes = hnodeBase[nt];
+    plan->haloNodes = (int32_t *)malloc(sizeof(int32_t) * (size_t)(plan->nbHaloNodes ? plan->nbHaloNodes : 1));
+    for (int t = 0; t < nt; t++) {
+        if (!tSlot[t].empty()) memcpy(plan->slotNodes + 4 * slotBase[t], tSlot[t].data(), sizeof(uint16_t) * tSlot[t].size());
+        if (!tHnode[t].empty()) memcpy(plan->haloNodes + hnodeBase[t], tHnode[t].data(), sizeof(int32_t) * tHnode[t].size());
+        std::vector<uint16_t>().swap(tSlot[t]);
+        std::vector<int32_t>().swap(tHnode[t]);
     }
     plan->symmetric = symmetric ? 1 : 0;
     plan->nbTgt = tgtBase[nt];
@@ -502,19 +562,22 @@ extern "C" int dc_plan_build(dc_plan_t *plan, const int *conn, int nbElem, int n
         std::vector<uint16_t>().swap(tItems[t]);
     }
     int64_t haloTotal = 0, slotsTotal = 0;
-    int maxUsed = 0, maxHalo = 0, maxTasks = 0, maxItems = 0, maxTgt = 0;
+    int maxUsed = 0, maxHalo = 0, maxTasks = 0, maxItems = 0, maxTgt = 0, maxNodes = 0;
     for (int64_t u = 0; u < nbUnits; u++) {
         dc_unit_t &d = units[(size_t)u];
         const int t = unitThread[(size_t)u];
         d.taskFirst += (int32_t)taskBase[t];
         d.itemFirst += itemBase[t];
         d.tgtFirst += tgtBase[t];
+        d.slotFirst += slotBase[t];
+        d.hnodeFirst += hnodeBase[t];
         maxTgt = std::max(maxTgt, (d.tgtCount + 1) & ~1);
+        maxNodes = std::max(maxNodes, ((d.nodeFirst + d.nodeCount + 1) & ~1) - (d.nodeFirst & ~1));
         d.haloFirst = haloTotal;                       /* multiple of 4: bulk copies need 16-byte sources */
         haloTotal += (d.haloCount + 3) & ~3;
         slotsTotal += d.ownElemCount + d.haloCount;
         maxUsed = std::max(maxUsed, d.ownElemCount + d.haloCount);
-        maxHalo = std::max(maxHalo, (d.haloCount + 3) & ~3);
+        maxHalo = std::max(maxHalo, d.hnodeCount);
         maxTasks = std::max(maxTasks, d.taskCount);
         maxItems = std::max(maxItems, d.itemCount);
     }
@@ -522,6 +585,7 @@ extern "C" int dc_plan_build(dc_plan_t *plan, const int *conn, int nbElem, int n
     plan->maxTasks = maxTasks;
     plan->maxItems = maxItems;
     plan->maxTgt = maxTgt;
+    plan->maxNodes = maxNodes;
     plan->haloElems = (int32_t *)calloc((size_t)(haloTotal ? haloTotal : 1), sizeof(int32_t));
     for (int64_t u = 0; u < nbUnits; u++) {
         const std::vector<int> &h = seeds[(size_t)u].halo;
@@ -552,7 +616,7 @@ extern "C" void dc_contrib_free(dc_contrib_list_t *c)
 extern "C" void dc_plan_free(dc_plan_t *plan)
 {
     free(plan->units); free(plan->tasks); free(plan->items); free(plan->haloElems); free(plan->diagRel);
-    free(plan->tgt);
+    free(plan->tgt); free(plan->slotNodes); free(plan->haloNodes);
     dc_contrib_free(&plan->big);
     memset(plan, 0, sizeof *plan);
 }

@@ -121,7 +121,8 @@ def setup_device_slabs(n, rank, world, device, builder="geometric", vec=0, slots
 
     from . import Context, HostPlan, permute_double_2d
 
-    names = ["conn", "row", "col", "node_perm", "units", "tasks", "items", "halo", "diagRel", "tgt", "intf_left", "intf_right"]
+    names = ["conn", "row", "col", "node_perm", "units", "tasks", "items", "slotNodes", "haloNodes", "diagRel", "tgt",
+             "intf_left", "intf_right"]
     t0 = time.time()
     tensors, meta = {}, None
     if rank == 0:
@@ -136,7 +137,8 @@ def setup_device_slabs(n, rank, world, device, builder="geometric", vec=0, slots
         if arr["bigEdges"]:
             raise RuntimeError("setup_device_slabs: rows exceeding the unit budget are not supported on this path")
         host = dict(conn=slab["conn"], row=slab["row"], col=slab["col"], node_perm=node_perm, units=arr["units"],
-                    tasks=arr["tasks"], items=arr["items"].view(np.int16), halo=arr["halo"],
+                    tasks=arr["tasks"], items=arr["items"].view(np.int16), slotNodes=arr["slotNodes"].view(np.int16),
+                    haloNodes=arr["haloNodes"],
                     diagRel=plan.diag_rel(slab["N"]), tgt=arr["tgt"],
                     intf_left=plane_edges(node_perm, slab["row"], slab["col"], n, 0) if world > 1 else np.zeros(0, np.int64),
                     intf_right=plane_edges(node_perm, slab["row"], slab["col"], n, n) if world > 1 else np.zeros(0, np.int64))
@@ -144,7 +146,7 @@ def setup_device_slabs(n, rank, world, device, builder="geometric", vec=0, slots
             tensors[k] = torch.from_numpy(np.ascontiguousarray(host[k])).to(device)
         st = plan.stats()
         meta = dict(shapes={k: (tuple(tensors[k].shape), str(tensors[k].dtype)) for k in names},
-                    ints={k: arr[k] for k in ("nbUnits", "maxSlots", "maxHalo", "maxTasks", "maxItems", "maxTgt", "symmetric")},
+                    ints={k: arr[k] for k in ("nbUnits", "maxSlots", "maxHalo", "maxNodes", "maxTasks", "maxItems", "maxTgt", "symmetric")},
                     E=slab["E"], N=slab["N"], nnz=slab["nnz"], stats=st, tree_s=t_tree, plan_s=t_plan)
         del plan, slab, host, arr
     if world > 1:
@@ -160,14 +162,15 @@ def setup_device_slabs(n, rank, world, device, builder="geometric", vec=0, slots
     # own coordinates: generated in the original numbering, permuted on the device
     _, coord_old, _ = kuhn_cube_fast(n, seed=seed, x_offset=rank * n, coords_only=True)
     d_old = torch.from_numpy(coord_old).to(device)
-    d_coord = torch.empty_like(d_old)
+    d_coord = torch.zeros((d_old.shape[0] + 2, 3), dtype=torch.float64, device=device)[:d_old.shape[0]]   # 2 spare nodes
     permute_double_2d(d_old, d_coord, tensors["node_perm"], 3, torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     del d_old, coord_old
     ctx = Context(torch.device(device).index or 0)
     ctx.set_mesh_device(tensors["conn"], d_coord, tensors["row"], tensors["col"], meta["nnz"], 0)
-    plan_t = dict(units=tensors["units"], tasks=tensors["tasks"], items=tensors["items"], halo=tensors["halo"],
-                  diagRel=tensors["diagRel"], tgt=tensors["tgt"], **meta["ints"])
+    plan_t = dict(units=tensors["units"], tasks=tensors["tasks"], items=tensors["items"],
+                  slotNodes=tensors["slotNodes"], haloNodes=tensors["haloNodes"], diagRel=tensors["diagRel"],
+                  tgt=tensors["tgt"], **meta["ints"])
     ctx.set_plan_device(plan_t)
     intf = {}
     if rank > 0:

@@ -44,7 +44,9 @@ void dc_cuda_destroy(dc_cuda_ctx *ctx);
  * renumbered, tree order; h_coord: [nbNodes][3]; h_row: [nbNodes+1]; h_col: [nnz]. */
 int  dc_cuda_set_mesh(dc_cuda_ctx *ctx, const int *h_conn, const double *h_coord,
                       const int *h_row, const int *h_col, int nbElem, int nbNodes, int colBase);
-/* Same, adopting arrays that already live in device memory (not copied, not freed). */
+/* Same, adopting arrays that already live in device memory (not copied, not freed).
+ * d_coord must have room for 2 nodes (48 bytes) beyond nbNodes: the kernel copies a unit's
+ * own coordinates as 48-byte granules. */
 int  dc_cuda_set_mesh_device(dc_cuda_ctx *ctx, const int *d_conn, const double *d_coord,
                              const int *d_row, const int *d_col, int nbElem, int nbNodes,
                              int64_t nnz, int colBase);
@@ -56,9 +58,10 @@ int  dc_cuda_upload_plan(dc_cuda_ctx *ctx, const struct dc_plan_s *plan);
 /* Same, adopting schedule arrays that already live in device memory (e.g. received from
  * another rank over NCCL); not copied, not freed.  No big-row fallback list on this path. */
 int  dc_cuda_set_plan_device(dc_cuda_ctx *ctx, const void *d_units, const void *d_tasks,
-                             const void *d_items, const int *d_halo, const int *d_diagRel,
-                             const int *d_tgt, int64_t nbUnits, int maxSlots, int maxHalo,
-                             int maxTasks, int maxItems, int maxTgt, int symmetric);
+                             const void *d_items, const void *d_slotNodes, const int *d_haloNodes,
+                             const int *d_diagRel, const int *d_tgt, int64_t nbUnits, int maxSlots,
+                             int maxHalo, int maxNodes, int maxTasks, int maxItems, int maxTgt,
+                             int symmetric);
 /* Explicit contribution lists for DC_MODE_LIST (all edges). */
 int  dc_cuda_upload_lists(dc_cuda_ctx *ctx, const int64_t *h_edge, const int64_t *h_ptr,
                           const uint32_t *h_item, int64_t nbEdges, int64_t nbItems);

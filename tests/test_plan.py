@@ -27,6 +27,8 @@ def test_plan_covers_every_contribution_once(tmp_path, n, vec, slots, hub, sym):
     plan = dc.HostPlan(mesh["conn"], mesh["N"], mesh["row"], mesh["col"], 0, rec, slots, symmetric=sym)
     units, tasks, items, halo = _plan_arrays(plan)
     tgt = np.ctypeslib.as_array(plan.c.tgt, shape=(max(plan.c.nbTgt, 1), 2))
+    slotNodes = np.ctypeslib.as_array(plan.c.slotNodes, shape=(max(plan.c.nbSlotNodes, 1),))
+    haloNodes = np.ctypeslib.as_array(plan.c.haloNodes, shape=(max(plan.c.nbHaloNodes, 1),))
     rows_of = np.repeat(np.arange(mesh["N"]), np.diff(mesh["row"]))
     E, N, nnz = mesh["E"], mesh["N"], mesh["nnz"]
     conn = mesh["conn"].astype(np.int64) - 1
@@ -50,6 +52,14 @@ def test_plan_covers_every_contribution_once(tmp_path, n, vec, slots, hub, sym):
         assert nslots <= slots
         elems = list(range(u.ownElemFirst, u.ownElemFirst + u.ownElemCount)) + \
             halo[u.haloFirst:u.haloFirst + u.haloCount].tolist()
+        # node table: own interval from the even node at or below nodeFirst, then the halo nodes
+        aligned = u.nodeFirst & ~1
+        span = ((u.nodeFirst + u.nodeCount + 1) & ~1) - aligned
+        hn = haloNodes[u.hnodeFirst:u.hnodeFirst + u.hnodeCount]
+        sn = slotNodes[u.slotFirst * 4:(u.slotFirst + nslots) * 4].reshape(nslots, 4).astype(np.int64)
+        resolved = np.where(sn < span, sn + aligned, hn[np.clip(sn - span, 0, max(len(hn) - 1, 0))] if len(hn) else sn + aligned)
+        assert np.array_equal(resolved, conn[elems])
+        assert u.slotFirst % 2 == 0 and u.hnodeFirst % 4 == 0 and u.hnodeCount % 4 == 0
         for t in tasks[u.taskFirst:u.taskFirst + u.taskCount]:
             block = items[u.itemFirst + t.itemRel:u.itemFirst + t.itemRel + 32 * t.iters].reshape(t.iters, 32)
             assert (t.kind == 2) == sym
