@@ -286,8 +286,10 @@ static int assemble_t(dc_cuda_ctx *c, int mode, double *d_values, cudaStream_t s
                 return fail(-13, "dc_cuda_assemble: symmetric schedule with a non-symmetric operator");
             int rc;
             if (c->symmetric)
-                rc = (c->threads == 128) ? launch_units<Op, 128, 4, true>(c, d_values, s)
-                                         : launch_units<Op, 256, 2, true>(c, d_values, s);
+                rc = (c->threads == 128)   ? launch_units<Op, 128, 4, true>(c, d_values, s)
+                     : (c->threads == 192) ? launch_units<Op, 192, 3, true>(c, d_values, s)
+                     : (c->threads == 257) ? launch_units<Op, 256, 3, true>(c, d_values, s)
+                                           : launch_units<Op, 256, 2, true>(c, d_values, s);
             else
                 rc = (c->threads == 128) ? launch_units<Op, 128, 4, false>(c, d_values, s)
                                          : launch_units<Op, 256, 2, false>(c, d_values, s);
@@ -449,7 +451,8 @@ extern "C" int dc_cuda_set_option(dc_cuda_ctx *c, const char *name, int value)
 {
     if (!c || !name) return fail(-1, "dc_cuda_set_option: null argument");
     if (!strcmp(name, "unit_threads")) {
-        if (value != 128 && value != 256) return fail(-12, "dc_cuda_set_option: unit_threads must be 128 or 256");
+        if (value != 128 && value != 192 && value != 256 && value != 257)
+            return fail(-12, "dc_cuda_set_option: unit_threads must be 128, 192 or 256");
         c->threads = value;
         return 0;
     }

@@ -233,6 +233,28 @@ __global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *_
         double acc[DD];
 #pragma unroll
         for (int c = 0; c < DD; c++) acc[c] = 0.0;
+        if (SYM && task.kind == DC_TASK_OWNDIAG) {
+            /* diagonal edges only: one gradient per contribution, symmetric block */
+            for (int i = 0; i < task.iters; i++) {
+                const uint32_t cur = it[i * 32];
+                if (cur != DC_ITEM_NULL) Op::accumulate_diag(recs + (cur >> 4) * RS, c_params, cur & 3u, acc);
+            }
+            Op::mirror(acc);
+            const bool valid = (task.mask >> lane) & 1u;
+            int t0 = -1;
+            if (valid) t0 = tgtS[(int)task.first + lane].x;
+            if (DD == 1) {
+                if (valid) st_stream_f64(values + t0, acc[0]);
+            } else {
+#pragma unroll
+                for (int c = 0; c < DD; c++) myStage[lane * DD + c] = acc[c];
+                myTgt[lane] = t0;
+                __syncwarp();
+                flush_stage<DD>(values, myStage, myTgt, lane);
+                __syncwarp();
+            }
+            continue;
+        }
         for (int i = 0; i < task.iters; i++) {
             const uint32_t cur = it[i * 32];
             if (cur != DC_ITEM_NULL) Op::accumulate(recs + (cur >> 4) * RS, c_params, cur & 15u, acc);

@@ -89,6 +89,13 @@ struct OpLaplacian {
         const uint32_t q = (uint32_t)(0x9863875265413210ULL >> (4 * ab)) & 15u;
         acc[0] = __dadd_rn(acc[0], rec[q]);
     }
+    /* diagonal block (a == b): same update */
+    template <typename R>
+    __device__ __forceinline__ static void accumulate_diag(R rec, const double *params, uint32_t a, double (&acc)[1])
+    {
+        accumulate(rec, params, 5u * a, acc);
+    }
+    __device__ __forceinline__ static void mirror(double (&)[1]) {}
 };
 
 /* Isotropic linear elasticity, 3x3 blocks, volume folded symmetrically into the gradients:
@@ -134,6 +141,37 @@ struct OpElasticity {
                 if (i == j) v = __fma_rn(mu, dot, v);
                 acc[i * 3 + j] = v;
             }
+    }
+    /* diagonal block (a == b): p is symmetric bit for bit (p[i][j] = h_i*h_j), so the lower
+     * triangle repeats the upper one -- 6 products, 6 update chains, one gradient read.
+     * acc must be (and stays) symmetric; only its upper triangle is updated here and
+     * mirror() completes it before the block is stored. */
+    template <typename R>
+    __device__ __forceinline__ static void accumulate_diag(R rec, const double *params, uint32_t a, double (&acc)[9])
+    {
+        const double h[3] = {rec[3 * a], rec[3 * a + 1], rec[3 * a + 2]};
+        const double lam = params[0], mu = params[1];
+        double p[3][3];
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = i; j < 3; j++) p[i][j] = __dmul_rn(h[i], h[j]);
+        const double dot = __dadd_rn(__dadd_rn(p[0][0], p[1][1]), p[2][2]);
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = i; j < 3; j++) {
+                double v = __fma_rn(lam, p[i][j], acc[i * 3 + j]);
+                v = __fma_rn(mu, p[i][j], v);
+                if (i == j) v = __fma_rn(mu, dot, v);
+                acc[i * 3 + j] = v;
+            }
+    }
+    __device__ __forceinline__ static void mirror(double (&acc)[9])
+    {
+        acc[3] = acc[1];
+        acc[6] = acc[2];
+        acc[7] = acc[5];
     }
 };
 

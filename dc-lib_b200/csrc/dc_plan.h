@@ -31,6 +31,8 @@
 #define DC_TASK_UPPER  2            /* symmetric schedule: 32 owned edges (diagonal or col > row) */
                                     /* listed in tgt; an upper-edge lane also writes the        */
                                     /* transposed block to (col,row)                            */
+#define DC_TASK_OWNDIAG 3           /* symmetric schedule: 32 owned DIAGONAL edges (a == b in    */
+                                    /* every item, no transposed target)                        */
 
 typedef struct {
     int64_t edgeFirst;      /* first CSR edge of the unit                          */

@@ -269,31 +269,45 @@ void build_unit(const Mesh &m, const UnitSeed &s, int32_t *diagRel, UnitOut &out
                 const int rel = (int)(k - edgeFirst);
                 owned.push_back(Owned{rel, k, kt, (int)perEdge[(size_t)rel].size()});
             }
-        std::stable_sort(owned.begin(), owned.end(), [](const Owned &x, const Owned &y) { return x.count > y.count; });
+        /* diagonals first (their own task kind: only one gradient per contribution, symmetric
+         * block), then upper edges; inside each class by descending contribution count */
+        std::stable_sort(owned.begin(), owned.end(), [](const Owned &x, const Owned &y) {
+            const bool dx = x.kt < 0, dy = y.kt < 0;
+            if (dx != dy) return dx;
+            return x.count > y.count;
+        });
         for (const Owned &o : owned) {
             out.tgt.push_back(o.k);
             out.tgt.push_back(o.kt);
         }
+        size_t nbDiag = 0;
+        while (nbDiag < owned.size() && owned[nbDiag].kt < 0) nbDiag++;
         for (size_t base = 0; base < owned.size(); base += 32) {
+            const bool diagTask = base < nbDiag;
+            const size_t classEnd = diagTask ? nbDiag : owned.size();
             dc_task_t t;
-            t.kind = DC_TASK_UPPER;
+            t.kind = diagTask ? DC_TASK_OWNDIAG : DC_TASK_UPPER;
             t.first = (uint32_t)base;
             t.mask = 0;
             t.itemRel = (uint32_t)out.items.size();
             size_t iters = 0;
-            for (size_t l = 0; l < 32 && base + l < owned.size(); l++) {
+            if (diagTask && base + 32 > nbDiag) {
+                /* last diagonal task: stop at the class boundary, the next task starts there */
+            }
+            for (size_t l = 0; l < 32 && base + l < classEnd; l++) {
                 t.mask |= 1u << l;
                 iters = std::max(iters, (size_t)owned[base + l].count);
             }
             t.iters = (uint16_t)iters;
             out.items.resize(out.items.size() + iters * 32, (uint16_t)DC_ITEM_NULL);
             uint16_t *dst = out.items.data() + t.itemRel;
-            for (size_t l = 0; l < 32 && base + l < owned.size(); l++) {
+            for (size_t l = 0; l < 32 && base + l < classEnd; l++) {
                 const std::vector<uint16_t> &v = perEdge[(size_t)owned[base + l].rel];
                 for (size_t i = 0; i < v.size(); i++) dst[i * 32 + l] = v[i];
                 out.useful += (int64_t)v.size();
             }
             out.tasks.push_back(t);
+            if (diagTask && base + 32 > nbDiag) base = nbDiag - 32;      /* next task begins at the boundary */
         }
         return;
     }

@@ -62,7 +62,7 @@ def test_plan_covers_every_contribution_once(tmp_path, n, vec, slots, hub, sym):
         assert u.slotFirst % 2 == 0 and u.hnodeFirst % 4 == 0 and u.hnodeCount % 4 == 0
         for t in tasks[u.taskFirst:u.taskFirst + u.taskCount]:
             block = items[u.itemFirst + t.itemRel:u.itemFirst + t.itemRel + 32 * t.iters].reshape(t.iters, 32)
-            assert (t.kind == 2) == sym
+            assert (t.kind in (2, 3)) == sym
             for lane in range(32):
                 kT = -1
                 if t.kind == 0:
@@ -70,13 +70,14 @@ def test_plan_covers_every_contribution_once(tmp_path, n, vec, slots, hub, sym):
                         assert (block[:, lane] == 0xFFFF).all()
                         continue
                     k = u.edgeFirst + t.first + lane
-                elif t.kind == 2:
+                elif t.kind in (2, 3):
                     if not (t.mask >> lane) & 1:
                         assert (block[:, lane] == 0xFFFF).all()
                         continue
                     assert t.first + lane < u.tgtCount
                     k, kT = (int(v) for v in tgt[u.tgtFirst + t.first + lane])
                     assert u.edgeFirst <= k < u.edgeFirst + u.edgeCount and col[k] >= rows_of[k]
+                    assert (t.kind == 3) == (col[k] == rows_of[k])              # diagonals have their own tasks
                     if col[k] == rows_of[k]:
                         assert kT == -1                                          # a diagonal edge
                     else:
