@@ -131,7 +131,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="dc_b200", choices=["dc_b200", "reference"])
     ap.add_argument("--workload", default=os.environ.get("DC_BENCH_WORKLOAD", "target350"))
-    ap.add_argument("--slots", type=int, default=int(os.environ.get("DC_BENCH_SLOTS", "400")))
+    ap.add_argument("--slots", type=int, default=int(os.environ.get("DC_BENCH_SLOTS", "512")))
+    ap.add_argument("--threads", type=int, default=int(os.environ.get("DC_BENCH_THREADS", "256")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -144,7 +145,7 @@ def main():
                           f"{'D&C + colouring VEC_SIZE ' + str(vec) if vec else 'pure D&C'} tree "
                           f"({'METIS node partitions' if builder == 'metis' else 'coordinate-bisection node partitions'}), "
                           "reset + assembly per step",
-              "mode": "deterministic", "unit_slots": args.slots,
+              "mode": "deterministic", "unit_slots": args.slots, "unit_threads": args.threads,
               "l2": "value arrays larger than L2 (no flush needed)" if 6 * n ** 3 * 2.5 * dim * dim * 8 > 2.5e8
                     else "working set fits L2; see roofline note"}
 
@@ -177,6 +178,7 @@ def main():
 
     # one slab (cube) per GPU; rank 0 builds tree / CSR / schedule, the others get them over NCCL
     ctx, info = multigpu.setup_device_slabs(n, rank, world, device, builder=builder, vec=vec, slots=args.slots, dist=dist)
+    ctx.set_option("unit_threads", args.threads)
     E, N, nnz, st = info["E"], info["N"], info["nnz"], info["stats"]
     op, prm = (dc.OP_ELASTICITY, [LAMBDA, MU]) if dim == 3 else (dc.OP_LAPLACIAN, None)
     per = dim * dim

@@ -58,6 +58,7 @@ struct dc_cuda_ctx {
     double *d_values = nullptr;
     int64_t valuesLen = 0;
     int64_t launches = 0;
+    long long *d_phaseClock = nullptr;   /* debug: per-unit phase stamps (dc_cuda_debug_phases) */
 };
 
 extern "C" const char *dc_cuda_last_error(void) { return g_err.c_str(); }
@@ -271,7 +272,7 @@ static int launch_units(dc_cuda_ctx *c, double *d_values, cudaStream_t s)
     kern<<<(unsigned)c->nbUnits, THREADS, (size_t)L.total, s>>>(c->d_units, c->d_tasks, c->d_items, c->d_slotNodes,
                                                                  c->d_halo, c->d_diagRel,
                                                                  reinterpret_cast<const int2 *>(c->d_tgt), c->d_coord,
-                                                                 d_values, L);
+                                                                 d_values, L, c->d_phaseClock);
     return 0;
 }
 
@@ -444,6 +445,23 @@ extern "C" int dc_cuda_unpack_add_edges(double *d_values, const int64_t *d_edge,
     unpack_add_edges<<<grid_for(nbEdges * perEdge, 256), 256, 0, (cudaStream_t)stream>>>(d_values, d_edge, nbEdges,
                                                                                          perEdge, d_buf);
     CK(cudaGetLastError());
+    return 0;
+}
+
+/* debug: enable per-unit phase stamps; the next assembly fills h_out[nbUnits][8] on request */
+extern "C" int dc_cuda_debug_phases(dc_cuda_ctx *c, long long *h_out)
+{
+    if (!c) return fail(-1, "dc_cuda_debug_phases: null context");
+    CK(cudaSetDevice(c->device));
+    if (!c->d_phaseClock) {
+        CK(cudaMalloc((void **)&c->d_phaseClock, sizeof(long long) * 8 * (size_t)(c->nbUnits > 0 ? c->nbUnits : 1)));
+        return 0;
+    }
+    CK(cudaDeviceSynchronize());
+    if (h_out)
+        CK(cudaMemcpy(h_out, c->d_phaseClock, sizeof(long long) * 8 * (size_t)c->nbUnits, cudaMemcpyDeviceToHost));
+    cudaFree(c->d_phaseClock);
+    c->d_phaseClock = nullptr;
     return 0;
 }
 

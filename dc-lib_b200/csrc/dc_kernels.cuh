@@ -120,7 +120,7 @@ struct UnitSmem {
         L.offTgt = L.offTasks + up(maxTasks * 16);
         L.offItems = L.offTgt + up(maxTgt * 8);
         L.offRecs = L.offItems + up(maxItems * 2);
-        L.total = L.offRecs + maxSlots * RS * 8;
+        L.total = L.offRecs + (maxSlots + 1) * RS * 8;      /* + the all-zero record padding items point to */
         return L;
     }
 };
@@ -149,8 +149,13 @@ __global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *_
                                                               const int *__restrict__ diagRel,
                                                               const int2 *__restrict__ tgtPairs,
                                                               const double *__restrict__ coord,
-                                                              double *__restrict__ values, const UnitLayout L)
+                                                              double *__restrict__ values, const UnitLayout L,
+                                                              long long *__restrict__ phaseClock)
 {
+    /* phaseClock (normally null): 8 clock64() stamps per unit, written by thread 0 -- start,
+     * TMA issued, mesh data landed, halo coordinates staged, records built, schedule landed,
+     * first task done by warp 0, unit finished (tools/phase_times.py) */
+#define DC_STAMP(i) do { if (phaseClock && tid == 0) phaseClock[(int64_t)blockIdx.x * 8 + (i)] = clock64(); } while (0)
     constexpr int DD = UnitSmem<Op>::DD;
     constexpr int RS = UnitSmem<Op>::RS;
     constexpr int NW = THREADS / 32;
@@ -174,9 +179,12 @@ __global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *_
 
     /* P0: everything the unit reads that is contiguous in HBM comes in as TMA bulk copies:
      * slot -> node-table indices, halo node ids, own coordinates; tasks, items, targets */
+    int *nextTask = reinterpret_cast<int *>(smem_raw + 16);             /* dynamic task counter */
+    DC_STAMP(0);
     if (tid == 0) {
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
+        *nextTask = NW;
     }
     __syncthreads();
     if (tid == 0) {
@@ -194,7 +202,9 @@ __global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *_
         if (itemBytes) tma_bulk_g2s(itemS, items + u.itemFirst, itemBytes, &bar[1]);
         if (tgtBytes) tma_bulk_g2s(tgtS, tgtPairs + u.tgtFirst, tgtBytes, &bar[1]);
     }
+    DC_STAMP(1);
     mbar_wait(&bar[0], 0);
+    DC_STAMP(2);
 
     /* P1a: coordinates of the halo nodes (one gather per node, not per element) */
     for (int i = tid; i < u.hnodeCount; i += THREADS) {
@@ -205,39 +215,75 @@ __global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *_
         dst[2] = __ldg(src + 2);
     }
     __syncthreads();
+    DC_STAMP(3);
 
-    /* P1b: one record per touched element, everything from shared memory */
-    for (int s = tid; s < nSlots; s += THREADS) {
-        const uint2 ln = slotN[s];
-        const uint32_t n[4] = {ln.x & 0xFFFFu, ln.x >> 16, ln.y & 0xFFFFu, ln.y >> 16};
-        double x[4][3];
+    /* P1b: one record per touched element, everything from shared memory; slot nSlots is an
+     * all-zero record: padding items point at it and add exact zeros, so the accumulation
+     * loops need no test and can be software-pipelined */
+    if (tid < RS) recs[nSlots * RS + tid] = 0.0;
+    for (int s0 = tid; s0 < nSlots; s0 += 2 * THREADS) {
+        /* two elements per thread in flight: the dependent chain of one setup (cross products,
+         * reciprocal, square root) overlaps the other's */
+        const int s1 = s0 + THREADS;
+        const bool two = s1 < nSlots;
+        const uint2 la = slotN[s0], lb = slotN[two ? s1 : s0];
+        const uint32_t na[4] = {la.x & 0xFFFFu, la.x >> 16, la.y & 0xFFFFu, la.y >> 16};
+        const uint32_t nb[4] = {lb.x & 0xFFFFu, lb.x >> 16, lb.y & 0xFFFFu, lb.y >> 16};
+        double xa[4][3], xb[4][3];
 #pragma unroll
         for (int a = 0; a < 4; a++)
 #pragma unroll
-            for (int k = 0; k < 3; k++) x[a][k] = coordS[n[a] * 3 + k];
-        double rec[Op::NS];
-        Op::setup(x, c_params, rec);
+            for (int k = 0; k < 3; k++) {
+                xa[a][k] = coordS[na[a] * 3 + k];
+                xb[a][k] = coordS[nb[a] * 3 + k];
+            }
+        double ra[Op::NS], rb[Op::NS];
+        Op::setup(xa, c_params, ra);
+        Op::setup(xb, c_params, rb);
 #pragma unroll
-        for (int i = 0; i < Op::NS; i++) recs[s * RS + i] = rec[i];
+        for (int i = 0; i < Op::NS; i++) recs[s0 * RS + i] = ra[i];
+        if (two) {
+#pragma unroll
+            for (int i = 0; i < Op::NS; i++) recs[s1 * RS + i] = rb[i];
+        }
     }
+    DC_STAMP(4);
     mbar_wait(&bar[1], 0);
     __syncthreads();   /* records complete */
+    DC_STAMP(5);
 
     /* P2: tasks round-robin over warps; a lane owns one CSR edge and adds its contributions
      * in ascending element order (the order of the item rows) */
     double *myStage = reinterpret_cast<double *>(smem_raw + L.offStage + warp * UnitSmem<Op>::STAGE);
     int *myTgt = reinterpret_cast<int *>(myStage + 32 * DD);
-    for (int t = warp; t < u.taskCount; t += NW) {
+    /* tasks are listed longest first (diagonal tasks, then upper edges by contribution count);
+     * a warp takes the next one as soon as it is free, so the makespan stays near the mean */
+    for (int t = warp; t < u.taskCount;) {
         const dc_task_t task = taskS[t];
+        {
+            int nxt = 0;
+            if (lane == 0) nxt = atomicAdd(nextTask, 1);
+            t = __shfl_sync(0xffffffffu, nxt, 0);
+        }
         const uint16_t *it = itemS + task.itemRel + lane;
         double acc[DD];
 #pragma unroll
         for (int c = 0; c < DD; c++) acc[c] = 0.0;
         if (SYM && task.kind == DC_TASK_OWNDIAG) {
             /* diagonal edges only: one gradient per contribution, symmetric block */
-            for (int i = 0; i < task.iters; i++) {
-                const uint32_t cur = it[i * 32];
-                if (cur != DC_ITEM_NULL) Op::accumulate_diag(recs + (cur >> 4) * RS, c_params, cur & 3u, acc);
+            const int iters = task.iters;
+            if (iters > 0) {
+                double nxt[Op::NOPS_DIAG], cur[Op::NOPS_DIAG];
+                uint32_t item = it[0];
+                Op::fetch_diag(recs + (item >> 4) * RS, item & 3u, nxt);
+                item = it[(iters > 1 ? 1 : 0) * 32];
+                for (int i = 0; i < iters; i++) {
+#pragma unroll
+                    for (int q = 0; q < Op::NOPS_DIAG; q++) cur[q] = nxt[q];
+                    Op::fetch_diag(recs + (item >> 4) * RS, item & 3u, nxt);      /* iteration i+1 (clamped) */
+                    item = it[(i + 2 < iters ? i + 2 : iters - 1) * 32];
+                    Op::apply_diag(cur, c_params, acc);
+                }
             }
             Op::mirror(acc);
             const bool valid = (task.mask >> lane) & 1u;
@@ -255,9 +301,21 @@ __global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *_
             }
             continue;
         }
-        for (int i = 0; i < task.iters; i++) {
-            const uint32_t cur = it[i * 32];
-            if (cur != DC_ITEM_NULL) Op::accumulate(recs + (cur >> 4) * RS, c_params, cur & 15u, acc);
+        {
+            const int iters = task.iters;
+            if (iters > 0) {
+                double nxt[Op::NOPS], cur[Op::NOPS];
+                uint32_t item = it[0];
+                Op::fetch(recs + (item >> 4) * RS, item & 15u, nxt);
+                item = it[(iters > 1 ? 1 : 0) * 32];
+                for (int i = 0; i < iters; i++) {
+#pragma unroll
+                    for (int q = 0; q < Op::NOPS; q++) cur[q] = nxt[q];
+                    Op::fetch(recs + (item >> 4) * RS, item & 15u, nxt);            /* iteration i+1 (clamped) */
+                    item = it[(i + 2 < iters ? i + 2 : iters - 1) * 32];
+                    Op::apply(cur, c_params, acc);
+                }
+            }
         }
         if (task.kind == DC_TASK_DIAG) {
             if ((task.mask >> lane) & 1u) {
@@ -305,6 +363,10 @@ __global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *_
             }
         }
     }
+    DC_STAMP(6);
+    __syncthreads();
+    DC_STAMP(7);
+#undef DC_STAMP
 }
 
 /* ---- fallback: explicit per-edge lists, everything from global memory ----- */

@@ -96,6 +96,24 @@ struct OpLaplacian {
         accumulate(rec, params, 5u * a, acc);
     }
     __device__ __forceinline__ static void mirror(double (&)[1]) {}
+    /* the same updates split in two for software pipelining: fetch = the shared-memory reads,
+     * apply = the arithmetic */
+    static constexpr int NOPS = 1, NOPS_DIAG = 1;
+    template <typename R>
+    __device__ __forceinline__ static void fetch(R rec, uint32_t ab, double (&ops)[1])
+    {
+        ops[0] = rec[(uint32_t)(0x9863875265413210ULL >> (4 * ab)) & 15u];
+    }
+    template <typename R>
+    __device__ __forceinline__ static void fetch_diag(R rec, uint32_t a, double (&ops)[1]) { fetch(rec, 5u * a, ops); }
+    __device__ __forceinline__ static void apply(const double (&ops)[1], const double *, double (&acc)[1])
+    {
+        acc[0] = __dadd_rn(acc[0], ops[0]);
+    }
+    __device__ __forceinline__ static void apply_diag(const double (&ops)[1], const double *p, double (&acc)[1])
+    {
+        apply(ops, p, acc);
+    }
 };
 
 /* Isotropic linear elasticity, 3x3 blocks, volume folded symmetrically into the gradients:
@@ -172,6 +190,59 @@ struct OpElasticity {
         acc[3] = acc[1];
         acc[6] = acc[2];
         acc[7] = acc[5];
+    }
+    /* the same updates split in two for software pipelining: fetch = the shared-memory reads,
+     * apply = the arithmetic */
+    static constexpr int NOPS = 6, NOPS_DIAG = 3;
+    template <typename R>
+    __device__ __forceinline__ static void fetch(R rec, uint32_t ab, double (&ops)[6])
+    {
+        const uint32_t a = ab >> 2, b = ab & 3u;
+        ops[0] = rec[3 * a]; ops[1] = rec[3 * a + 1]; ops[2] = rec[3 * a + 2];
+        ops[3] = rec[3 * b]; ops[4] = rec[3 * b + 1]; ops[5] = rec[3 * b + 2];
+    }
+    template <typename R>
+    __device__ __forceinline__ static void fetch_diag(R rec, uint32_t a, double (&ops)[3])
+    {
+        ops[0] = rec[3 * a]; ops[1] = rec[3 * a + 1]; ops[2] = rec[3 * a + 2];
+    }
+    __device__ __forceinline__ static void apply(const double (&ops)[6], const double *params, double (&acc)[9])
+    {
+        const double lam = params[0], mu = params[1];
+        double p[3][3];
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) p[i][j] = __dmul_rn(ops[i], ops[3 + j]);
+        const double dot = __dadd_rn(__dadd_rn(p[0][0], p[1][1]), p[2][2]);
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                double v = __fma_rn(lam, p[i][j], acc[i * 3 + j]);
+                v = __fma_rn(mu, p[j][i], v);
+                if (i == j) v = __fma_rn(mu, dot, v);
+                acc[i * 3 + j] = v;
+            }
+    }
+    __device__ __forceinline__ static void apply_diag(const double (&h)[3], const double *params, double (&acc)[9])
+    {
+        const double lam = params[0], mu = params[1];
+        double p[3][3];
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = i; j < 3; j++) p[i][j] = __dmul_rn(h[i], h[j]);
+        const double dot = __dadd_rn(__dadd_rn(p[0][0], p[1][1]), p[2][2]);
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = i; j < 3; j++) {
+                double v = __fma_rn(lam, p[i][j], acc[i * 3 + j]);
+                v = __fma_rn(mu, p[i][j], v);
+                if (i == j) v = __fma_rn(mu, dot, v);
+                acc[i * 3 + j] = v;
+            }
     }
 };
 

@@ -24,8 +24,9 @@
 #define DC_PLAN_H
 #include <stdint.h>
 
-#define DC_ITEM_NULL   0xFFFFu      /* padding entry of an item row              */
-#define DC_SLOT_LIMIT  4095         /* slots are 12-bit: item = slot<<4 | a<<2 | b */
+#define DC_SLOT_LIMIT  4094         /* slots are 12-bit: item = slot<<4 | a<<2 | b; item rows are  */
+                                    /* padded with (nSlots << 4): the kernel keeps an all-zero     */
+                                    /* record in slot nSlots, so padding adds exact zeros          */
 #define DC_TASK_EDGES  0            /* 32 consecutive edges of the unit (general schedule)   */
 #define DC_TASK_DIAG   1            /* the diagonal edges of 32 consecutive nodes            */
 #define DC_TASK_UPPER  2            /* symmetric schedule: 32 owned edges (diagonal or col > row) */

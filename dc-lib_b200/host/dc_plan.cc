@@ -191,6 +191,8 @@ void build_unit(const Mesh &m, const UnitSeed &s, int32_t *diagRel, UnitOut &out
     if ((int)perEdge.size() < edgeCount) perEdge.resize((size_t)edgeCount);
     for (int k = 0; k < edgeCount; k++) perEdge[k].clear();
     std::vector<char> isDiag((size_t)edgeCount, 0);
+    /* padding of the item rows: slot nSlots is the kernel's all-zero record */
+    const uint16_t padItem = (uint16_t)((s.ownCount + (int)s.halo.size()) << 4);
 
     /* node table: own interval (from the even node at or below nodeFirst, padded to an even
      * count so that the block of coordinates is a 16-byte granule copy), then halo nodes */
@@ -299,7 +301,7 @@ void build_unit(const Mesh &m, const UnitSeed &s, int32_t *diagRel, UnitOut &out
                 iters = std::max(iters, (size_t)owned[base + l].count);
             }
             t.iters = (uint16_t)iters;
-            out.items.resize(out.items.size() + iters * 32, (uint16_t)DC_ITEM_NULL);
+            out.items.resize(out.items.size() + iters * 32, padItem);
             uint16_t *dst = out.items.data() + t.itemRel;
             for (size_t l = 0; l < 32 && base + l < classEnd; l++) {
                 const std::vector<uint16_t> &v = perEdge[(size_t)owned[base + l].rel];
@@ -327,7 +329,7 @@ void build_unit(const Mesh &m, const UnitSeed &s, int32_t *diagRel, UnitOut &out
         for (int l = 0; l < 32 && base + l < edgeCount; l++)
             if (!((t.mask >> l) & 1u)) iters = std::max(iters, perEdge[(size_t)(base + l)].size());
         t.iters = (uint16_t)iters;
-        out.items.resize(out.items.size() + iters * 32, (uint16_t)DC_ITEM_NULL);
+        out.items.resize(out.items.size() + iters * 32, padItem);
         uint16_t *dst = out.items.data() + t.itemRel;
         for (int l = 0; l < 32 && base + l < edgeCount; l++) {
             if ((t.mask >> l) & 1u) continue;
@@ -337,6 +339,7 @@ void build_unit(const Mesh &m, const UnitSeed &s, int32_t *diagRel, UnitOut &out
         }
         out.tasks.push_back(t);
     }
+    std::vector<dc_task_t> diagTasks;
     /* diagonal tasks: 32 consecutive nodes */
     for (int base = 0; base < s.nodeCount; base += 32) {
         dc_task_t t;
@@ -352,7 +355,7 @@ void build_unit(const Mesh &m, const UnitSeed &s, int32_t *diagRel, UnitOut &out
             iters = std::max(iters, perEdge[(size_t)d].size());
         }
         t.iters = (uint16_t)iters;
-        out.items.resize(out.items.size() + iters * 32, (uint16_t)DC_ITEM_NULL);
+        out.items.resize(out.items.size() + iters * 32, padItem);
         uint16_t *dst = out.items.data() + t.itemRel;
         for (int l = 0; l < 32 && base + l < s.nodeCount; l++) {
             if (!((t.mask >> l) & 1u)) continue;
@@ -360,8 +363,10 @@ void build_unit(const Mesh &m, const UnitSeed &s, int32_t *diagRel, UnitOut &out
             for (size_t i = 0; i < v.size(); i++) dst[i * 32 + l] = v[i];
             out.useful += (int64_t)v.size();
         }
-        if (t.mask) out.tasks.push_back(t); else out.items.resize(t.itemRel);
+        if (t.mask) diagTasks.push_back(t); else out.items.resize(t.itemRel);
     }
+    /* longest tasks first: the kernel hands tasks to warps dynamically */
+    out.tasks.insert(out.tasks.begin(), diagTasks.begin(), diagTasks.end());
 }
 
 template <typename T>
