@@ -260,13 +260,22 @@ def main():
 
     peak, peak_src = measured_peak()
     b_alg = 16 * E + 24 * N + 4 * (N + 1) + 4 * nnz + 8 * per * nnz
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if dim == 3 and os.path.exists(tpath):
+        # DRAM bytes per launch from the committed ncu --set full capture of this kernel (same
+        # operator, schedule and tree builder, smaller cube), scaled by the element count
+        with open(tpath) as f:
+            tj = json.load(f)
+        traffic, traffic_src = tj["dram_bytes_per_element"] * E, tj["source"]
     achieved = b_alg / (kernel_ms * 1e-3) / 1e9
     line = {
         "metric": "assembled elements/s (fp64, CSR scatter-add)", "value": world * E / (ms * 1e-3), "unit": "elements/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "kernel": "gather_units", "kernel_ms": kernel_ms,
+                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                     "kernel": "gather_units", "kernel_ms": kernel_ms,
                      "algorithmic_bytes_per_launch": b_alg, "bytes_per_element": b_alg / E},
         "e2e": {"value": world * E / (e2e_ms * 1e-3), "unit": "elements/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": 24 * N, "d2h_bytes_per_step": 8 * per * nnz, "steps": e2e_steps,
