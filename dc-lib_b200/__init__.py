@@ -92,6 +92,7 @@ def _declare(L):
     L.dc_cuda_download_range.argtypes = [vp, c_int64, c_int64, vp, vp]
     L.dc_cuda_upload_lists.argtypes = [vp, vp, vp, vp, c_int64, c_int64]
     L.dc_cuda_assemble.argtypes = [vp, c_int, vp, c_int, c_int, vp, vp]
+    L.dc_cuda_assemble_with.argtypes = [vp, vp, vp, c_int, c_int, vp, vp]
     L.dc_cuda_values.argtypes = [vp, c_int, POINTER(c_void_p)]
     L.dc_cuda_download_values.argtypes = [vp, c_int, vp, vp]
     L.dc_cuda_permute_double_2d.argtypes = [vp, vp, vp, c_int64, c_int, vp]
@@ -359,6 +360,12 @@ class Context:
         prm = np.ascontiguousarray(params if params is not None else [], dtype=np.float64)
         self._ck(lib().dc_cuda_assemble(self.h, op, _p(prm) if prm.size else None, prm.size, mode, _p(values), stream),
                  "dc_cuda_assemble")
+
+    def assemble_with(self, launcher, params, mode, values, stream=None):
+        """launcher: address of a function defined with DC_DEVICE_OPERATOR in a user .cu file."""
+        prm = np.ascontiguousarray(params if params is not None else [], dtype=np.float64)
+        self._ck(lib().dc_cuda_assemble_with(self.h, launcher, _p(prm) if prm.size else None, prm.size, mode,
+                                             _p(values), stream), "dc_cuda_assemble_with")
 
     def assemble_to_host(self, op, params, mode, out, stream=None):
         """The call a reference user makes: values land in the HOST array `out`."""

@@ -7,7 +7,7 @@
 #include <string.h>
 #include <string>
 #include "dc_cuda.h"
-#include "dc_kernels.cuh"
+#include "dc_device_operator.cuh"
 
 using namespace dcdev;
 
@@ -261,83 +261,61 @@ extern "C" int dc_cuda_upload_lists(dc_cuda_ctx *c, const int64_t *h_edge, const
     return 0;
 }
 
-template <class Op, int THREADS, int MINB, bool SYM>
-static int launch_units(dc_cuda_ctx *c, double *d_values, cudaStream_t s)
+static void fill_args(const dc_cuda_ctx *c, int mode, dc_launch_args *a)
 {
-    const UnitLayout L = UnitSmem<Op>::layout(c->maxSlots, c->maxHalo, c->maxNodes, c->maxTasks, c->maxItems,
-                                              c->maxTgt, THREADS);
-    if (L.total > 227 * 1024) return fail(-11, "dc_cuda_assemble: unit does not fit in shared memory");
-    auto kern = gather_units<Op, THREADS, MINB, SYM>;
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-    kern<<<(unsigned)c->nbUnits, THREADS, (size_t)L.total, s>>>(c->d_units, c->d_tasks, c->d_items, c->d_slotNodes,
-                                                                 c->d_halo, c->d_diagRel,
-                                                                 reinterpret_cast<const int2 *>(c->d_tgt), c->d_coord,
-                                                                 d_values, L, c->d_phaseClock);
-    return 0;
+    memset(a, 0, sizeof *a);
+    a->mode = mode; a->threads = c->threads; a->smCount = c->smCount; a->symmetric = c->symmetric;
+    a->colBase = c->colBase; a->nbElem = c->nbElem; a->nbNodes = c->nbNodes; a->nnz = c->nnz;
+    a->nbUnits = c->nbUnits; a->nbBigEdges = c->nbBigEdges; a->nbListEdges = c->nbListEdges;
+    a->maxSlots = c->maxSlots; a->maxHalo = c->maxHalo; a->maxNodes = c->maxNodes; a->maxTasks = c->maxTasks;
+    a->maxItems = c->maxItems; a->maxTgt = c->maxTgt;
+    a->d_conn = c->d_conn; a->d_row = c->d_row; a->d_col = c->d_col; a->d_coord = c->d_coord;
+    a->d_units = c->d_units; a->d_tasks = c->d_tasks; a->d_items = c->d_items; a->d_slotNodes = c->d_slotNodes;
+    a->d_haloNodes = c->d_halo; a->d_diagRel = c->d_diagRel; a->d_tgt = c->d_tgt;
+    a->d_bigEdge = c->d_bigEdge; a->d_bigPtr = c->d_bigPtr; a->d_bigEdgeT = c->d_bigEdgeT; a->d_bigItem = c->d_bigItem;
+    a->d_listEdge = c->d_listEdge; a->d_listPtr = c->d_listPtr; a->d_listItem = c->d_listItem;
+    a->d_phaseClock = c->d_phaseClock;
 }
 
-template <class Op>
-static int assemble_t(dc_cuda_ctx *c, int mode, double *d_values, cudaStream_t s)
+static int explain(int rc)
 {
-    constexpr int DD = Op::D * Op::D;
-    if (mode == DC_MODE_DETERMINISTIC) {
-        if (!c->d_units && c->nbBigEdges == 0) return fail(-6, "dc_cuda_assemble: no plan uploaded");
-        if (c->nbUnits > 0) {
-            if (c->symmetric && !Op::SYMMETRIC)
-                return fail(-13, "dc_cuda_assemble: symmetric schedule with a non-symmetric operator");
-            int rc;
-            if (c->symmetric)
-                rc = (c->threads == 128)   ? launch_units<Op, 128, 4, true>(c, d_values, s)
-                     : (c->threads == 192) ? launch_units<Op, 192, 3, true>(c, d_values, s)
-                     : (c->threads == 257) ? launch_units<Op, 256, 3, true>(c, d_values, s)
-                                           : launch_units<Op, 256, 2, true>(c, d_values, s);
-            else
-                rc = (c->threads == 128) ? launch_units<Op, 128, 4, false>(c, d_values, s)
-                                         : launch_units<Op, 256, 2, false>(c, d_values, s);
-            if (rc) return rc;
-            c->launches++;
-        }
-        if (c->nbBigEdges > 0) {
-            gather_lists<Op><<<(unsigned)((c->nbBigEdges + 127) / 128), 128, 0, s>>>(
-                c->d_bigEdge, c->d_bigPtr, c->d_bigItem, c->d_bigEdgeT, c->nbBigEdges, c->d_conn, c->d_coord, d_values);
-            c->launches++;
-        }
-    } else if (mode == DC_MODE_ATOMIC) {
-        const int64_t n = c->nnz * DD;
-        reset_values<<<c->smCount * 8, 256, 0, s>>>(d_values, n);
-        scatter_atomic<Op><<<(unsigned)((c->nbElem + 127) / 128), 128, 0, s>>>(
-            c->d_conn, c->d_coord, c->d_row, c->d_col, c->colBase, c->nbElem, d_values);
-        c->launches += 2;
-    } else if (mode == DC_MODE_LIST) {
-        if (!c->d_listPtr) return fail(-6, "dc_cuda_assemble: no contribution lists uploaded");
-        gather_lists<Op><<<(unsigned)((c->nbListEdges + 127) / 128), 128, 0, s>>>(
-            c->d_listEdge, c->d_listPtr, c->d_listItem, (const int64_t *)nullptr, c->nbListEdges, c->d_conn, c->d_coord,
-            d_values);
-        c->launches++;
-    } else {
-        return fail(-7, "dc_cuda_assemble: unknown mode");
+    switch (rc) {
+        case DC_LAUNCH_OK: return 0;
+        case DC_LAUNCH_NO_PLAN: return fail(rc, "dc_cuda_assemble: no schedule / contribution lists uploaded for this mode");
+        case DC_LAUNCH_BAD_MODE: return fail(rc, "dc_cuda_assemble: unknown mode");
+        case DC_LAUNCH_PARAMS: return fail(rc, "dc_cuda_assemble: wrong number of operator parameters");
+        case DC_LAUNCH_SMEM: return fail(rc, "dc_cuda_assemble: unit does not fit in shared memory (lower unit_slots)");
+        case DC_LAUNCH_NOT_SYMMETRIC:
+            return fail(rc, "dc_cuda_assemble: symmetric schedule with a non-symmetric operator");
+        default: return fail(rc, "dc_cuda_assemble: CUDA launch failed", cudaGetLastError());
     }
-    CK(cudaGetLastError());
-    return 0;
+}
+
+/* the built-in operators are instantiated here exactly the way a user operator is in its own file */
+DC_DEVICE_OPERATOR(dc_builtin_laplacian, dcdev::OpLaplacian)
+DC_DEVICE_OPERATOR(dc_builtin_elasticity, dcdev::OpElasticity)
+
+extern "C" int dc_cuda_assemble_with(dc_cuda_ctx *c, dc_operator_launcher launcher, const double *h_params,
+                                     int nbParams, int mode, double *d_values, void *stream)
+{
+    if (!c || !c->d_coord) return fail(-1, "dc_cuda_assemble: no mesh");
+    if (!d_values || !launcher) return fail(-1, "dc_cuda_assemble: null argument");
+    CK(cudaSetDevice(c->device));
+    dc_launch_args a;
+    fill_args(c, mode, &a);
+    const int rc = launcher(&a, h_params, nbParams, d_values, stream);
+    c->launches += a.launches;
+    return explain(rc);
 }
 
 extern "C" int dc_cuda_assemble(dc_cuda_ctx *c, int op, const double *h_params, int nbParams, int mode,
                                 double *d_values, void *stream)
 {
-    if (!c || !c->d_conn) return fail(-1, "dc_cuda_assemble: no mesh");
-    if (!d_values) return fail(-1, "dc_cuda_assemble: null values");
-    if (nbParams > DC_MAX_PARAMS) return fail(-8, "dc_cuda_assemble: too many operator parameters");
-    CK(cudaSetDevice(c->device));
-    cudaStream_t s = (cudaStream_t)stream;
-    if (nbParams > 0)
-        CK(cudaMemcpyToSymbolAsync(c_params, h_params, sizeof(double) * (size_t)nbParams, 0,
-                                   cudaMemcpyHostToDevice, s));
     switch (op) {
         case DC_OP_P1_TET_LAPLACIAN:
-            return assemble_t<OpLaplacian>(c, mode, d_values, s);
+            return dc_cuda_assemble_with(c, dc_builtin_laplacian, h_params, nbParams, mode, d_values, stream);
         case DC_OP_P1_TET_ELASTICITY:
-            if (nbParams < 2) return fail(-8, "dc_cuda_assemble: elasticity needs {lambda, mu}");
-            return assemble_t<OpElasticity>(c, mode, d_values, s);
+            return dc_cuda_assemble_with(c, dc_builtin_elasticity, h_params, nbParams, mode, d_values, stream);
         default:
             return fail(-9, "dc_cuda_assemble: unknown operator");
     }
@@ -469,7 +447,7 @@ extern "C" int dc_cuda_set_option(dc_cuda_ctx *c, const char *name, int value)
 {
     if (!c || !name) return fail(-1, "dc_cuda_set_option: null argument");
     if (!strcmp(name, "unit_threads")) {
-        if (value != 128 && value != 192 && value != 256 && value != 257)
+        if (value != 128 && value != 192 && value != 256)
             return fail(-12, "dc_cuda_set_option: unit_threads must be 128, 192 or 256");
         c->threads = value;
         return 0;

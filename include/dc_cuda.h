@@ -70,6 +70,14 @@ int  dc_cuda_upload_lists(dc_cuda_ctx *ctx, const int64_t *h_edge, const int64_t
  * coefficients on the host ({} for the Laplacian, {lambda, mu} for elasticity). */
 int  dc_cuda_assemble(dc_cuda_ctx *ctx, int op, const double *h_params, int nbParams, int mode,
                       double *d_values, void *stream);
+/* Same with a user-defined device operator: `launcher` is the function a user's .cu file
+ * defines with DC_DEVICE_OPERATOR(name, Functor) (dc-lib_b200/csrc/dc_device_operator.cuh) --
+ * the device-side replacement of the reference's host function pointers. */
+struct dc_launch_args;
+typedef int (*dc_operator_launcher)(struct dc_launch_args *args, const double *h_params, int nbParams,
+                                    double *d_values, void *stream);
+int  dc_cuda_assemble_with(dc_cuda_ctx *ctx, dc_operator_launcher launcher, const double *h_params,
+                           int nbParams, int mode, double *d_values, void *stream);
 /* Convenience: values owned by the context. */
 int  dc_cuda_values(dc_cuda_ctx *ctx, int dim, double **d_values);
 int  dc_cuda_download_values(dc_cuda_ctx *ctx, int dim, double *h_values, void *stream);

@@ -84,6 +84,30 @@ void dco_laplacian_ke(const double x[4][3], double ke[16])
         }
 }
 
+/* Two more scalar operators, used to test the device-operator hook with user-written
+ * operators (tests/custom_op/custom_ops.cu): a symmetric mass matrix and a non-symmetric
+ * advection matrix.  ke[a*4+b]. */
+void dco_mass_ke(const double x[4][3], double ke[16])
+{
+    double g[4][3], vol;
+    dco_tet_gradients(x, g, &vol);
+    double off = vol * 0.05, diag = vol * 0.1;
+    for (int a = 0; a < 4; a++)
+        for (int b = 0; b < 4; b++) ke[a * 4 + b] = (a == b) ? diag : off;
+}
+
+void dco_advection_ke(const double x[4][3], const double w[3], double ke[16])
+{
+    double g[4][3], vol;
+    dco_tet_gradients(x, g, &vol);
+    double q = vol * 0.25;
+    for (int b = 0; b < 4; b++) {
+        double gw = fma(g[b][2], w[2], fma(g[b][1], w[1], g[b][0] * w[0]));
+        double v = q * gw;
+        for (int a = 0; a < 4; a++) ke[a * 4 + b] = v;
+    }
+}
+
 /* Isotropic elasticity with the volume folded symmetrically into the gradients:
  * h_a = g_a * sqrt(vol);  p[i][j] = ha_i*hb_j;  dot = (p00+p11)+p22.  The scatter-add of
  * block (a,b) into its CSR entry v is three fused updates per component,
@@ -149,7 +173,9 @@ void dco_assemble_range(const dco_user_t *u, int firstElem, int lastElem)
         }
         if (u->opDim == 1) {
             double ke[16];
-            dco_laplacian_ke(x, ke);
+            if (u->opKind == 1) dco_mass_ke(x, ke);
+            else if (u->opKind == 2) dco_advection_ke(x, u->w, ke);
+            else dco_laplacian_ke(x, ke);
             for (int a = 0; a < 4; a++)
                 for (int b = 0; b < 4; b++)
                     u->values[find_edge(u, n[a], n[b])] += ke[a * 4 + b];
@@ -177,6 +203,13 @@ void dco_seq_callback(void *user, void *dcargs)
     const dco_args_t *a = (const dco_args_t *)dcargs;
     if (u->resetInSeq) reset_leaf(u, a);
     dco_assemble_range(u, a->firstElem, a->lastElem);
+}
+
+/* README-generation callback shape fn(userArgs, firstElem, lastElem) (README.md:122-124): the
+ * library resets the leaf itself, the callback only assembles the range */
+void dco_range_callback(void *user, int firstElem, int lastElem)
+{
+    dco_assemble_range((const dco_user_t *)user, firstElem, lastElem);
 }
 
 /* In DC_VEC builds the vec callback runs first on a leaf (tree_traversal.cc:47-56),

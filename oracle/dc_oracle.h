@@ -30,6 +30,8 @@ typedef struct {
     int    opDim;               /* 1 = P1 Laplacian, 3 = isotropic elasticity */
     double lambda, mu;          /* Lame coefficients (opDim == 3) */
     int    resetInSeq;          /* 1: seq callback zeroes the leaf's edges (pure D&C) */
+    int    opKind;              /* opDim == 1 only: 0 Laplacian, 1 mass, 2 advection  */
+    double w[3];                /* advection velocity                                 */
 } dco_user_t;
 
 /* flat copy of one tree record (IO.cc:102-117), children as indices (-1 = none) */
@@ -41,6 +43,8 @@ typedef struct {
 /* element kernels (the numeric contract shared with the device operators) */
 void dco_tet_gradients(const double x[4][3], double g[4][3], double *vol);
 void dco_laplacian_ke(const double x[4][3], double ke[16]);
+void dco_mass_ke(const double x[4][3], double ke[16]);
+void dco_advection_ke(const double x[4][3], const double w[3], double ke[16]);
 void dco_elasticity_h(const double x[4][3], double h[4][3]);
 void dco_elasticity_add(const double ha[3], const double hb[3], double lambda, double mu, double v[9]);
 void dco_elasticity_ke(const double x[4][3], double lambda, double mu, double ke[16][9]);
@@ -48,6 +52,7 @@ void dco_elasticity_ke(const double x[4][3], double lambda, double mu, double ke
 /* leaf callbacks with the reference's signature void(*)(void*, DCargs_t*) */
 void dco_seq_callback(void *user, void *dcargs);
 void dco_vec_callback(void *user, void *dcargs);
+void dco_range_callback(void *user, int firstElem, int lastElem);
 void dco_assemble_range(const dco_user_t *u, int firstElem, int lastElem);
 
 /* tree_traversal.cc:27-103 restated over a flat tree; split = DC_VEC call shape */

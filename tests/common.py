@@ -25,7 +25,7 @@ def _ip(v):
 class DcoUser(ctypes.Structure):
     _fields_ = [("elemToNode", c_void_p), ("coord", c_void_p), ("row", c_void_p), ("col", c_void_p),
                 ("values", c_void_p), ("colBase", c_int), ("opDim", c_int), ("lam", c_double),
-                ("mu", c_double), ("resetInSeq", c_int)]
+                ("mu", c_double), ("resetInSeq", c_int), ("opKind", c_int), ("w", c_double * 3)]
 
 
 class DcoNode(ctypes.Structure):
@@ -57,8 +57,10 @@ def oracle():
 LAMBDA, MU = 0.5769230769230769, 0.3846153846153846     # E = 1, nu = 0.3
 
 
-def make_user(mesh, dim, values, reset_in_seq=1):
+def make_user(mesh, dim, values, reset_in_seq=1, op_kind=0, w=(0.0, 0.0, 0.0)):
     u = DcoUser()
+    u.opKind = op_kind
+    u.w[0], u.w[1], u.w[2] = w
     u.elemToNode = mesh["conn"].ctypes.data
     u.coord = mesh["coord"].ctypes.data
     u.row = mesh["row"].ctypes.data
@@ -71,10 +73,10 @@ def make_user(mesh, dim, values, reset_in_seq=1):
     return u
 
 
-def oracle_serial(mesh, dim):
+def oracle_serial(mesh, dim, op_kind=0, w=(0.0, 0.0, 0.0)):
     """Secondary oracle: zero everything, then elements in ascending (tree) order."""
     values = np.full(mesh["nnz"] * dim * dim, np.nan)
-    u = make_user(mesh, dim, values)
+    u = make_user(mesh, dim, values, op_kind=op_kind, w=w)
     oracle().dco_assemble_serial(byref(u), mesh["E"], mesh["nnz"])
     return values
 

@@ -206,3 +206,53 @@ def test_device_resident_setup_path(tmp_path):
     torch.cuda.synchronize()
     s = multigpu.build_slab(8, 0, 1, builder="geometric")
     assert v.cpu().numpy().tobytes() == oracle_serial(s, 3).tobytes()
+
+
+def _custom_ops():
+    import ctypes
+    path = os.path.join(os.path.dirname(__file__), "custom_op", "libcustom_ops.so")
+    if not os.path.exists(path):
+        pytest.fail("tests/custom_op/libcustom_ops.so missing: run __graft_entry__.build()")
+    return ctypes.CDLL(path)
+
+
+@pytest.mark.parametrize("sym", [True, False])
+def test_user_defined_symmetric_operator(tmp_path, sym):
+    """Device-operator hook: a mass matrix written in a user .cu file (KeOperator convenience
+    form), run through both schedules and all three modes."""
+    import ctypes
+    import torch
+    ops = _custom_ops()
+    mesh = prepare_mesh(MineLib(0), 10, tmp_path)
+    want = oracle_serial(mesh, 1, op_kind=1)
+    ctx, _ = _ctx(mesh, slots=300, lists=True, sym=sym)
+    launcher = ctypes.cast(ops.user_mass_op, ctypes.c_void_p)
+    for mode in (dc.MODE_DETERMINISTIC, dc.MODE_LIST, dc.MODE_ATOMIC):
+        v = torch.full((mesh["nnz"],), float("nan"), dtype=torch.float64, device="cuda:0")
+        ctx.assemble_with(launcher, None, mode, v)
+        torch.cuda.synchronize()
+        got = v.cpu().numpy()
+        if mode == dc.MODE_ATOMIC:
+            assert _rel_err(got, want) <= REL_TOL
+        else:
+            assert got.tobytes() == want.tobytes()
+
+
+def test_user_defined_non_symmetric_operator(tmp_path):
+    """A non-symmetric operator (advection) must use the general schedule; the symmetric one
+    refuses it loudly."""
+    import ctypes
+    import torch
+    ops = _custom_ops()
+    w = (0.3, -1.1, 0.7)
+    mesh = prepare_mesh(MineLib(4), 10, tmp_path)
+    want = oracle_serial(mesh, 1, op_kind=2, w=w)
+    launcher = ctypes.cast(ops.user_advection_op, ctypes.c_void_p)
+    ctx, _ = _ctx(mesh, slots=300, sym=False)
+    v = torch.full((mesh["nnz"],), float("nan"), dtype=torch.float64, device="cuda:0")
+    ctx.assemble_with(launcher, list(w), dc.MODE_DETERMINISTIC, v)
+    torch.cuda.synchronize()
+    assert v.cpu().numpy().tobytes() == want.tobytes()
+    ctx2, _ = _ctx(mesh, slots=300, sym=True)
+    with pytest.raises(RuntimeError, match="non-symmetric"):
+        ctx2.assemble_with(launcher, list(w), dc.MODE_DETERMINISTIC, v)
