@@ -134,6 +134,9 @@ def main():
     ap.add_argument("--slots", type=int, default=int(os.environ.get("DC_BENCH_SLOTS", "512")))
     ap.add_argument("--threads", type=int, default=int(os.environ.get("DC_BENCH_THREADS", "256")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--verify", action="store_true",
+                    help="full-size property checks on the device (repeatability, atomic mode within 1e-12, "
+                         "rigid translations in the kernel of the operator); printed as a second JSON line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     n, dim, vec, builder = WORKLOADS[args.workload]
@@ -294,6 +297,40 @@ def main():
         base.pop("ms_per_step")
         line["cpu_baseline"] = base
     print(json.dumps(line), flush=True)
+    if args.verify and world == 1:
+        # size-independent properties at the full workload size (the oracle cannot run here)
+        ctx.assemble(op, prm, dc.MODE_DETERMINISTIC, vals, stream)
+        torch.cuda.synchronize()
+        again = torch.empty_like(vals)
+        ctx.assemble(op, prm, dc.MODE_DETERMINISTIC, again, stream)
+        torch.cuda.synchronize()
+        chunk = 1 << 26
+
+        def chunks(total_len):
+            for first in range(0, total_len, chunk):
+                yield first, min(total_len, first + chunk)
+
+        repeatable = all(bool(torch.equal(vals[a:b], again[a:b])) for a, b in chunks(vals.numel()))
+        ctx.assemble(op, prm, dc.MODE_ATOMIC, again, stream)           # red.global.add.f64 path, free order
+        torch.cuda.synchronize()
+        scale = max(float(vals[a:b].abs().max()) for a, b in chunks(vals.numel()))
+        atomic_rel = max(float((again[a:b] - vals[a:b]).abs().max()) for a, b in chunks(vals.numel())) / scale
+        del again
+        torch.cuda.empty_cache()
+        row_t = ctx._keep[2]
+        acc = torch.zeros((N, per), dtype=torch.float64, device=device)
+        echunk = chunk // 16
+        edge_row = torch.searchsorted(row_t[1:].contiguous(), torch.arange(0, nnz, echunk, device=device, dtype=row_t.dtype),
+                                      right=True)                      # row of the first edge of every chunk
+        for ci, (a, b) in enumerate((f, min(nnz, f + echunk)) for f in range(0, nnz, echunk)):
+            ids = torch.searchsorted(row_t[1:].contiguous(), torch.arange(a, b, device=device, dtype=row_t.dtype), right=True)
+            acc.index_add_(0, ids, vals.view(nnz, per)[a:b])
+        rowsum_rel = float(acc.abs().max()) / scale               # constants / translations: K * 1 = 0
+        del edge_row
+        print(json.dumps({"verify": {"elements": E, "deterministic_repeat_bitwise": repeatable,
+                                     "atomic_vs_deterministic_max_rel": atomic_rel,
+                                     "row_block_sums_max_rel": rowsum_rel, "tolerance": 1e-12,
+                                     "ok": repeatable and atomic_rel <= 1e-12 and rowsum_rel <= 1e-9}}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -129,6 +129,53 @@ struct Selector {
         }
     }
 
+    /* Pack consecutive non-separator leaves (their node intervals are adjacent, in ascending
+     * node order) into units until the slot budget is full.  Unlike whole subtrees, whose sizes
+     * jump by factors of two, this fills the budget, which lowers the halo ratio. */
+    void pack_leaves(const std::vector<std::pair<int, int>> &leaves, size_t first, size_t last)
+    {
+        const int tid = omp_get_thread_num();
+        std::vector<int> cur, leafSet, merged;
+        int curFirst = -1, curCount = 0;
+        auto flush = [&]() {
+            if (curCount > 0) {
+                UnitSeed s{curFirst, curCount, 0, 0, {}};
+                s.halo.swap(cur);
+                seedsT[tid].push_back(std::move(s));
+            }
+            cur.clear();
+            curFirst = -1;
+            curCount = 0;
+        };
+        for (size_t l = first; l < last; l++) {
+            const int nf = leaves[l].first, nc = leaves[l].second;
+            if (nc <= 0) continue;
+            leafSet.assign(m.n2eVal.begin() + m.n2ePtr[nf], m.n2eVal.begin() + m.n2ePtr[(size_t)nf + nc]);
+            std::sort(leafSet.begin(), leafSet.end());
+            leafSet.erase(std::unique(leafSet.begin(), leafSet.end()), leafSet.end());
+            if ((int)leafSet.size() > maxSlots) {          /* a leaf too big on its own: cut by rows */
+                flush();
+                split_rows(nf, nc);
+                continue;
+            }
+            if (curCount > 0 && curFirst + curCount == nf) {
+                merged.resize(cur.size() + leafSet.size());
+                merged.resize((size_t)(std::set_union(cur.begin(), cur.end(), leafSet.begin(), leafSet.end(), merged.begin()) -
+                                       merged.begin()));
+                if ((int)merged.size() <= maxSlots) {
+                    cur.swap(merged);
+                    curCount += nc;
+                    continue;
+                }
+            }
+            flush();
+            cur.swap(leafSet);
+            curFirst = nf;
+            curCount = nc;
+        }
+        flush();
+    }
+
     /* take the subtree as one unit if it fits the slot budget, else descend */
     void select(int64_t idx)
     {
@@ -455,9 +502,20 @@ extern "C" int dc_plan_build(dc_plan_t *plan, const int *conn, int nbElem, int n
     if (treeRec && nbTreeRec > 0) {
         int64_t cursor = 0;
         index_tree(treeRec, nbTreeRec, cursor, sel.tree, true);
-        #pragma omp parallel num_threads(nt)
-        #pragma omp single
-        sel.select(0);
+        if (getenv("DC_PLAN_SUBTREE_UNITS")) {
+            #pragma omp parallel num_threads(nt)
+            #pragma omp single
+            sel.select(0);
+        } else {
+            std::vector<std::pair<int, int>> leaves;           /* (firstNode, nodeCount) in ascending node order */
+            for (const TreeIdx &t : sel.tree)
+                if (!t.isSep && t.isLeaf) leaves.emplace_back(t.firstNode, t.lastNode - t.firstNode + 1);
+            std::sort(leaves.begin(), leaves.end());
+            const size_t nbChunks = std::min<size_t>(leaves.size(), (size_t)nt * 16);
+            #pragma omp parallel for schedule(dynamic, 1) num_threads(nt)
+            for (size_t c = 0; c < nbChunks; c++)
+                sel.pack_leaves(leaves, leaves.size() * c / nbChunks, leaves.size() * (c + 1) / nbChunks);
+        }
     } else {
         sel.split_rows(0, nbNodes);          /* no tree: plain row blocks */
     }
