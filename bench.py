@@ -133,6 +133,7 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("DC_BENCH_WORKLOAD", "target350"))
     ap.add_argument("--slots", type=int, default=int(os.environ.get("DC_BENCH_SLOTS", "512")))
     ap.add_argument("--threads", type=int, default=int(os.environ.get("DC_BENCH_THREADS", "256")))
+    ap.add_argument("--persistent", type=int, default=int(os.environ.get("DC_BENCH_PERSISTENT", "1")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verify", action="store_true",
                     help="full-size property checks on the device (repeatability, atomic mode within 1e-12, "
@@ -182,6 +183,7 @@ def main():
     # one slab (cube) per GPU; rank 0 builds tree / CSR / schedule, the others get them over NCCL
     ctx, info = multigpu.setup_device_slabs(n, rank, world, device, builder=builder, vec=vec, slots=args.slots, dist=dist)
     ctx.set_option("unit_threads", args.threads)
+    ctx.set_option("persistent", args.persistent)
     E, N, nnz, st = info["E"], info["N"], info["nnz"], info["stats"]
     op, prm = (dc.OP_ELASTICITY, [LAMBDA, MU]) if dim == 3 else (dc.OP_LAPLACIAN, None)
     per = dim * dim

@@ -41,7 +41,8 @@ struct dc_cuda_ctx {
     uint16_t *d_slotNodes = nullptr;
     int *d_tgt = nullptr;
     int64_t *d_bigEdgeT = nullptr;
-    int threads = 256;       /* CTA size of the unit kernel (128 or 256) */
+    int threads = 256;       /* CTA size of the unit kernel (128, 192 or 256) */
+    int persistent = 1;      /* persistent grid with next-unit prefetch (0: one CTA per unit) */
     int64_t nbUnits = 0, nbBigEdges = 0;
     bool ownsPlan = true;
     dc_unit_t *d_units = nullptr;
@@ -265,6 +266,7 @@ static void fill_args(const dc_cuda_ctx *c, int mode, dc_launch_args *a)
 {
     memset(a, 0, sizeof *a);
     a->mode = mode; a->threads = c->threads; a->smCount = c->smCount; a->symmetric = c->symmetric;
+    a->persistent = c->persistent;
     a->colBase = c->colBase; a->nbElem = c->nbElem; a->nbNodes = c->nbNodes; a->nnz = c->nnz;
     a->nbUnits = c->nbUnits; a->nbBigEdges = c->nbBigEdges; a->nbListEdges = c->nbListEdges;
     a->maxSlots = c->maxSlots; a->maxHalo = c->maxHalo; a->maxNodes = c->maxNodes; a->maxTasks = c->maxTasks;
@@ -450,6 +452,10 @@ extern "C" int dc_cuda_set_option(dc_cuda_ctx *c, const char *name, int value)
         if (value != 128 && value != 192 && value != 256)
             return fail(-12, "dc_cuda_set_option: unit_threads must be 128, 192 or 256");
         c->threads = value;
+        return 0;
+    }
+    if (!strcmp(name, "persistent")) {
+        c->persistent = value ? 1 : 0;
         return 0;
     }
     return fail(-12, "dc_cuda_set_option: unknown option");

@@ -31,7 +31,7 @@
 /* What the library hands to a launcher: its device arrays and the geometry of the schedule.
  * Filled by dc_cuda_assemble / dc_cuda_assemble_with; opaque to operator code. */
 struct dc_launch_args {
-    int mode, threads, smCount, symmetric, colBase;
+    int mode, threads, smCount, symmetric, colBase, persistent;
     int nbElem, nbNodes;
     int64_t nnz, nbUnits, nbBigEdges, nbListEdges;
     int maxSlots, maxHalo, maxNodes, maxTasks, maxItems, maxTgt;
@@ -66,10 +66,20 @@ inline int launch_units(dc_launch_args *a, double *d_values, cudaStream_t s)
     auto kern = gather_units<Op, THREADS, MINB, SYM>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total) != cudaSuccess)
         return DC_LAUNCH_CUDA;
-    kern<<<(unsigned)a->nbUnits, THREADS, (size_t)L.total, s>>>(a->d_units, a->d_tasks, a->d_items, a->d_slotNodes,
-                                                                 a->d_haloNodes, a->d_diagRel,
-                                                                 reinterpret_cast<const int2 *>(a->d_tgt), a->d_coord,
-                                                                 d_values, L, a->d_phaseClock);
+    /* persistent grid: SMs x resident CTAs (the kernel strides over the units), or one CTA per
+     * unit when a->persistent == 0 */
+    int64_t grid = a->nbUnits;
+    if (a->persistent) {
+        int perSm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kern, THREADS, (size_t)L.total) != cudaSuccess || perSm < 1)
+            return DC_LAUNCH_CUDA;
+        const int64_t resident = (int64_t)perSm * a->smCount;
+        if (resident < grid) grid = resident;
+    }
+    kern<<<(unsigned)grid, THREADS, (size_t)L.total, s>>>(a->d_units, (int)a->nbUnits, a->d_tasks, a->d_items,
+                                                           a->d_slotNodes, a->d_haloNodes, a->d_diagRel,
+                                                           reinterpret_cast<const int2 *>(a->d_tgt), a->d_coord,
+                                                           d_values, L, a->d_phaseClock);
     return DC_LAUNCH_OK;
 }
 

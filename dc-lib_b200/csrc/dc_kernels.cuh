@@ -112,7 +112,7 @@ struct UnitSmem {
     {
         auto up = [](int v) { return (v + 15) & ~15; };
         UnitLayout L;
-        L.offStage = 32;
+        L.offStage = 32 + 2 * (int)sizeof(dc_unit_t);      /* barriers, task counter, two unit descriptors */
         L.offSlotN = L.offStage + up((threads / 32) * STAGE);
         L.offHnode = L.offSlotN + up(((maxSlots + 1) & ~1) * 8);
         L.offCoord = L.offHnode + up(maxHalo * 4);
@@ -140,125 +140,21 @@ __device__ __forceinline__ void flush_stage(double *__restrict__ values, const d
     }
 }
 
-template <class Op, int THREADS, int MINB, bool SYM>
-__global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *__restrict__ units,
-                                                              const dc_task_t *__restrict__ tasks,
-                                                              const uint16_t *__restrict__ items,
-                                                              const uint16_t *__restrict__ slotNodes,
-                                                              const int *__restrict__ haloNodes,
-                                                              const int *__restrict__ diagRel,
-                                                              const int2 *__restrict__ tgtPairs,
-                                                              const double *__restrict__ coord,
-                                                              double *__restrict__ values, const UnitLayout L,
-                                                              long long *__restrict__ phaseClock)
+/* The accumulation + output phase of one unit (P2): warps take tasks from a shared counter
+ * (tasks are listed longest first); a lane owns one CSR edge and adds its contributions in
+ * ascending element order (the order of the item rows). */
+template <class Op, int NW, bool SYM, class AfterFirst>
+__device__ __forceinline__ void run_tasks(const dc_unit_t &u, const dc_task_t *taskS, const uint16_t *itemS,
+                                          const int2 *tgtS, const double *recs, int *nextTask, double *myStage,
+                                          int *myTgt, const int *__restrict__ diagRel, double *__restrict__ values,
+                                          int warp, int lane, AfterFirst afterFirst)
 {
-    /* phaseClock (normally null): 8 clock64() stamps per unit, written by thread 0 -- start,
-     * TMA issued, mesh data landed, halo coordinates staged, records built, schedule landed,
-     * first task done by warp 0, unit finished (tools/phase_times.py) */
-#define DC_STAMP(i) do { if (phaseClock && tid == 0) phaseClock[(int64_t)blockIdx.x * 8 + (i)] = clock64(); } while (0)
     constexpr int DD = UnitSmem<Op>::DD;
     constexpr int RS = UnitSmem<Op>::RS;
-    constexpr int NW = THREADS / 32;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);          /* bar[0]: mesh data, bar[1]: schedule */
-    const uint2 *slotN = reinterpret_cast<const uint2 *>(smem_raw + L.offSlotN);
-    int *hnodeS = reinterpret_cast<int *>(smem_raw + L.offHnode);
-    double *coordS = reinterpret_cast<double *>(smem_raw + L.offCoord);
-    dc_task_t *taskS = reinterpret_cast<dc_task_t *>(smem_raw + L.offTasks);
-    int2 *tgtS = reinterpret_cast<int2 *>(smem_raw + L.offTgt);
-    uint16_t *itemS = reinterpret_cast<uint16_t *>(smem_raw + L.offItems);
-    double *recs = reinterpret_cast<double *>(smem_raw + L.offRecs);
-
-    const dc_unit_t u = units[blockIdx.x];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nSlots = u.ownElemCount + u.haloCount;
-    /* the unit's node table starts at the even node at or below nodeFirst and spans an even
-     * number of nodes: 48-byte granules, so the own coordinates are one aligned bulk copy */
-    const int alignedFirst = u.nodeFirst & ~1;
-    const int ownSpan = ((u.nodeFirst + u.nodeCount + 1) & ~1) - alignedFirst;
-
-    /* P0: everything the unit reads that is contiguous in HBM comes in as TMA bulk copies:
-     * slot -> node-table indices, halo node ids, own coordinates; tasks, items, targets */
-    int *nextTask = reinterpret_cast<int *>(smem_raw + 16);             /* dynamic task counter */
-    DC_STAMP(0);
-    if (tid == 0) {
-        mbar_init(&bar[0], 1);
-        mbar_init(&bar[1], 1);
-        *nextTask = NW;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        const uint32_t slotBytes = (uint32_t)((nSlots + 1) & ~1) * 8u;
-        const uint32_t hnodeBytes = (uint32_t)u.hnodeCount * 4u;
-        const uint32_t coordBytes = (uint32_t)ownSpan * 24u;
-        mbar_expect_tx(&bar[0], slotBytes + hnodeBytes + coordBytes);
-        if (slotBytes) tma_bulk_g2s(const_cast<uint2 *>(slotN), slotNodes + u.slotFirst * 4, slotBytes, &bar[0]);
-        if (hnodeBytes) tma_bulk_g2s(hnodeS, haloNodes + u.hnodeFirst, hnodeBytes, &bar[0]);
-        if (coordBytes) tma_bulk_g2s(coordS, coord + (int64_t)alignedFirst * 3, coordBytes, &bar[0]);
-        const uint32_t taskBytes = (uint32_t)u.taskCount * 16u, itemBytes = (uint32_t)u.itemCount * 2u;
-        const uint32_t tgtBytes = SYM ? (uint32_t)((u.tgtCount + 1) & ~1) * 8u : 0u;
-        mbar_expect_tx(&bar[1], taskBytes + itemBytes + tgtBytes);
-        if (taskBytes) tma_bulk_g2s(taskS, tasks + u.taskFirst, taskBytes, &bar[1]);
-        if (itemBytes) tma_bulk_g2s(itemS, items + u.itemFirst, itemBytes, &bar[1]);
-        if (tgtBytes) tma_bulk_g2s(tgtS, tgtPairs + u.tgtFirst, tgtBytes, &bar[1]);
-    }
-    DC_STAMP(1);
-    mbar_wait(&bar[0], 0);
-    DC_STAMP(2);
-
-    /* P1a: coordinates of the halo nodes (one gather per node, not per element) */
-    for (int i = tid; i < u.hnodeCount; i += THREADS) {
-        const double *src = coord + (int64_t)hnodeS[i] * 3;
-        double *dst = coordS + (ownSpan + i) * 3;
-        dst[0] = __ldg(src);
-        dst[1] = __ldg(src + 1);
-        dst[2] = __ldg(src + 2);
-    }
-    __syncthreads();
-    DC_STAMP(3);
-
-    /* P1b: one record per touched element, everything from shared memory; slot nSlots is an
-     * all-zero record: padding items point at it and add exact zeros, so the accumulation
-     * loops need no test and can be software-pipelined */
-    if (tid < RS) recs[nSlots * RS + tid] = 0.0;
-    for (int s0 = tid; s0 < nSlots; s0 += 2 * THREADS) {
-        /* two elements per thread in flight: the dependent chain of one setup (cross products,
-         * reciprocal, square root) overlaps the other's */
-        const int s1 = s0 + THREADS;
-        const bool two = s1 < nSlots;
-        const uint2 la = slotN[s0], lb = slotN[two ? s1 : s0];
-        const uint32_t na[4] = {la.x & 0xFFFFu, la.x >> 16, la.y & 0xFFFFu, la.y >> 16};
-        const uint32_t nb[4] = {lb.x & 0xFFFFu, lb.x >> 16, lb.y & 0xFFFFu, lb.y >> 16};
-        double xa[4][3], xb[4][3];
-#pragma unroll
-        for (int a = 0; a < 4; a++)
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
-                xa[a][k] = coordS[na[a] * 3 + k];
-                xb[a][k] = coordS[nb[a] * 3 + k];
-            }
-        double ra[Op::NS], rb[Op::NS];
-        Op::setup(xa, c_params, ra);
-        Op::setup(xb, c_params, rb);
-#pragma unroll
-        for (int i = 0; i < Op::NS; i++) recs[s0 * RS + i] = ra[i];
-        if (two) {
-#pragma unroll
-            for (int i = 0; i < Op::NS; i++) recs[s1 * RS + i] = rb[i];
-        }
-    }
-    DC_STAMP(4);
-    mbar_wait(&bar[1], 0);
-    __syncthreads();   /* records complete */
-    DC_STAMP(5);
-
-    /* P2: tasks round-robin over warps; a lane owns one CSR edge and adds its contributions
-     * in ascending element order (the order of the item rows) */
-    double *myStage = reinterpret_cast<double *>(smem_raw + L.offStage + warp * UnitSmem<Op>::STAGE);
-    int *myTgt = reinterpret_cast<int *>(myStage + 32 * DD);
-    /* tasks are listed longest first (diagonal tasks, then upper edges by contribution count);
-     * a warp takes the next one as soon as it is free, so the makespan stays near the mean */
+    bool first = true;
     for (int t = warp; t < u.taskCount;) {
+        if (!first) afterFirst();          /* runs once, between the warp's first and second task */
+        first = false;
         const dc_task_t task = taskS[t];
         {
             int nxt = 0;
@@ -270,7 +166,9 @@ __global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *_
 #pragma unroll
         for (int c = 0; c < DD; c++) acc[c] = 0.0;
         if (SYM && task.kind == DC_TASK_OWNDIAG) {
-            /* diagonal edges only: one gradient per contribution, symmetric block */
+            /* diagonal edges only: one gradient per contribution, symmetric block.  The loop is
+             * software-pipelined: item two iterations ahead, operands one ahead (indices are
+             * clamped; padding items point at the all-zero record) */
             const int iters = task.iters;
             if (iters > 0) {
                 double nxt[Op::NOPS_DIAG], cur[Op::NOPS_DIAG];
@@ -280,7 +178,7 @@ __global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *_
                 for (int i = 0; i < iters; i++) {
 #pragma unroll
                     for (int q = 0; q < Op::NOPS_DIAG; q++) cur[q] = nxt[q];
-                    Op::fetch_diag(recs + (item >> 4) * RS, item & 3u, nxt);      /* iteration i+1 (clamped) */
+                    Op::fetch_diag(recs + (item >> 4) * RS, item & 3u, nxt);
                     item = it[(i + 2 < iters ? i + 2 : iters - 1) * 32];
                     Op::apply_diag(cur, c_params, acc);
                 }
@@ -311,7 +209,7 @@ __global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *_
                 for (int i = 0; i < iters; i++) {
 #pragma unroll
                     for (int q = 0; q < Op::NOPS; q++) cur[q] = nxt[q];
-                    Op::fetch(recs + (item >> 4) * RS, item & 15u, nxt);            /* iteration i+1 (clamped) */
+                    Op::fetch(recs + (item >> 4) * RS, item & 15u, nxt);
                     item = it[(i + 2 < iters ? i + 2 : iters - 1) * 32];
                     Op::apply(cur, c_params, acc);
                 }
@@ -363,9 +261,204 @@ __global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *_
             }
         }
     }
-    DC_STAMP(6);
+}
+
+/* One CTA processes units blockIdx.x, blockIdx.x + gridDim.x, ... (a persistent grid of
+ * SMs x resident CTAs, or one CTA per unit when the grid equals the unit count).  The fixed
+ * latencies of a unit -- its descriptor, the bulk copies of its node tables and coordinates,
+ * the gather of its halo coordinates -- are issued while the previous unit accumulates:
+ *
+ *   records(u) | sync A | TMA mesh(u+1) ... accumulate + store(u), then halo gather(u+1) | sync B | TMA sched(u+1)
+ *
+ * The node-table region is dead after the records are built and the schedule region after
+ * the accumulation, so nothing is double-buffered. */
+template <class Op, int THREADS, int MINB, bool SYM>
+__global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *__restrict__ units, int nbUnits,
+                                                              const dc_task_t *__restrict__ tasks,
+                                                              const uint16_t *__restrict__ items,
+                                                              const uint16_t *__restrict__ slotNodes,
+                                                              const int *__restrict__ haloNodes,
+                                                              const int *__restrict__ diagRel,
+                                                              const int2 *__restrict__ tgtPairs,
+                                                              const double *__restrict__ coord,
+                                                              double *__restrict__ values, const UnitLayout L,
+                                                              long long *__restrict__ phaseClock)
+{
+    /* phaseClock (normally null): 8 clock64() stamps per unit, written by thread 0
+     * (tools/phase_times.py) */
+#define DC_STAMP(unit, i) do { if (phaseClock && tid == 0) phaseClock[(int64_t)(unit) * 8 + (i)] = clock64(); } while (0)
+    constexpr int DD = UnitSmem<Op>::DD;
+    constexpr int RS = UnitSmem<Op>::RS;
+    constexpr int NW = THREADS / 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);   /* [0] mesh data, [1] schedule, [2] next descriptor */
+    int *nextTask = reinterpret_cast<int *>(smem_raw + 24);           /* dynamic task counter */
+    dc_unit_t *descS = reinterpret_cast<dc_unit_t *>(smem_raw + 32);  /* descriptors of this and the next unit */
+    uint2 *slotN = reinterpret_cast<uint2 *>(smem_raw + L.offSlotN);
+    int *hnodeS = reinterpret_cast<int *>(smem_raw + L.offHnode);
+    double *coordS = reinterpret_cast<double *>(smem_raw + L.offCoord);
+    dc_task_t *taskS = reinterpret_cast<dc_task_t *>(smem_raw + L.offTasks);
+    int2 *tgtS = reinterpret_cast<int2 *>(smem_raw + L.offTgt);
+    uint16_t *itemS = reinterpret_cast<uint16_t *>(smem_raw + L.offItems);
+    double *recs = reinterpret_cast<double *>(smem_raw + L.offRecs);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double *myStage = reinterpret_cast<double *>(smem_raw + L.offStage + warp * UnitSmem<Op>::STAGE);
+    int *myTgt = reinterpret_cast<int *>(myStage + 32 * DD);
+
+    /* bulk copies of a unit's inputs (thread 0).  The node table starts at the even node at or
+     * below nodeFirst and spans an even number of nodes: 48-byte granules. */
+    auto issue_mesh = [&](const dc_unit_t &d) {
+        const int nSl = d.ownElemCount + d.haloCount;
+        const int alignedFirst = d.nodeFirst & ~1;
+        const int ownSpan = ((d.nodeFirst + d.nodeCount + 1) & ~1) - alignedFirst;
+        const uint32_t slotBytes = (uint32_t)((nSl + 1) & ~1) * 8u, hnodeBytes = (uint32_t)d.hnodeCount * 4u;
+        const uint32_t coordBytes = (uint32_t)ownSpan * 24u;
+        mbar_expect_tx(&bar[0], slotBytes + hnodeBytes + coordBytes);
+        if (slotBytes) tma_bulk_g2s(slotN, slotNodes + d.slotFirst * 4, slotBytes, &bar[0]);
+        if (hnodeBytes) tma_bulk_g2s(hnodeS, haloNodes + d.hnodeFirst, hnodeBytes, &bar[0]);
+        if (coordBytes) tma_bulk_g2s(coordS, coord + (int64_t)alignedFirst * 3, coordBytes, &bar[0]);
+    };
+    auto issue_sched = [&](const dc_unit_t &d) {
+        const uint32_t taskBytes = (uint32_t)d.taskCount * 16u, itemBytes = (uint32_t)d.itemCount * 2u;
+        const uint32_t tgtBytes = SYM ? (uint32_t)((d.tgtCount + 1) & ~1) * 8u : 0u;
+        mbar_expect_tx(&bar[1], taskBytes + itemBytes + tgtBytes);
+        if (taskBytes) tma_bulk_g2s(taskS, tasks + d.taskFirst, taskBytes, &bar[1]);
+        if (itemBytes) tma_bulk_g2s(itemS, items + d.itemFirst, itemBytes, &bar[1]);
+        if (tgtBytes) tma_bulk_g2s(tgtS, tgtPairs + d.tgtFirst, tgtBytes, &bar[1]);
+    };
+    /* coordinates of a unit's halo nodes: one gather per node (not per element) */
+    auto gather_halo = [&](const dc_unit_t &d, int first, int stride) {
+        const int ownSpan = ((d.nodeFirst + d.nodeCount + 1) & ~1) - (d.nodeFirst & ~1);
+        for (int i = first; i < d.hnodeCount; i += stride) {
+            const double *src = coord + (int64_t)hnodeS[i] * 3;
+            double *dst = coordS + (ownSpan + i) * 3;
+            dst[0] = __ldg(src);
+            dst[1] = __ldg(src + 1);
+            dst[2] = __ldg(src + 2);
+        }
+    };
+
+    int unit = blockIdx.x;
+    if (unit >= nbUnits) return;
+    DC_STAMP(unit, 0);
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        mbar_init(&bar[2], 1);
+        *nextTask = NW;
+        descS[0] = units[unit];
+    }
     __syncthreads();
-    DC_STAMP(7);
+    if (tid == 0) {
+        issue_mesh(descS[0]);
+        issue_sched(descS[0]);
+    }
+    mbar_wait(&bar[0], 0);
+    gather_halo(descS[0], tid, THREADS);
+    __syncthreads();
+
+    for (int k = 0;; k++) {
+        const dc_unit_t u = descS[k & 1];
+        const int nSlots = u.ownElemCount + u.haloCount;
+        const int next = unit + (int)gridDim.x;
+        const bool hasNext = next < nbUnits;
+        /* descriptor of the next unit: bulk copy requested now, needed after the records are built */
+        if (tid == 0 && hasNext) {
+            mbar_expect_tx(&bar[2], (uint32_t)sizeof(dc_unit_t));
+            tma_bulk_g2s(&descS[(k + 1) & 1], units + next, (uint32_t)sizeof(dc_unit_t), &bar[2]);
+        }
+        DC_STAMP(unit, 1);
+
+        /* P1b: one record per touched element, everything from shared memory; slot nSlots is an
+         * all-zero record: padding items point at it and add exact zeros, so the accumulation
+         * loops need no test and can be software-pipelined */
+        if (tid < RS) recs[nSlots * RS + tid] = 0.0;
+        for (int s0 = tid; s0 < nSlots; s0 += 2 * THREADS) {
+            /* two elements per thread in flight: the dependent chain of one setup (cross products,
+             * reciprocal, square root) overlaps the other's */
+            const int s1 = s0 + THREADS;
+            const bool two = s1 < nSlots;
+            const uint2 la = slotN[s0], lb = slotN[two ? s1 : s0];
+            const uint32_t na[4] = {la.x & 0xFFFFu, la.x >> 16, la.y & 0xFFFFu, la.y >> 16};
+            const uint32_t nb[4] = {lb.x & 0xFFFFu, lb.x >> 16, lb.y & 0xFFFFu, lb.y >> 16};
+            double xa[4][3], xb[4][3];
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int q = 0; q < 3; q++) {
+                    xa[a][q] = coordS[na[a] * 3 + q];
+                    xb[a][q] = coordS[nb[a] * 3 + q];
+                }
+            double ra[Op::NS], rb[Op::NS];
+            Op::setup(xa, c_params, ra);
+            Op::setup(xb, c_params, rb);
+#pragma unroll
+            for (int i = 0; i < Op::NS; i++) recs[s0 * RS + i] = ra[i];
+            if (two) {
+#pragma unroll
+                for (int i = 0; i < Op::NS; i++) recs[s1 * RS + i] = rb[i];
+            }
+        }
+        __syncthreads();   /* A: records complete; node tables and coordinates are dead */
+        DC_STAMP(unit, 2);
+        if (tid == 0 && hasNext) {
+            mbar_wait(&bar[2], k & 1);
+            issue_mesh(descS[(k + 1) & 1]);            /* lands while this unit accumulates */
+        }
+        mbar_wait(&bar[1], k & 1);
+        DC_STAMP(unit, 3);
+
+        /* halo coordinates of the next unit: every thread loads its nodes into registers between
+         * the warp's first and second task (the bulk copy of the node ids has landed by then) and
+         * stores them after its last task, so the gather latency hides behind the accumulation */
+        constexpr int HN = (THREADS >= 256) ? 1 : 2;   /* halo nodes per thread kept in registers */
+        double hx[HN][3];
+        bool loaded = false;
+        auto load_halo = [&]() {
+            if (!hasNext || loaded) return;
+            loaded = true;
+            mbar_wait(&bar[0], (k + 1) & 1);
+            const int cnt = descS[(k + 1) & 1].hnodeCount;
+#pragma unroll
+            for (int j = 0; j < HN; j++) {
+                const int i = tid + j * THREADS;
+                if (i < cnt) {
+                    const double *src = coord + (int64_t)hnodeS[i] * 3;
+                    hx[j][0] = __ldg(src);
+                    hx[j][1] = __ldg(src + 1);
+                    hx[j][2] = __ldg(src + 2);
+                }
+            }
+        };
+        run_tasks<Op, NW, SYM>(u, taskS, itemS, tgtS, recs, nextTask, myStage, myTgt, diagRel, values, warp, lane,
+                               load_halo);
+        DC_STAMP(unit, 4);
+        if (hasNext) {
+            load_halo();                            /* warps with fewer than two tasks */
+            const dc_unit_t &nx = descS[(k + 1) & 1];
+            const int ownSpan = ((nx.nodeFirst + nx.nodeCount + 1) & ~1) - (nx.nodeFirst & ~1);
+#pragma unroll
+            for (int j = 0; j < HN; j++) {
+                const int i = tid + j * THREADS;
+                if (i < nx.hnodeCount) {
+                    double *dst = coordS + (ownSpan + i) * 3;
+                    dst[0] = hx[j][0];
+                    dst[1] = hx[j][1];
+                    dst[2] = hx[j][2];
+                }
+            }
+            gather_halo(nx, tid + HN * THREADS, THREADS);      /* the rare unit with more halo nodes */
+        }
+        DC_STAMP(unit, 5);
+        __syncthreads();   /* B: accumulation finished everywhere; schedule region is dead */
+        DC_STAMP(unit, 6);
+        if (!hasNext) break;
+        if (tid == 0) {
+            *nextTask = NW;
+            issue_sched(descS[(k + 1) & 1]);
+        }
+        unit = next;
+    }
 #undef DC_STAMP
 }
 

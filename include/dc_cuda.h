@@ -107,7 +107,9 @@ int  dc_cuda_pack_edges(const double *d_values, const int64_t *d_edge, int64_t n
 int  dc_cuda_unpack_add_edges(double *d_values, const int64_t *d_edge, int64_t nbEdges, int perEdge,
                               const double *d_buf, void *stream);
 
-/* Tuning knobs: "unit_threads" = CTA size of the unit kernel (128 or 256, default 256). */
+/* Tuning knobs: "unit_threads" = CTA size of the unit kernel (128, 192 or 256; default 256);
+ * "persistent" = 1 (default): SMs x resident CTAs stride over the units and prefetch the next
+ * unit's inputs, 0: one CTA per unit. */
 int  dc_cuda_set_option(dc_cuda_ctx *ctx, const char *name, int value);
 
 /* Number of kernels this context has launched (for honest launch accounting). */
