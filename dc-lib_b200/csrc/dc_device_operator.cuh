@@ -60,12 +60,23 @@ namespace dcdev {
 template <class Op, int THREADS, int MINB, bool SYM>
 inline int launch_units(dc_launch_args *a, double *d_values, cudaStream_t s)
 {
-    const UnitLayout L = UnitSmem<Op>::layout(a->maxSlots, a->maxHalo, a->maxNodes, a->maxTasks, a->maxItems,
-                                              a->maxTgt, THREADS);
+    UnitLayout L = UnitSmem<Op>::layout(a->maxSlots, a->maxHalo, a->maxNodes, a->maxTasks, a->maxItems, a->maxTgt,
+                                        THREADS);
     if (L.total > 227 * 1024) return DC_LAUNCH_SMEM;
     auto kern = gather_units<Op, THREADS, MINB, SYM>;
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total) != cudaSuccess)
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
         return DC_LAUNCH_CUDA;
+    if (a->persistent) {
+        /* double-buffer the schedule (tasks, targets, items) if that costs no resident CTA */
+        const UnitLayout L2 = UnitSmem<Op>::layout(a->maxSlots, a->maxHalo, a->maxNodes, a->maxTasks, a->maxItems,
+                                                   a->maxTgt, THREADS, true);
+        int one = 0, two = 0;
+        if (L2.total <= 227 * 1024 &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&one, kern, THREADS, (size_t)L.total) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&two, kern, THREADS, (size_t)L2.total) == cudaSuccess &&
+            two == one && two > 0)
+            L = L2;
+    }
     /* persistent grid: SMs x resident CTAs (the kernel strides over the units), or one CTA per
      * unit when a->persistent == 0 */
     int64_t grid = a->nbUnits;

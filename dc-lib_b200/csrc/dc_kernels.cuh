@@ -96,6 +96,7 @@ struct UnitLayout {
     int offTgt;      /* symmetric schedule: (edge, transposed edge) pairs                    */
     int offItems;    /* uint16 items                                                         */
     int offRecs;     /* element records                                                      */
+    int schedStride; /* > 0: tasks/targets/items are double-buffered, second copy this far away */
     int total;
 };
 
@@ -108,7 +109,7 @@ struct UnitSmem {
     /* per-warp staging: 32 blocks + 32 target edges */
     static constexpr int STAGE = 32 * DD * 8 + 32 * 4;
     static UnitLayout layout(int maxSlots, int maxHalo, int maxNodes, int maxTasks, int maxItems, int maxTgt,
-                             int threads)
+                             int threads, bool doubleSched = false)
     {
         auto up = [](int v) { return (v + 15) & ~15; };
         UnitLayout L;
@@ -120,6 +121,11 @@ struct UnitSmem {
         L.offTgt = L.offTasks + up(maxTasks * 16);
         L.offItems = L.offTgt + up(maxTgt * 8);
         L.offRecs = L.offItems + up(maxItems * 2);
+        L.schedStride = 0;
+        if (doubleSched) {
+            L.schedStride = L.offRecs - L.offTasks;
+            L.offRecs += L.schedStride;
+        }
         L.total = L.offRecs + (maxSlots + 1) * RS * 8;      /* + the all-zero record padding items point to */
         return L;
     }
@@ -297,9 +303,6 @@ __global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *_
     uint2 *slotN = reinterpret_cast<uint2 *>(smem_raw + L.offSlotN);
     int *hnodeS = reinterpret_cast<int *>(smem_raw + L.offHnode);
     double *coordS = reinterpret_cast<double *>(smem_raw + L.offCoord);
-    dc_task_t *taskS = reinterpret_cast<dc_task_t *>(smem_raw + L.offTasks);
-    int2 *tgtS = reinterpret_cast<int2 *>(smem_raw + L.offTgt);
-    uint16_t *itemS = reinterpret_cast<uint16_t *>(smem_raw + L.offItems);
     double *recs = reinterpret_cast<double *>(smem_raw + L.offRecs);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double *myStage = reinterpret_cast<double *>(smem_raw + L.offStage + warp * UnitSmem<Op>::STAGE);
@@ -318,13 +321,15 @@ __global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *_
         if (hnodeBytes) tma_bulk_g2s(hnodeS, haloNodes + d.hnodeFirst, hnodeBytes, &bar[0]);
         if (coordBytes) tma_bulk_g2s(coordS, coord + (int64_t)alignedFirst * 3, coordBytes, &bar[0]);
     };
-    auto issue_sched = [&](const dc_unit_t &d) {
+    /* schedule of iteration `iter` (double-buffered when the layout has room for it) */
+    auto issue_sched = [&](const dc_unit_t &d, int iter) {
+        unsigned char *base = smem_raw + (iter & 1) * L.schedStride;
         const uint32_t taskBytes = (uint32_t)d.taskCount * 16u, itemBytes = (uint32_t)d.itemCount * 2u;
         const uint32_t tgtBytes = SYM ? (uint32_t)((d.tgtCount + 1) & ~1) * 8u : 0u;
         mbar_expect_tx(&bar[1], taskBytes + itemBytes + tgtBytes);
-        if (taskBytes) tma_bulk_g2s(taskS, tasks + d.taskFirst, taskBytes, &bar[1]);
-        if (itemBytes) tma_bulk_g2s(itemS, items + d.itemFirst, itemBytes, &bar[1]);
-        if (tgtBytes) tma_bulk_g2s(tgtS, tgtPairs + d.tgtFirst, tgtBytes, &bar[1]);
+        if (taskBytes) tma_bulk_g2s(base + L.offTasks, tasks + d.taskFirst, taskBytes, &bar[1]);
+        if (itemBytes) tma_bulk_g2s(base + L.offItems, items + d.itemFirst, itemBytes, &bar[1]);
+        if (tgtBytes) tma_bulk_g2s(base + L.offTgt, tgtPairs + d.tgtFirst, tgtBytes, &bar[1]);
     };
     /* coordinates of a unit's halo nodes: one gather per node (not per element) */
     auto gather_halo = [&](const dc_unit_t &d, int first, int stride) {
@@ -351,7 +356,7 @@ __global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *_
     __syncthreads();
     if (tid == 0) {
         issue_mesh(descS[0]);
-        issue_sched(descS[0]);
+        issue_sched(descS[0], 0);
     }
     mbar_wait(&bar[0], 0);
     gather_halo(descS[0], tid, THREADS);
@@ -359,6 +364,9 @@ __global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *_
 
     for (int k = 0;; k++) {
         const dc_unit_t u = descS[k & 1];
+        const dc_task_t *taskS = reinterpret_cast<const dc_task_t *>(smem_raw + (k & 1) * L.schedStride + L.offTasks);
+        const int2 *tgtS = reinterpret_cast<const int2 *>(smem_raw + (k & 1) * L.schedStride + L.offTgt);
+        const uint16_t *itemS = reinterpret_cast<const uint16_t *>(smem_raw + (k & 1) * L.schedStride + L.offItems);
         const int nSlots = u.ownElemCount + u.haloCount;
         const int next = unit + (int)gridDim.x;
         const bool hasNext = next < nbUnits;
@@ -399,13 +407,14 @@ __global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *_
                 for (int i = 0; i < Op::NS; i++) recs[s1 * RS + i] = rb[i];
             }
         }
+        mbar_wait(&bar[1], k & 1);   /* this unit's schedule (every thread passes before the phase is re-armed) */
         __syncthreads();   /* A: records complete; node tables and coordinates are dead */
         DC_STAMP(unit, 2);
         if (tid == 0 && hasNext) {
             mbar_wait(&bar[2], k & 1);
             issue_mesh(descS[(k + 1) & 1]);            /* lands while this unit accumulates */
         }
-        mbar_wait(&bar[1], k & 1);
+        if (tid == 0 && hasNext && L.schedStride) issue_sched(descS[(k + 1) & 1], k + 1);   /* into the other buffer */
         DC_STAMP(unit, 3);
 
         /* halo coordinates of the next unit: every thread loads its nodes into registers between
@@ -455,7 +464,7 @@ __global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *_
         if (!hasNext) break;
         if (tid == 0) {
             *nextTask = NW;
-            issue_sched(descS[(k + 1) & 1]);
+            if (!L.schedStride) issue_sched(descS[(k + 1) & 1], k + 1);
         }
         unit = next;
     }
