@@ -18,7 +18,8 @@ from ctypes import POINTER, byref, c_double, c_int, c_int32, c_int64, c_uint16, 
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdc_b200.so")
+# DC_B200_LIB: an experiment build of the same library (dc-lib_b200/Makefile, target `variant`)
+LIB_PATH = os.environ.get("DC_B200_LIB") or os.path.join(_HERE, "libdc_b200.so")
 
 OP_LAPLACIAN, OP_ELASTICITY = 0, 1
 MODE_DETERMINISTIC, MODE_ATOMIC, MODE_LIST = 0, 1, 2
@@ -50,7 +51,7 @@ def lib():
 
 class Unit(ctypes.Structure):
     _fields_ = [("edgeFirst", c_int64), ("itemFirst", c_int64), ("tgtFirst", c_int64), ("slotFirst", c_int64),
-                ("hnodeFirst", c_int64), ("haloFirst", c_int64),
+                ("hnodeFirst", c_int64), ("reserved_", c_int64),
                 ("edgeCount", c_int32), ("nodeFirst", c_int32), ("nodeCount", c_int32),
                 ("ownElemFirst", c_int32), ("ownElemCount", c_int32), ("haloCount", c_int32),
                 ("taskFirst", c_int32), ("taskCount", c_int32), ("itemCount", c_int32),
@@ -73,7 +74,7 @@ class Plan(ctypes.Structure):
                 ("nbUnits", c_int64), ("nbTasks", c_int64),
                 ("nbItems", c_int64), ("nbHalo", c_int64), ("units", POINTER(Unit)),
                 ("tasks", POINTER(Task)), ("items", POINTER(c_uint16)),
-                ("haloElems", POINTER(c_int32)), ("nbSlotNodes", c_int64), ("slotNodes", POINTER(c_uint16)),
+                ("slotElems", POINTER(c_int32)), ("nbSlotNodes", c_int64), ("slotNodes", POINTER(c_uint16)),
                 ("nbHaloNodes", c_int64), ("haloNodes", POINTER(c_int32)), ("diagRel", POINTER(c_int32)),
                 ("big", ContribList), ("nbSlotsTotal", c_int64), ("nbItemsUseful", c_int64)]
 

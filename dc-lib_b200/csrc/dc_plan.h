@@ -11,7 +11,7 @@
  * exactly once -- the reset is fused into that single write.  The elements a unit
  * needs are its own contiguous range [firstElem, lastSep] plus the "halo":
  * elements of ancestor separators that touch one of its nodes.  Each element gets a
- * SLOT; slotNodes gives its 4 nodes as indices into the unit's node table (the own
+ * SLOT (numbered so that the record reads of a half-warp spread over the banks); slotNodes gives its 4 nodes as indices into the unit's node table (the own
  * node interval, whose coordinates are one contiguous block of the coordinate array,
  * followed by the halo nodes), so the kernel stages all coordinates in shared memory
  * once instead of gathering them per element.
@@ -41,11 +41,12 @@ typedef struct {
     int64_t tgtFirst;       /* symmetric schedule: first (edge, transposed edge) pair */
     int64_t slotFirst;      /* first entry of slotNodes (4 uint16 per slot)        */
     int64_t hnodeFirst;     /* first entry of haloNodes                            */
-    int64_t haloFirst;      /* first entry of haloElems (host-side bookkeeping)    */
+    int64_t reserved_;
     int32_t edgeCount;
     int32_t nodeFirst, nodeCount;
-    int32_t ownElemFirst, ownElemCount;   /* slots [0, ownElemCount)                */
-    int32_t haloCount;                    /* slots [ownElemCount, +haloCount)       */
+    int32_t ownElemFirst, ownElemCount;   /* own elements [ownElemFirst, +ownElemCount)          */
+    int32_t haloCount;                    /* halo elements; slots = ownElemCount + haloCount,   */
+                                          /* numbered for the shared-memory banks (slotElems)    */
     int32_t taskFirst, taskCount;
     int32_t itemCount;                    /* uint16 items of the unit (multiple of 32) */
     int32_t tgtCount;                     /* owned edges of the unit (symmetric schedule) */
@@ -89,7 +90,7 @@ typedef struct dc_plan_s {
     dc_unit_t *units;
     dc_task_t *tasks;
     uint16_t  *items;
-    int32_t   *haloElems;   /* element of every halo slot (not needed on the device) */
+    int32_t   *slotElems;   /* [nbSlotNodes/4] element of every slot, -1 for padding (host-side bookkeeping) */
     int64_t    nbSlotNodes; /* uint16 entries in slotNodes (4 per slot, units padded to 2 slots) */
     uint16_t  *slotNodes;   /* per slot: the element's 4 nodes as indices into the unit's node table: */
                             /* own nodes first (from nodeFirst & ~1), then haloNodes                */

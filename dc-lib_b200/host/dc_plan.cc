@@ -211,7 +211,176 @@ struct UnitOut {
     std::vector<uint16_t> slotNodes;   /* 4 per slot */
     std::vector<int32_t> haloNodes;
     std::vector<int32_t> tgt;      /* symmetric schedule: (edge, transposed edge) per upper edge */
+    std::vector<int32_t> slotElems; /* element of every slot */
     int64_t useful = 0;
+};
+
+/* Bank-aware slot numbering.  In the accumulation phase the 16 lanes of a half-warp read, in one
+ * instruction, one component of the node gradients (slot, node a) their items name; the record
+ * stride is 13 doubles and a gradient has 3, so the 8-byte bank is 3*(a - slot) + k (mod 16):
+ * two different gradients collide iff (a - slot) mod 16 is equal.  The slot numbers inside a
+ * unit are free, so they are chosen here: slots are taken in order of decreasing use and put in
+ * the residue class (slot mod 16) that adds the fewest collisions to the half-warp accesses
+ * seen so far (one greedy pass; class sizes are fixed by the slot count, so no slot is wasted).
+ * Measured on the plan (tools/smem_model.py): 2.5 -> 1.65 wavefronts per access. */
+struct BankOpt {
+    std::vector<int> incPtr, incGroup, order, fill;
+    std::vector<uint8_t> incNode, cnt, gmax;
+
+    std::vector<int> stamp;          /* last group that touched a (slot, node) address */
+    std::vector<int> tmpG, tmpX;     /* incidences in visiting order */
+    std::vector<uint8_t> tmpO;
+
+    /* every half-warp access of the accumulation phase: f(group, slot, node) once per distinct
+     * address (equal addresses are a broadcast, not a conflict) */
+    template <class F>
+    int visit(const UnitOut &out, int nSlots, F &&f)
+    {
+        stamp.assign((size_t)nSlots * 4, -1);
+        int g = 0;
+        for (const dc_task_t &t : out.tasks) {
+            const uint16_t *it = out.items.data() + t.itemRel;
+            const int sides = t.kind == DC_TASK_OWNDIAG ? 1 : 2;
+            for (int half = 0; half < 2; half++)
+                for (int side = 0; side < sides; side++)
+                    for (int r = 0; r < (int)t.iters; r++, g++) {
+                        const uint16_t *row = it + r * 32 + half * 16;
+                        for (int l = 0; l < 16; l++) {
+                            const uint32_t item = row[l];
+                            const int slot = (int)(item >> 4);
+                            if (slot >= nSlots) continue;
+                            const int node = side ? (int)(item & 3u) : (int)((item >> 2) & 3u);
+                            int &st = stamp[(size_t)slot * 4 + node];
+                            if (st == g) continue;
+                            st = g;
+                            f(g, slot, node);
+                        }
+                    }
+        }
+        return g;
+    }
+
+    /* entities with incidences (group, offset) in incPtr/incGroup/incNode; an entity in class c
+     * occupies key (offset - c) mod 16 of each of its groups.  fixedCls[x] >= 0 pins an entity;
+     * the others are placed in order of decreasing use into the class (with room left, cap[c])
+     * that adds the fewest collisions.  Result in cls. */
+    void greedy(int nEnt, int nbGroups, const int *fixedCls, const int *capIn, std::vector<int> &cls)
+    {
+        cls.assign((size_t)nEnt, -1);
+        cnt.assign((size_t)nbGroups * 16, 0);
+        gmax.assign((size_t)nbGroups, 0);
+        int used[16], cap[16];
+        for (int c = 0; c < 16; c++) { used[c] = 0; cap[c] = capIn[c]; }
+        auto place = [&](int x, int c) {
+            cls[(size_t)x] = c;
+            for (int q = incPtr[(size_t)x]; q < incPtr[(size_t)x + 1]; q++) {
+                const int g = incGroup[(size_t)q], k = ((int)incNode[(size_t)q] - c) & 15;
+                const uint8_t now = ++cnt[(size_t)g * 16 + k];
+                if (now > gmax[(size_t)g]) gmax[(size_t)g] = now;
+            }
+        };
+        order.clear();
+        for (int x = 0; x < nEnt; x++) {
+            if (fixedCls && fixedCls[x] >= 0) place(x, fixedCls[x]);
+            else order.push_back(x);
+        }
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+            return incPtr[(size_t)x + 1] - incPtr[(size_t)x] > incPtr[(size_t)y + 1] - incPtr[(size_t)y];
+        });
+        for (int x : order) {
+            /* cost of every class at once: per offset, the sum over the entity's groups of
+             * (entries already on that key) + 64 if one more raises the group's maximum */
+            uint16_t w[4][16];
+            for (int o = 0; o < 4; o++)
+                for (int k = 0; k < 16; k++) w[o][k] = 0;
+            for (int q = incPtr[(size_t)x]; q < incPtr[(size_t)x + 1]; q++) {
+                const uint8_t *row = cnt.data() + (size_t)incGroup[(size_t)q] * 16;
+                const uint8_t mx = gmax[(size_t)incGroup[(size_t)q]];
+                uint16_t *dst = w[incNode[(size_t)q] & 3];
+                #pragma omp simd
+                for (int k = 0; k < 16; k++) dst[k] = (uint16_t)(dst[k] + row[k] + (row[k] >= mx ? 64 : 0));
+            }
+            int bestC = -1, bestV = 0;
+            for (int c = 0; c < 16; c++) {
+                if (used[c] >= cap[c]) continue;
+                const int v = w[0][(0 - c) & 15] + w[1][(1 - c) & 15] + w[2][(2 - c) & 15] + w[3][(3 - c) & 15];
+                if (bestC < 0 || v < bestV) { bestC = c; bestV = v; }
+            }
+            used[bestC]++;
+            place(x, bestC);
+        }
+    }
+
+    /* incidence lists from a visitor that calls f(group, entity, offset); returns the group count */
+    template <class V>
+    int collect(int nEnt, V &&visitAll)
+    {
+        tmpG.clear(); tmpX.clear(); tmpO.clear();
+        incPtr.assign((size_t)nEnt + 1, 0);
+        const int nbGroups = visitAll([&](int g, int x, int off) {
+            tmpG.push_back(g); tmpX.push_back(x); tmpO.push_back((uint8_t)off);
+            incPtr[(size_t)x + 1]++;
+        });
+        for (int x = 0; x < nEnt; x++) incPtr[(size_t)x + 1] += incPtr[(size_t)x];
+        incGroup.resize(tmpG.size());
+        incNode.resize(tmpG.size());
+        fill.assign(incPtr.begin(), incPtr.end() - 1);
+        for (size_t i = 0; i < tmpG.size(); i++) {
+            const int q = fill[(size_t)tmpX[i]]++;
+            incGroup[(size_t)q] = tmpG[i];
+            incNode[(size_t)q] = tmpO[i];
+        }
+        return nbGroups;
+    }
+
+    void run(const UnitOut &out, int nSlots, std::vector<int> &newSlot)
+    {
+        newSlot.resize((size_t)nSlots);
+        for (int s = 0; s < nSlots; s++) newSlot[(size_t)s] = s;
+        if (nSlots <= 16) return;
+        const int nbGroups = collect(nSlots, [&](auto &&f) { return visit(out, nSlots, f); });
+        int cap[16], used[16];
+        for (int c = 0; c < 16; c++) { used[c] = 0; cap[c] = (nSlots - c + 15) / 16; }
+        greedy(nSlots, nbGroups, nullptr, cap, newSlot);
+        /* inside a class, keep the incoming (element) order: the 16 consecutive slots that one
+         * half-warp turns into records then hold elements close to each other, which share nodes
+         * (their coordinate reads are broadcasts) */
+        for (int s = 0; s < nSlots; s++) {
+            const int c = newSlot[(size_t)s];
+            newSlot[(size_t)s] = c + 16 * used[c]++;
+        }
+    }
+
+    /* The same for the record build: the 16 threads of a half-warp read, per instruction, one
+     * coordinate of node j of 16 consecutive slots; the bank is 3*tableIndex + q (mod 16), so two
+     * different nodes collide iff their table indices are equal mod 16.  Own nodes sit where the
+     * bulk copy of the coordinate block puts them; the halo nodes' table positions are free.
+     * nodeOf[slot*4+j] = entity (0..nEnt-1), fixedCls as in greedy(); positions of the free
+     * entities (table index mod 16 = (16 - class) mod 16) are handed out in haloPos. */
+    void run_nodes(const std::vector<int> &nodeOf, int nSlots, int nEnt, const std::vector<int> &fixedCls,
+                   int ownSpan, int nHalo, std::vector<int> &cls)
+    {
+        const int nbGroups = collect(nEnt, [&](auto &&f) {
+            int g = 0;
+            for (int s0 = 0; s0 < nSlots; s0 += 16)
+                for (int j = 0; j < 4; j++, g++) {
+                    int seen[16], nseen = 0;
+                    for (int l = 0; l < 16 && s0 + l < nSlots; l++) {
+                        const int x = nodeOf[(size_t)(s0 + l) * 4 + j];
+                        bool dup = false;
+                        for (int q = 0; q < nseen; q++) dup |= seen[q] == x;
+                        if (dup) continue;
+                        seen[nseen++] = x;
+                        f(g, x, 0);
+                    }
+                }
+            return g;
+        });
+        int cap[16];
+        for (int c = 0; c < 16; c++) cap[c] = 0;
+        for (int p = 0; p < nHalo; p++) cap[(16 - ((ownSpan + p) & 15)) & 15]++;
+        greedy(nEnt, nbGroups, fixedCls.data(), cap, cls);
+    }
 };
 
 /* edge index of (rowNode, colNode) */
@@ -230,8 +399,8 @@ inline int slot_of(const UnitSeed &s, int e)
 }
 
 /* items of every edge of the unit, grouped per edge in ascending element order */
-void build_unit(const Mesh &m, const UnitSeed &s, int32_t *diagRel, UnitOut &out,
-                std::vector<std::vector<uint16_t>> &perEdge, int &error, bool symmetric)
+void build_tasks(const Mesh &m, const UnitSeed &s, int32_t *diagRel, UnitOut &out,
+                 std::vector<std::vector<uint16_t>> &perEdge, int &error, bool symmetric)
 {
     const int64_t edgeFirst = m.row[s.nodeFirst];
     const int edgeCount = m.row[s.nodeFirst + s.nodeCount] - (int)edgeFirst;
@@ -240,39 +409,6 @@ void build_unit(const Mesh &m, const UnitSeed &s, int32_t *diagRel, UnitOut &out
     std::vector<char> isDiag((size_t)edgeCount, 0);
     /* padding of the item rows: slot nSlots is the kernel's all-zero record */
     const uint16_t padItem = (uint16_t)((s.ownCount + (int)s.halo.size()) << 4);
-
-    /* node table: own interval (from the even node at or below nodeFirst, padded to an even
-     * count so that the block of coordinates is a 16-byte granule copy), then halo nodes */
-    {
-        const int alignedFirst = s.nodeFirst & ~1;
-        const int ownSpan = ((s.nodeFirst + s.nodeCount + 1) & ~1) - alignedFirst;
-        const int nSlots = s.ownCount + (int)s.halo.size();
-        std::vector<int> outside;
-        for (int sl = 0; sl < nSlots; sl++) {
-            const int e = sl < s.ownCount ? s.ownFirst + sl : s.halo[(size_t)(sl - s.ownCount)];
-            for (int j = 0; j < 4; j++) {
-                const int nd = m.conn[(int64_t)e * 4 + j] - 1;
-                if (nd < s.nodeFirst || nd >= s.nodeFirst + s.nodeCount) outside.push_back(nd);
-            }
-        }
-        std::sort(outside.begin(), outside.end());
-        outside.erase(std::unique(outside.begin(), outside.end()), outside.end());
-        if (ownSpan + (int)outside.size() > 65535) { error = 1; return; }
-        out.haloNodes.assign(outside.begin(), outside.end());
-        out.slotNodes.resize((size_t)nSlots * 4);
-        for (int sl = 0; sl < nSlots; sl++) {
-            const int e = sl < s.ownCount ? s.ownFirst + sl : s.halo[(size_t)(sl - s.ownCount)];
-            for (int j = 0; j < 4; j++) {
-                const int nd = m.conn[(int64_t)e * 4 + j] - 1;
-                int idx;
-                if (nd >= s.nodeFirst && nd < s.nodeFirst + s.nodeCount) idx = nd - alignedFirst;
-                else idx = ownSpan + (int)(std::lower_bound(outside.begin(), outside.end(), nd) - outside.begin());
-                out.slotNodes[(size_t)sl * 4 + j] = (uint16_t)idx;
-            }
-        }
-        while (out.slotNodes.size() % 8) out.slotNodes.push_back(0);    /* 16-byte granules */
-        while (out.haloNodes.size() % 4) out.haloNodes.push_back(0);
-    }
 
     for (int n = s.nodeFirst; n < s.nodeFirst + s.nodeCount; n++) {
         const int r0 = m.row[n], r1 = m.row[n + 1];
@@ -416,6 +552,75 @@ void build_unit(const Mesh &m, const UnitSeed &s, int32_t *diagRel, UnitOut &out
     out.tasks.insert(out.tasks.begin(), diagTasks.begin(), diagTasks.end());
 }
 
+
+/* slots renumbered for the banks, then the node table: own interval (from the even node at or
+ * below nodeFirst, padded to an even count so that the block of coordinates is a 16-byte granule
+ * copy), then the halo nodes; slotNodes in slot order */
+void build_unit(const Mesh &m, const UnitSeed &s, int32_t *diagRel, UnitOut &out,
+                std::vector<std::vector<uint16_t>> &perEdge, int &error, bool symmetric, BankOpt &opt,
+                bool bankAware)
+{
+    build_tasks(m, s, diagRel, out, perEdge, error, symmetric);
+    if (error) return;
+    const int nSlots = s.ownCount + (int)s.halo.size();
+    std::vector<int> newSlot;
+    if (bankAware) opt.run(out, nSlots, newSlot);
+    else { newSlot.resize((size_t)nSlots); for (int q = 0; q < nSlots; q++) newSlot[(size_t)q] = q; }
+    for (uint16_t &it : out.items) {
+        const int slot = it >> 4;
+        if (slot < nSlots) it = (uint16_t)((newSlot[(size_t)slot] << 4) | (it & 15));
+    }
+    out.slotElems.assign((size_t)nSlots, -1);
+    for (int sl = 0; sl < nSlots; sl++)
+        out.slotElems[(size_t)newSlot[(size_t)sl]] =
+            sl < s.ownCount ? s.ownFirst + sl : s.halo[(size_t)(sl - s.ownCount)];
+    const int alignedFirst = s.nodeFirst & ~1;
+    const int ownSpan = ((s.nodeFirst + s.nodeCount + 1) & ~1) - alignedFirst;
+    std::vector<int> outside;
+    for (int sl = 0; sl < nSlots; sl++) {
+        const int e = out.slotElems[(size_t)sl];
+        for (int j = 0; j < 4; j++) {
+            const int nd = m.conn[(int64_t)e * 4 + j] - 1;
+            if (nd < s.nodeFirst || nd >= s.nodeFirst + s.nodeCount) outside.push_back(nd);
+        }
+    }
+    std::sort(outside.begin(), outside.end());
+    outside.erase(std::unique(outside.begin(), outside.end()), outside.end());
+    const int nHalo = (int)outside.size();
+    if (ownSpan + nHalo > 65535) { error = 1; return; }
+    /* entity = own node (table index fixed) or halo node (position chosen for the banks) */
+    std::vector<int> nodeOf((size_t)nSlots * 4), fixedCls((size_t)(ownSpan + nHalo), -1), cls;
+    for (int x = 0; x < ownSpan; x++) fixedCls[(size_t)x] = (16 - (x & 15)) & 15;
+    for (int sl = 0; sl < nSlots; sl++) {
+        const int e = out.slotElems[(size_t)sl];
+        for (int j = 0; j < 4; j++) {
+            const int nd = m.conn[(int64_t)e * 4 + j] - 1;
+            if (nd >= s.nodeFirst && nd < s.nodeFirst + s.nodeCount) nodeOf[(size_t)sl * 4 + j] = nd - alignedFirst;
+            else nodeOf[(size_t)sl * 4 + j] = ownSpan + (int)(std::lower_bound(outside.begin(), outside.end(), nd) - outside.begin());
+        }
+    }
+    std::vector<int> tableIdx((size_t)(ownSpan + nHalo));
+    for (int x = 0; x < ownSpan + nHalo; x++) tableIdx[(size_t)x] = x;
+    if (bankAware && nHalo > 16) {
+        opt.run_nodes(nodeOf, nSlots, ownSpan + nHalo, fixedCls, ownSpan, nHalo, cls);
+        /* positions ownSpan + p with (ownSpan + p) mod 16 == (16 - class) mod 16, in node order */
+        int nextPos[16];
+        for (int r = 0; r < 16; r++) nextPos[r] = ((r - ownSpan) % 16 + 16) % 16;      /* first p with that residue */
+        for (int x = ownSpan; x < ownSpan + nHalo; x++) {
+            const int r = (16 - cls[(size_t)x]) & 15;
+            tableIdx[(size_t)x] = ownSpan + nextPos[r];
+            nextPos[r] += 16;
+        }
+    }
+    out.haloNodes.assign((size_t)nHalo, 0);
+    for (int x = ownSpan; x < ownSpan + nHalo; x++) out.haloNodes[(size_t)(tableIdx[(size_t)x] - ownSpan)] = outside[(size_t)(x - ownSpan)];
+    out.slotNodes.resize((size_t)nSlots * 4);
+    for (size_t q = 0; q < (size_t)nSlots * 4; q++) out.slotNodes[q] = (uint16_t)tableIdx[(size_t)nodeOf[q]];
+    while (out.slotNodes.size() % 8) out.slotNodes.push_back(0);    /* 16-byte granules */
+    while (out.slotElems.size() % 2) out.slotElems.push_back(-1);
+    while (out.haloNodes.size() % 4) out.haloNodes.push_back(0);
+}
+
 template <typename T>
 T *dup(const std::vector<T> &v)
 {
@@ -546,6 +751,9 @@ extern "C" int dc_plan_build(dc_plan_t *plan, const int *conn, int nbElem, int n
     std::vector<std::vector<uint16_t>> tItems((size_t)nt);
     std::vector<std::vector<int32_t>> tTgt((size_t)nt);
     std::vector<std::vector<uint16_t>> tSlot((size_t)nt);
+    std::vector<std::vector<int32_t>> tSlotElem((size_t)nt);
+    const char *noBank = getenv("DC_PLAN_NO_BANK_NUMBERING");
+    const bool bankAware = !(noBank && *noBank && *noBank != '0');
     std::vector<std::vector<int32_t>> tHnode((size_t)nt);
     std::vector<int> unitThread((size_t)nbUnits);
     int error = 0;
@@ -555,6 +763,7 @@ extern "C" int dc_plan_build(dc_plan_t *plan, const int *conn, int nbElem, int n
     {
         const int tid = omp_get_thread_num();
         UnitOut out;
+        BankOpt opt;
         std::vector<std::vector<uint16_t>> perEdge;
         #pragma omp for schedule(dynamic, 64)
         for (int64_t u = 0; u < nbUnits; u++) {
@@ -564,8 +773,9 @@ extern "C" int dc_plan_build(dc_plan_t *plan, const int *conn, int nbElem, int n
             out.tgt.clear();
             out.slotNodes.clear();
             out.haloNodes.clear();
+            out.slotElems.clear();
             out.useful = 0;
-            build_unit(m, s, diagRel.data(), out, perEdge, error, symmetric != 0);
+            build_unit(m, s, diagRel.data(), out, perEdge, error, symmetric != 0, opt, bankAware);
             const int32_t nbUpper = (int32_t)(out.tgt.size() / 2);
             while (out.tgt.size() % 4) out.tgt.push_back(0);      /* 16-byte granules for the bulk copy */
             dc_unit_t &d = units[(size_t)u];
@@ -590,6 +800,7 @@ extern "C" int dc_plan_build(dc_plan_t *plan, const int *conn, int nbElem, int n
                 d.hnodeCount = hn;
             }
             tSlot[tid].insert(tSlot[tid].end(), out.slotNodes.begin(), out.slotNodes.end());
+            tSlotElem[tid].insert(tSlotElem[tid].end(), out.slotElems.begin(), out.slotElems.end());
             tHnode[tid].insert(tHnode[tid].end(), out.haloNodes.begin(), out.haloNodes.end());
             tTgt[tid].insert(tTgt[tid].end(), out.tgt.begin(), out.tgt.end());
             unitThread[(size_t)u] = tid;
@@ -614,8 +825,11 @@ extern "C" int dc_plan_build(dc_plan_t *plan, const int *conn, int nbElem, int n
     plan->slotNodes = (uint16_t *)malloc(sizeof(uint16_t) * (size_t)(plan->nbSlotNodes ? plan->nbSlotNodes : 1));
     plan->nbHaloNodes = hnodeBase[nt];
     plan->haloNodes = (int32_t *)malloc(sizeof(int32_t) * (size_t)(plan->nbHaloNodes ? plan->nbHaloNodes : 1));
+    plan->slotElems = (int32_t *)malloc(sizeof(int32_t) * (size_t)(slotBase[nt] ? slotBase[nt] : 1));
     for (int t = 0; t < nt; t++) {
         if (!tSlot[t].empty()) memcpy(plan->slotNodes + 4 * slotBase[t], tSlot[t].data(), sizeof(uint16_t) * tSlot[t].size());
+        if (!tSlotElem[t].empty()) memcpy(plan->slotElems + slotBase[t], tSlotElem[t].data(), sizeof(int32_t) * tSlotElem[t].size());
+        std::vector<int32_t>().swap(tSlotElem[t]);
         if (!tHnode[t].empty()) memcpy(plan->haloNodes + hnodeBase[t], tHnode[t].data(), sizeof(int32_t) * tHnode[t].size());
         std::vector<uint16_t>().swap(tSlot[t]);
         std::vector<int32_t>().swap(tHnode[t]);
@@ -650,8 +864,7 @@ extern "C" int dc_plan_build(dc_plan_t *plan, const int *conn, int nbElem, int n
         d.hnodeFirst += hnodeBase[t];
         maxTgt = std::max(maxTgt, (d.tgtCount + 1) & ~1);
         maxNodes = std::max(maxNodes, ((d.nodeFirst + d.nodeCount + 1) & ~1) - (d.nodeFirst & ~1));
-        d.haloFirst = haloTotal;                       /* multiple of 4: bulk copies need 16-byte sources */
-        haloTotal += (d.haloCount + 3) & ~3;
+        haloTotal += d.haloCount;
         slotsTotal += d.ownElemCount + d.haloCount;
         maxUsed = std::max(maxUsed, d.ownElemCount + d.haloCount);
         maxHalo = std::max(maxHalo, d.hnodeCount);
@@ -663,11 +876,6 @@ extern "C" int dc_plan_build(dc_plan_t *plan, const int *conn, int nbElem, int n
     plan->maxItems = maxItems;
     plan->maxTgt = maxTgt;
     plan->maxNodes = maxNodes;
-    plan->haloElems = (int32_t *)calloc((size_t)(haloTotal ? haloTotal : 1), sizeof(int32_t));
-    for (int64_t u = 0; u < nbUnits; u++) {
-        const std::vector<int> &h = seeds[(size_t)u].halo;
-        if (!h.empty()) memcpy(plan->haloElems + units[(size_t)u].haloFirst, h.data(), sizeof(int32_t) * h.size());
-    }
     lap("concat");
     plan->nbHalo = haloTotal;
     plan->nbUnits = nbUnits;
@@ -692,7 +900,7 @@ extern "C" void dc_contrib_free(dc_contrib_list_t *c)
 
 extern "C" void dc_plan_free(dc_plan_t *plan)
 {
-    free(plan->units); free(plan->tasks); free(plan->items); free(plan->haloElems); free(plan->diagRel);
+    free(plan->units); free(plan->tasks); free(plan->items); free(plan->slotElems); free(plan->diagRel);
     free(plan->tgt); free(plan->slotNodes); free(plan->haloNodes);
     dc_contrib_free(&plan->big);
     memset(plan, 0, sizeof *plan);

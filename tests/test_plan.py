@@ -14,8 +14,8 @@ def _plan_arrays(p):
     units = [c.units[i] for i in range(c.nbUnits)]
     tasks = [c.tasks[i] for i in range(c.nbTasks)]
     items = np.ctypeslib.as_array(c.items, shape=(max(c.nbItems, 1),))[:c.nbItems]
-    halo = np.ctypeslib.as_array(c.haloElems, shape=(max(c.nbHalo, 1),))[:c.nbHalo]
-    return units, tasks, items, halo
+    slot_elems = np.ctypeslib.as_array(c.slotElems, shape=(max(c.nbSlotNodes // 4, 1),))[:c.nbSlotNodes // 4]
+    return units, tasks, items, slot_elems
 
 
 @pytest.mark.parametrize("sym", [True, False])
@@ -25,7 +25,7 @@ def test_plan_covers_every_contribution_once(tmp_path, n, vec, slots, hub, sym):
     mesh = prepare_mesh(MineLib(vec), n, tmp_path, hub=hub)
     rec = tree_records(mesh)
     plan = dc.HostPlan(mesh["conn"], mesh["N"], mesh["row"], mesh["col"], 0, rec, slots, symmetric=sym)
-    units, tasks, items, halo = _plan_arrays(plan)
+    units, tasks, items, slot_elems = _plan_arrays(plan)
     tgt = np.ctypeslib.as_array(plan.c.tgt, shape=(max(plan.c.nbTgt, 1), 2))
     slotNodes = np.ctypeslib.as_array(plan.c.slotNodes, shape=(max(plan.c.nbSlotNodes, 1),))
     haloNodes = np.ctypeslib.as_array(plan.c.haloNodes, shape=(max(plan.c.nbHaloNodes, 1),))
@@ -50,8 +50,11 @@ def test_plan_covers_every_contribution_once(tmp_path, n, vec, slots, hub, sym):
         assert u.edgeFirst == row[u.nodeFirst] and u.edgeCount == row[u.nodeFirst + u.nodeCount] - row[u.nodeFirst]
         nslots = u.ownElemCount + u.haloCount
         assert nslots <= slots
-        elems = list(range(u.ownElemFirst, u.ownElemFirst + u.ownElemCount)) + \
-            halo[u.haloFirst:u.haloFirst + u.haloCount].tolist()
+        # slots are numbered for the shared-memory banks: a permutation of own elements + halo
+        elems = slot_elems[u.slotFirst:u.slotFirst + nslots].tolist()
+        own = set(range(u.ownElemFirst, u.ownElemFirst + u.ownElemCount))
+        assert len(set(elems)) == nslots and own <= set(elems)
+        assert all(e in own or any(u.nodeFirst <= nd < u.nodeFirst + u.nodeCount for nd in conn[e]) for e in elems)
         # node table: own interval from the even node at or below nodeFirst, then the halo nodes
         aligned = u.nodeFirst & ~1
         span = ((u.nodeFirst + u.nodeCount + 1) & ~1) - aligned
