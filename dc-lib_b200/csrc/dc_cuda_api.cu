@@ -449,8 +449,8 @@ extern "C" int dc_cuda_set_option(dc_cuda_ctx *c, const char *name, int value)
 {
     if (!c || !name) return fail(-1, "dc_cuda_set_option: null argument");
     if (!strcmp(name, "unit_threads")) {
-        if (value != 128 && value != 192 && value != 256)
-            return fail(-12, "dc_cuda_set_option: unit_threads must be 128, 192 or 256");
+        if (value != 128 && value != 192 && value != 256 && value != 512)
+            return fail(-12, "dc_cuda_set_option: unit_threads must be 128, 192, 256 or 512");
         c->threads = value;
         return 0;
     }

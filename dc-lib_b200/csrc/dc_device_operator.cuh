@@ -113,6 +113,7 @@ inline int launch_operator(dc_launch_args *a, const double *h_params, int nbPara
             int rc;
             if (a->symmetric)
                 rc = (a->threads == 128)   ? launch_units<Op, 128, 4, true>(a, d_values, s)
+                     : (a->threads == 512) ? launch_units<Op, 512, 1, true>(a, d_values, s)
                      : (a->threads == 192) ? launch_units<Op, 192, 3, true>(a, d_values, s)
                                            : launch_units<Op, 256, 2, true>(a, d_values, s);
             else
