@@ -27,6 +27,7 @@ WORKLOADS = {
     "c3": (256, 1, 0, "geometric"),          # BASELINE config 3: ~100M tets, Laplacian
     "e256": (256, 3, 0, "geometric"),        # 100M tets, elasticity
     "e160": (160, 3, 0, "geometric"),        # 24.6M tets, elasticity
+    "l160": (160, 1, 0, "geometric"),        # 24.6M tets, Laplacian
     "c2": (40, 3, 4, "metis"),               # BASELINE config 2: 40^3, elasticity, D&C + colouring
     "m100": (100, 3, 0, "metis"),            # 6M tets, elasticity (METIS tree, as the reference builds it)
     "m64": (64, 3, 0, "metis"),
@@ -131,8 +132,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="dc_b200", choices=["dc_b200", "reference"])
     ap.add_argument("--workload", default=os.environ.get("DC_BENCH_WORKLOAD", "target350"))
-    ap.add_argument("--slots", type=int, default=int(os.environ.get("DC_BENCH_SLOTS", "512")))
-    ap.add_argument("--threads", type=int, default=int(os.environ.get("DC_BENCH_THREADS", "256")))
+    ap.add_argument("--slots", type=int, default=int(os.environ.get("DC_BENCH_SLOTS", "0")),
+                    help="element slots per work unit; 0 = the measured best for the operator")
+    ap.add_argument("--threads", type=int, default=int(os.environ.get("DC_BENCH_THREADS", "0")),
+                    help="threads per CTA of the unit kernel; 0 = the measured best for the operator")
     ap.add_argument("--persistent", type=int, default=int(os.environ.get("DC_BENCH_PERSISTENT", "1")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verify", action="store_true",
@@ -141,6 +144,11 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     n, dim, vec, builder = WORKLOADS[args.workload]
+    # unit geometry (profiles/README.md): 3x3-block elasticity runs best with two 256-thread CTAs per SM
+    # and 512-slot units, the scalar Laplacian with one 512-thread CTA and 1536-slot units
+    best_slots, best_threads = (512, 256) if dim == 3 else (1536, 512)
+    args.slots = args.slots or best_slots
+    args.threads = args.threads or best_threads
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))

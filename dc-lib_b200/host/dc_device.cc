@@ -13,7 +13,7 @@ namespace {
 
 dc_cuda_ctx *g_ctx = nullptr;
 int g_mode = DC_DEVICE_DETERMINISTIC;
-int g_maxSlots = 400;
+int g_maxSlots = 512;     /* measured best with 256-thread CTAs, two per SM (profiles/README.md) */
 int g_symmetric = 1;     /* both built-in operators have bitwise symmetric element matrices */
 
 [[noreturn]] void die(const char *what)

@@ -205,13 +205,32 @@ class MineLib:
         dc.DC_read_tree(path, E, N)
 
 
-def prepare_mesh(lib, n, tmp_path, hub=False, tag="t"):
+def scramble_mesh(conn, coord, seed=2024):
+    """BASELINE config C4's irregular mesh at test size: graded coordinates (smooth monotone warp
+    x -> x^1.5 of the unit cube), a seeded random relabelling of the nodes and a shuffle of the
+    elements, applied BEFORE DC_create_tree (the library has to find the locality again)."""
+    rng = np.random.default_rng(seed)
+    N, E = coord.shape[0], conn.shape[0]
+    span = coord.max(axis=0) - coord.min(axis=0)
+    unit = (coord - coord.min(axis=0)) / span
+    coord = np.ascontiguousarray(unit ** 1.5 * span)
+    relabel = rng.permutation(N).astype(np.int32)          # old node -> new node
+    new_coord = np.empty_like(coord)
+    new_coord[relabel] = coord
+    new_conn = relabel[conn - 1] + 1
+    new_conn = np.ascontiguousarray(new_conn[rng.permutation(E)], dtype=np.int32)
+    return new_conn, np.ascontiguousarray(new_coord)
+
+
+def prepare_mesh(lib, n, tmp_path, hub=False, tag="t", scramble=False):
     """Appendix-A driver: mesh -> create_tree -> permute/renumber -> CSR -> finalize -> store.
     Returns the user-side arrays plus the stored tree file bytes."""
     conn, N = dc.kuhn_cube(n)
     coord = dc.jitter_coords(n)
     if hub:
         conn, coord, N = dc.hub_collapse(conn, coord, n)
+    if scramble:
+        conn, coord = scramble_mesh(conn, coord)
     E = conn.shape[0]
     if getattr(lib, "geometric", False):
         lib.create_tree(conn, E, N, coord)

@@ -96,6 +96,32 @@ def test_all_modes_against_oracle(tmp_path, n, vec, dim, slots, hub, sym):
         assert plan.c.big.nbEdges > 0           # the fallback really ran
 
 
+@pytest.mark.parametrize("persistent", [0, 1])
+@pytest.mark.parametrize("threads", [128, 192, 256, 512])
+def test_kernel_variants_bit_exact(tmp_path, threads, persistent):
+    """Every instantiation of the unit kernel (CTA size, persistent grid or one CTA per unit), on a
+    plan with several units per resident CTA so that the persistent loop really cycles."""
+    mesh = prepare_mesh(MineLib(0), 16, tmp_path)
+    ctx, plan = _ctx(mesh, slots=64)
+    assert plan.c.nbUnits > 2 * 4 * 148        # four 128-thread CTAs per SM at most
+    ctx.set_option("unit_threads", threads)
+    ctx.set_option("persistent", persistent)
+    for dim in (1, 3):
+        assert _run(ctx, mesh, dim, dc.MODE_DETERMINISTIC).tobytes() == oracle_serial(mesh, dim).tobytes()
+
+
+@pytest.mark.parametrize("dim,vec", [(3, 0), (1, 4)])
+def test_graded_shuffled_mesh_bit_exact(tmp_path, dim, vec):
+    """BASELINE config C4's mesh at test size: graded coordinates, random node labels, shuffled
+    elements before DC_create_tree (METIS tree)."""
+    mesh = prepare_mesh(MineLib(vec), 12, tmp_path, scramble=True)
+    want = oracle_serial(mesh, dim)
+    for sym in (True, False):
+        ctx, _ = _ctx(mesh, slots=400, sym=sym)
+        assert _run(ctx, mesh, dim, dc.MODE_DETERMINISTIC).tobytes() == want.tobytes()
+        assert _rel_err(_run(ctx, mesh, dim, dc.MODE_ATOMIC), want) <= REL_TOL
+
+
 @pytest.mark.parametrize("n,dim", [(12, 3), (20, 1)])
 def test_geometric_tree_bit_exact(tmp_path, n, dim):
     """Trees cut by coordinate bisection (the at-scale builder) feed the same device path."""

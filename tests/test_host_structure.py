@@ -52,6 +52,19 @@ def test_tree_file_matches_reference_side_by_side(tmp_path, n, vec):
     assert a["coord"].tobytes() == b["coord"].tobytes()
 
 
+@pytest.mark.parametrize("n,vec", [(9, 0), (10, 4)])
+def test_graded_shuffled_mesh_matches_reference(tmp_path, n, vec):
+    """BASELINE config C4's irregular mesh at test size (graded, relabelled, shuffled): tree file,
+    permuted connectivity and coordinates byte-identical to the unmodified reference."""
+    if not have_ref(vec):
+        pytest.skip("reference not built (oracle/_ref)")
+    a = prepare_mesh(RefLib(vec), n, tmp_path, tag="ref", scramble=True)
+    b = prepare_mesh(MineLib(vec), n, tmp_path, tag="mine", scramble=True)
+    assert a["tree"] == b["tree"]
+    assert a["conn"].tobytes() == b["conn"].tobytes()
+    assert a["coord"].tobytes() == b["coord"].tobytes()
+
+
 def test_store_read_store_roundtrip(tmp_path):
     lib = MineLib(4)
     mesh = prepare_mesh(lib, 8, tmp_path)
