@@ -294,7 +294,7 @@ def main():
                 "h2d_bytes_per_step": 24 * N, "d2h_bytes_per_step": 8 * per * nnz, "steps": e2e_steps,
                 "host_buffer": "full-size pinned array" if ring == total else "2 GiB pinned ring", "checksum": checksum},
         "gpu_launches": launches, "clocks": sampler.summary(),
-        "setup": {"tree_and_csr_s": info["tree_s"], "plan_s": info["plan_s"], "total_s": info["setup_s"],
+        "setup": {"tree_and_csr_s": info["tree_s"], "csr_on_gpu_s": info["csr_s"], "plan_s": info["plan_s"], "total_s": info["setup_s"],
                   "units": st["units"], "element_setups_per_element": st["slots_total"] / E,
                   "item_padding_efficiency": st["items_useful"] / max(st["items"], 1), "host_cores": os.cpu_count()},
     }

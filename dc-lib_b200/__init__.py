@@ -118,6 +118,11 @@ def _declare(L):
     L.dc_get_elem_perm.argtypes = [vp, c_int]
     L.dc_cuda_pack_edges.argtypes = [vp, vp, c_int64, c_int, vp, vp]
     L.dc_cuda_unpack_add_edges.argtypes = [vp, vp, c_int64, c_int, vp, vp]
+    L.dc_cuda_csr_begin.argtypes = [vp, c_int, c_int, vp, POINTER(c_int64), POINTER(c_void_p), vp]
+    L.dc_cuda_csr_columns.argtypes = [vp, vp, c_int, vp]
+    L.dc_cuda_csr_node_to_elem.argtypes = [vp, vp, vp, vp]
+    L.dc_cuda_csr_end.argtypes = [vp]
+    L.dc_cuda_csr_end.restype = None
     L.dcx_build_csr.argtypes = [vp, c_int, c_int, vp, vp, c_int]
     L.dcx_build_csr.restype = c_int64
     L.dc_flatten_tree.argtypes = [vp, c_int64]
@@ -448,6 +453,35 @@ def unpack_add_edges(d_values, d_edge, perEdge, d_buf, stream=None):
     rc = lib().dc_cuda_unpack_add_edges(_p(d_values), _p(d_edge), d_edge.numel(), perEdge, _p(d_buf), stream)
     if rc:
         raise RuntimeError(lib().dc_cuda_last_error().decode())
+
+
+def build_csr_device(d_conn, nbNodes, colBase=0, node_to_elem=False, stream=None):
+    """CSR pattern of the renumbered mesh built on the GPU (include/dc_cuda.h, dc_cuda_csr_*).
+    d_conn: torch int32 CUDA tensor [nbElem, 4], 1-based.  Returns (row, col) as torch CUDA tensors,
+    plus (n2e_ptr, n2e_val) when node_to_elem is set; identical to build_csr_fast's arrays."""
+    import torch
+    assert d_conn.is_cuda and d_conn.dtype == torch.int32 and d_conn.is_contiguous()
+    E = d_conn.shape[0]
+    row = torch.empty(nbNodes + 1, dtype=torch.int32, device=d_conn.device)
+    nnz, h = c_int64(0), c_void_p()
+    if lib().dc_cuda_csr_begin(_p(d_conn), E, nbNodes, _p(row), byref(nnz), byref(h), stream):
+        raise RuntimeError("dc_cuda_csr_begin: " + lib().dc_cuda_last_error().decode())
+    try:
+        col = torch.empty(nnz.value, dtype=torch.int32, device=d_conn.device)
+        if lib().dc_cuda_csr_columns(h, _p(col), colBase, stream):
+            raise RuntimeError("dc_cuda_csr_columns: " + lib().dc_cuda_last_error().decode())
+        out = (row, col)
+        if node_to_elem:
+            ptr = torch.empty(nbNodes + 1, dtype=torch.int64, device=d_conn.device)
+            val = torch.empty(4 * E, dtype=torch.int32, device=d_conn.device)
+            if lib().dc_cuda_csr_node_to_elem(h, _p(ptr), _p(val), stream):
+                raise RuntimeError("dc_cuda_csr_node_to_elem: " + lib().dc_cuda_last_error().decode())
+            out = (row, col, ptr, val)
+        if lib().dc_cuda_sync(stream):
+            raise RuntimeError("dc_cuda_sync: " + lib().dc_cuda_last_error().decode())
+    finally:
+        lib().dc_cuda_csr_end(h)
+    return out
 
 
 def build_csr_fast(conn, nbNodes, colBase=0):

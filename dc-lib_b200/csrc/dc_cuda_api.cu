@@ -8,6 +8,7 @@
 #include <string>
 #include "dc_cuda.h"
 #include "dc_device_operator.cuh"
+#include "dc_csr.cuh"
 
 using namespace dcdev;
 
@@ -444,6 +445,120 @@ extern "C" int dc_cuda_debug_phases(dc_cuda_ctx *c, long long *h_out)
     c->d_phaseClock = nullptr;
     return 0;
 }
+
+/* ---- CSR pattern / node -> element lists on the device (csrc/dc_csr.cuh) -------------------- */
+
+struct dc_cuda_csr {
+    const int *d_conn = nullptr;
+    int nbElem = 0, nbNodes = 0;
+    int64_t nnz = 0;
+    int *d_deg = nullptr, *d_cnt = nullptr, *d_n2eVal = nullptr, *d_flag = nullptr;
+    const int *d_row = nullptr;
+    int64_t *d_n2ePtr = nullptr, *d_sums = nullptr;
+};
+
+static void csr_release(dc_cuda_csr *h)
+{
+    if (!h) return;
+    cudaFree(h->d_deg); cudaFree(h->d_cnt); cudaFree(h->d_n2eVal); cudaFree(h->d_n2ePtr); cudaFree(h->d_sums);
+    cudaFree(h->d_flag);
+    delete h;
+}
+
+/* exclusive scan of d_in[n] (int32 counts) into d_out[n+1]; the total stays in d_sums[nbBlocks] */
+template <typename OUT>
+static int scan_counts(const int *d_in, int64_t n, int64_t *d_sums, OUT *d_out, cudaStream_t s)
+{
+    using namespace dcdev;
+    const int64_t nbBlocks = (n + SCAN_TILE - 1) / SCAN_TILE;
+    if (nbBlocks == 0) {
+        CK(cudaMemsetAsync(d_out, 0, sizeof(OUT), s));
+        CK(cudaMemsetAsync(d_sums, 0, sizeof(int64_t), s));
+        return 0;
+    }
+    scan_block_sums<<<(unsigned)nbBlocks, 256, 0, s>>>(d_in, n, d_sums);
+    scan_sums<<<1, 1024, 0, s>>>(d_sums, nbBlocks);
+    scan_apply<OUT><<<(unsigned)nbBlocks, 256, 0, s>>>(d_in, n, d_sums, d_out);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int csr_begin_body(dc_cuda_csr *h, int *d_row, cudaStream_t s)
+{
+    using namespace dcdev;
+    const int nbNodes = h->nbNodes;
+    const int64_t entries = 4 * (int64_t)h->nbElem;
+    const int64_t nbBlocks = ((int64_t)nbNodes + SCAN_TILE - 1) / SCAN_TILE;
+    int rc = 0, bad = 0;
+    CK(cudaMalloc(&h->d_deg, sizeof(int) * (size_t)(nbNodes + 1)));
+    CK(cudaMalloc(&h->d_cnt, sizeof(int) * (size_t)(nbNodes + 1)));
+    CK(cudaMalloc(&h->d_n2ePtr, sizeof(int64_t) * (size_t)(nbNodes + 1)));
+    CK(cudaMalloc(&h->d_n2eVal, sizeof(int) * (size_t)(entries ? entries : 1)));
+    CK(cudaMalloc(&h->d_sums, sizeof(int64_t) * (size_t)(nbBlocks + 1)));
+    CK(cudaMalloc(&h->d_flag, sizeof(int)));
+    CK(cudaMemsetAsync(h->d_deg, 0, sizeof(int) * (size_t)(nbNodes + 1), s));
+    CK(cudaMemsetAsync(h->d_cnt, 0, sizeof(int) * (size_t)(nbNodes + 1), s));
+    CK(cudaMemsetAsync(h->d_flag, 0, sizeof(int), s));
+    if (entries)
+        csr_count_nodes<<<grid_for(entries, 256), 256, 0, s>>>(h->d_conn, entries, nbNodes, h->d_deg, h->d_flag);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(&bad, h->d_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (bad) return fail(-2, "dc_cuda_csr_begin: the connectivity names a node outside [1, nbNodes]");
+    if ((rc = scan_counts<int64_t>(h->d_deg, nbNodes, h->d_sums, h->d_n2ePtr, s))) return rc;
+    /* d_cnt serves as the fill cursor first, then holds the edges per row */
+    if (entries)
+        csr_fill_n2e<<<grid_for(entries, 256), 256, 0, s>>>(h->d_conn, entries, h->d_n2ePtr, h->d_cnt, h->d_n2eVal);
+    if (nbNodes)
+        csr_rows<false><<<grid_for((int64_t)nbNodes * 32, 256), 256, 0, s>>>(h->d_conn, h->d_n2ePtr, h->d_n2eVal, nbNodes,
+                                                                           h->d_cnt, nullptr, nullptr, 0);
+    CK(cudaGetLastError());
+    if ((rc = scan_counts<int>(h->d_cnt, nbNodes, h->d_sums, d_row, s))) return rc;
+    CK(cudaMemcpyAsync(&h->nnz, h->d_sums + nbBlocks, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (h->nnz > INT32_MAX) return fail(-3, "dc_cuda_csr_begin: the pattern exceeds 2^31-1 edges");
+    return 0;
+}
+
+extern "C" int dc_cuda_csr_begin(const int *d_conn, int nbElem, int nbNodes, int *d_row, int64_t *nnz,
+                                 dc_cuda_csr **handle, void *stream)
+{
+    if ((!d_conn && nbElem > 0) || !d_row || !nnz || !handle || nbElem < 0 || nbNodes < 0)
+        return fail(-1, "dc_cuda_csr_begin: bad argument");
+    dc_cuda_csr *h = new dc_cuda_csr;
+    h->d_conn = d_conn; h->nbElem = nbElem; h->nbNodes = nbNodes; h->d_row = d_row;
+    const int rc = csr_begin_body(h, d_row, (cudaStream_t)stream);
+    if (rc) { csr_release(h); return rc; }
+    *nnz = h->nnz;
+    *handle = h;
+    return 0;
+}
+
+extern "C" int dc_cuda_csr_columns(dc_cuda_csr *h, int *d_col, int colBase, void *stream)
+{
+    using namespace dcdev;
+    if (!h || (!d_col && h->nnz)) return fail(-1, "dc_cuda_csr_columns: bad argument");
+    if (h->nbNodes)
+        csr_rows<true><<<grid_for((int64_t)h->nbNodes * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+            h->d_conn, h->d_n2ePtr, h->d_n2eVal, h->nbNodes, nullptr, h->d_row, d_col, colBase);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int dc_cuda_csr_node_to_elem(dc_cuda_csr *h, int64_t *d_ptr, int *d_val, void *stream)
+{
+    using namespace dcdev;
+    if (!h) return fail(-1, "dc_cuda_csr_node_to_elem: bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (d_ptr)
+        CK(cudaMemcpyAsync(d_ptr, h->d_n2ePtr, sizeof(int64_t) * (size_t)(h->nbNodes + 1), cudaMemcpyDeviceToDevice, s));
+    if (d_val && h->nbNodes)
+        csr_sort_n2e<<<grid_for((int64_t)h->nbNodes * 32, 256), 256, 0, s>>>(h->d_n2ePtr, h->nbNodes, h->d_n2eVal, d_val);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" void dc_cuda_csr_end(dc_cuda_csr *h) { csr_release(h); }
 
 extern "C" int dc_cuda_set_option(dc_cuda_ctx *c, const char *name, int value)
 {

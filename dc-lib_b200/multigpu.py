@@ -40,7 +40,7 @@ def plane_edges(node_perm, row, col, n, side):
     return np.ascontiguousarray(idx[keep][np.argsort(key, kind="stable")], dtype=np.int64)
 
 
-def build_slab(n, rank, world, builder="geometric", vec=0, seed=12345):
+def build_slab(n, rank, world, builder="geometric", vec=0, seed=12345, csr_device=None):
     """Appendix-A driver for slab `rank` of a bar of `world` jittered Kuhn cubes stacked along x.
     Returns the user-side arrays, the flattened tree and, per neighbour, the local CSR edges
     shared with it (both nodes on the common plane) in an order both sides agree on."""
@@ -54,7 +54,19 @@ def build_slab(n, rank, world, builder="geometric", vec=0, seed=12345):
     node_perm = get_node_perm(N)
     DC_permute_double_2d_array(coord, N, 3)
     DC_renumber_int_array(conn.reshape(-1), 4 * E)
-    row, col = build_csr_fast(conn, N)
+    import time
+    t_csr = time.time()
+    if csr_device is not None:
+        # CSR pattern on the GPU (dc_cuda_csr_*): connectivity up, row pointers and columns back
+        # (the host needs them for DC_finalize_tree and the schedule builder)
+        import torch
+        from . import build_csr_device
+        d_row, d_col = build_csr_device(torch.from_numpy(conn).to(csr_device), N)
+        row, col = d_row.cpu().numpy(), d_col.cpu().numpy()
+        del d_row, d_col
+    else:
+        row, col = build_csr_fast(conn, N)
+    t_csr = time.time() - t_csr
     DC_finalize_tree(row, conn, E, 4)
     rec = flatten_tree()
 
@@ -65,7 +77,7 @@ def build_slab(n, rank, world, builder="geometric", vec=0, seed=12345):
     gid_of_new = np.empty(N, dtype=np.int64)
     gid_of_new[node_perm] = global_node_ids(n, rank)
     return dict(conn=conn, coord=coord, row=row, col=col, E=E, N=N, nnz=int(row[-1]), rec=rec, n=n,
-                intf=intf, gid_of_new=gid_of_new, node_perm=node_perm, rank=rank, world=world)
+                intf=intf, gid_of_new=gid_of_new, node_perm=node_perm, rank=rank, world=world, csr_s=t_csr)
 
 
 class InterfaceExchange:
@@ -127,7 +139,7 @@ def setup_device_slabs(n, rank, world, device, builder="geometric", vec=0, slots
     tensors, meta = {}, None
     if rank == 0:
         DC_set_num_threads(0)                      # all host cores (torchrun exports OMP_NUM_THREADS=1)
-        slab = build_slab(n, 0, 1, builder=builder, vec=vec, seed=seed)
+        slab = build_slab(n, 0, 1, builder=builder, vec=vec, seed=seed, csr_device=device)
         node_perm = slab["node_perm"]
         t_tree = time.time() - t0
         t1 = time.time()
@@ -147,7 +159,8 @@ def setup_device_slabs(n, rank, world, device, builder="geometric", vec=0, slots
         st = plan.stats()
         meta = dict(shapes={k: (tuple(tensors[k].shape), str(tensors[k].dtype)) for k in names},
                     ints={k: arr[k] for k in ("nbUnits", "maxSlots", "maxHalo", "maxNodes", "maxTasks", "maxItems", "maxTgt", "symmetric")},
-                    E=slab["E"], N=slab["N"], nnz=slab["nnz"], stats=st, tree_s=t_tree, plan_s=t_plan)
+                    E=slab["E"], N=slab["N"], nnz=slab["nnz"], stats=st, tree_s=t_tree, plan_s=t_plan,
+                    csr_s=slab["csr_s"])
         del plan, slab, host, arr
     if world > 1:
         box = [meta]

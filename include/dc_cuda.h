@@ -107,7 +107,22 @@ int  dc_cuda_pack_edges(const double *d_values, const int64_t *d_edge, int64_t n
 int  dc_cuda_unpack_add_edges(double *d_values, const int64_t *d_edge, int64_t nbEdges, int perEdge,
                               const double *d_buf, void *stream);
 
-/* Tuning knobs: "unit_threads" = CTA size of the unit kernel (128, 192 or 256; default 256);
+/* CSR pattern of the renumbered mesh, built on the device.  In the reference this is the user's
+ * step between DC_renumber_int_array and DC_finalize_tree (the library only ships the node ->
+ * element helper DC_create_nodeToElem, src/coloring.cc:79-112); at 10^8 elements the host build
+ * dominates the set-up.  d_conn: [nbElem][4] 1-based.  begin() fills d_row[nbNodes+1] (edge (i,j)
+ * iff an element holds both nodes, diagonal included) and returns nnz; columns() then writes the
+ * nnz column indices, ascending inside a row, shifted by colBase; node_to_elem() copies the
+ * node -> element lists (d_ptr[nbNodes+1], d_val[4*nbElem] ascending per node; either may be NULL).
+ * The arrays equal the host builder's bit for bit.  end() frees the work space. */
+typedef struct dc_cuda_csr dc_cuda_csr;
+int  dc_cuda_csr_begin(const int *d_conn, int nbElem, int nbNodes, int *d_row, int64_t *nnz,
+                       dc_cuda_csr **handle, void *stream);
+int  dc_cuda_csr_columns(dc_cuda_csr *handle, int *d_col, int colBase, void *stream);
+int  dc_cuda_csr_node_to_elem(dc_cuda_csr *handle, int64_t *d_ptr, int *d_val, void *stream);
+void dc_cuda_csr_end(dc_cuda_csr *handle);
+
+/* Tuning knobs: "unit_threads" = CTA size of the unit kernel (128, 192, 256 or 512; default 256);
  * "persistent" = 1 (default): SMs x resident CTAs stride over the units and prefetch the next
  * unit's inputs, 0: one CTA per unit. */
 int  dc_cuda_set_option(dc_cuda_ctx *ctx, const char *name, int value);
