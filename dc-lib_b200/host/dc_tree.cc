@@ -29,9 +29,18 @@ int *elemPerm = nullptr, *nodePerm = nullptr;
 
 namespace dc {
 
+/* The reference fixes the vector length at compile time (-DDC_VEC -DVEC_SIZE=n, one .so per
+ * variant, build/CMakeLists.txt:87-109); here it is a run-time option.  A program that is only
+ * re-linked (no DC_set_vec_size call) selects the variant with the environment instead:
+ * DC_VEC_SIZE=n, DC_MAX_ELEM_PER_PART=m. */
 Options &options()
 {
-    static Options o;
+    static Options o = [] {
+        Options init;
+        if (const char *v = getenv("DC_VEC_SIZE")) init.vecSize = atoi(v) > 0 ? atoi(v) : 0;
+        if (const char *v = getenv("DC_MAX_ELEM_PER_PART")) init.maxElemPerPart = atoi(v) > 0 ? atoi(v) : init.maxElemPerPart;
+        return init;
+    }();
     return o;
 }
 
