@@ -34,7 +34,7 @@ void DC_device_set_mesh (const double *coord, const int *elemToNode, const int *
                          const int *nodeToNodeColumn, int nbElem, int nbNodes, int colBase);
 void DC_device_update_coords (const double *coord);
 void DC_device_set_mode (int mode);
-/* Shared-memory budget of a work unit in touched elements (default 832). */
+/* Shared-memory budget of a work unit in touched elements (default 512). */
 void DC_device_set_unit_slots (int maxSlots);
 /* Reset + assemble into the HOST array nodeToNodeValue[nnz][operatorDim^2]
  * (device assembly followed by one device->host copy). */

@@ -282,3 +282,52 @@ def test_user_defined_non_symmetric_operator(tmp_path):
     ctx2, _ = _ctx(mesh, slots=300, sym=True)
     with pytest.raises(RuntimeError, match="non-symmetric"):
         ctx2.assemble_with(launcher, list(w), dc.MODE_DETERMINISTIC, v)
+
+
+def test_reference_facing_device_entry_points(tmp_path):
+    """DC_device_set_mesh / DC_assembly_device through the Fortran ABI (include/DC_device.h): the call
+    a DC-lib user makes after the switch; values land in the host array, bit-identical to the oracle."""
+    import ctypes
+    from ctypes import byref, c_int
+    mesh = prepare_mesh(MineLib(0), 10, tmp_path)       # the tree stays in the library after store
+    dc.DC_read_tree(mesh["tree_path"], mesh["E"], mesh["N"])
+    L = dc.lib()
+    vp = ctypes.c_void_p
+    for name in ("dc_device_init_", "dc_device_set_mesh_", "dc_assembly_device_", "dc_device_update_coords_",
+                 "dc_device_set_mode_", "dc_device_finalize_"):
+        getattr(L, name).restype = None
+    L.dc_device_init_(byref(c_int(0)))
+    L.dc_device_set_mesh_(vp(mesh["coord"].ctypes.data), vp(mesh["conn"].ctypes.data), vp(mesh["row"].ctypes.data),
+                          vp(mesh["col"].ctypes.data), byref(c_int(mesh["E"])), byref(c_int(mesh["N"])), byref(c_int(0)))
+    prm = np.array([LAMBDA, MU])
+    for op, dim, p, nb in ((dc.OP_LAPLACIAN, 1, None, 0), (dc.OP_ELASTICITY, 3, vp(prm.ctypes.data), 2)):
+        out = np.full(mesh["nnz"] * dim * dim, np.nan)
+        L.dc_assembly_device_(byref(c_int(op)), p, byref(c_int(nb)), vp(out.ctypes.data), byref(c_int(dim)))
+        assert out.tobytes() == oracle_serial(mesh, dim).tobytes()
+    # atomic mode through the same entry point, then new coordinates
+    L.dc_device_set_mode_(byref(c_int(1)))
+    out = np.full(mesh["nnz"], np.nan)
+    L.dc_assembly_device_(byref(c_int(dc.OP_LAPLACIAN)), None, byref(c_int(0)), vp(out.ctypes.data), byref(c_int(1)))
+    assert _rel_err(out, oracle_serial(mesh, 1)) <= REL_TOL
+    L.dc_device_set_mode_(byref(c_int(0)))
+    moved = dict(mesh, coord=np.ascontiguousarray(mesh["coord"] * 1.25))
+    L.dc_device_update_coords_(vp(moved["coord"].ctypes.data))
+    L.dc_assembly_device_(byref(c_int(dc.OP_LAPLACIAN)), None, byref(c_int(0)), vp(out.ctypes.data), byref(c_int(1)))
+    assert out.tobytes() == oracle_serial(moved, 1).tobytes()
+    L.dc_device_finalize_()
+
+
+def test_user_cpp_program_on_the_device_path(tmp_path):
+    """tests/dropin/device_driver.cc: a C++ user program (DC.h + DC_device.h) built with g++ and linked
+    to libdc_b200.so; its own host-callback traversal agrees with DC_assembly_device within 1e-12."""
+    import os
+    import subprocess
+    from common import ROOT
+    exe = os.path.join(str(tmp_path), "device_driver")
+    libdir, libfile = os.path.split(dc.LIB_PATH)
+    subprocess.check_call(["g++", "-std=c++11", "-O1", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "dropin", "device_driver.cc"), "-o", exe, "-L" + libdir,
+                           "-l:" + libfile, "-Wl,-rpath," + libdir, "-fopenmp"])
+    out = subprocess.check_output([exe, "12", os.path.join(str(tmp_path), "dev")]).decode()
+    vals = dict(kv.split("=") for kv in out.split() if "=" in kv)
+    assert float(vals["device_vs_host_rel"]) <= REL_TOL and float(vals["elasticity_rowsum_rel"]) <= REL_TOL
