@@ -146,17 +146,125 @@ __device__ __forceinline__ void flush_stage(double *__restrict__ values, const d
     }
 }
 
-/* The accumulation + output phase of one unit (P2): warps take tasks from a shared counter
- * (tasks are listed longest first); a lane owns one CSR edge and adds its contributions in
- * ascending element order (the order of the item rows). */
+/* One task (P2): a lane owns one CSR edge and adds its contributions in ascending element order
+ * (the order of the item rows); the block -- and, in the symmetric schedule, its transpose --
+ * leaves through the warp's staging area as full-line streaming stores. */
+template <class Op, bool SYM>
+__device__ __forceinline__ void do_task(const dc_unit_t &u, const dc_task_t task, const uint16_t *itemS,
+                                        const int2 *tgtS, const double *recs, double *myStage, int *myTgt,
+                                        const int *__restrict__ diagRel, double *__restrict__ values, int lane)
+{
+    constexpr int DD = UnitSmem<Op>::DD;
+    constexpr int RS = UnitSmem<Op>::RS;
+    const uint16_t *it = itemS + task.itemRel + lane;
+    double acc[DD];
+#pragma unroll
+    for (int c = 0; c < DD; c++) acc[c] = 0.0;
+    if (SYM && task.kind == DC_TASK_OWNDIAG) {
+        /* diagonal edges only: one gradient per contribution, symmetric block.  The loop is
+         * software-pipelined: item two iterations ahead, operands one ahead (indices are
+         * clamped; padding items point at the all-zero record) */
+        const int iters = task.iters;
+        if (iters > 0) {
+            double nxt[Op::NOPS_DIAG], cur[Op::NOPS_DIAG];
+            uint32_t item = it[0];
+            Op::fetch_diag(recs + (item >> 4) * RS, item & 3u, nxt);
+            item = it[(iters > 1 ? 1 : 0) * 32];
+            for (int i = 0; i < iters; i++) {
+#pragma unroll
+                for (int q = 0; q < Op::NOPS_DIAG; q++) cur[q] = nxt[q];
+                Op::fetch_diag(recs + (item >> 4) * RS, item & 3u, nxt);
+                item = it[(i + 2 < iters ? i + 2 : iters - 1) * 32];
+                Op::apply_diag(cur, c_params, acc);
+            }
+        }
+        Op::mirror(acc);
+        const bool valid = (task.mask >> lane) & 1u;
+        int t0 = -1;
+        if (valid) t0 = tgtS[(int)task.first + lane].x;
+        if (DD == 1) {
+            if (valid) st_stream_f64(values + t0, acc[0]);
+        } else {
+#pragma unroll
+            for (int c = 0; c < DD; c++) myStage[lane * DD + c] = acc[c];
+            myTgt[lane] = t0;
+            __syncwarp();
+            flush_stage<DD>(values, myStage, myTgt, lane);
+            __syncwarp();
+        }
+        return;
+    }
+    {
+        const int iters = task.iters;
+        if (iters > 0) {
+            double nxt[Op::NOPS], cur[Op::NOPS];
+            uint32_t item = it[0];
+            Op::fetch(recs + (item >> 4) * RS, item & 15u, nxt);
+            item = it[(iters > 1 ? 1 : 0) * 32];
+            for (int i = 0; i < iters; i++) {
+#pragma unroll
+                for (int q = 0; q < Op::NOPS; q++) cur[q] = nxt[q];
+                Op::fetch(recs + (item >> 4) * RS, item & 15u, nxt);
+                item = it[(i + 2 < iters ? i + 2 : iters - 1) * 32];
+                Op::apply(cur, c_params, acc);
+            }
+        }
+    }
+    if (task.kind == DC_TASK_DIAG) {
+        if ((task.mask >> lane) & 1u) {
+            const int d = __ldg(diagRel + u.nodeFirst + (int)task.first + lane);
+#pragma unroll
+            for (int c = 0; c < DD; c++) st_stream_f64(values + (u.edgeFirst + d) * DD + c, acc[c]);
+        }
+    } else if (SYM) {
+        /* owned edge: block to (row,col); upper edges also store the transpose at (col,row) */
+        const bool valid = (task.mask >> lane) & 1u;
+        int2 tg = make_int2(-1, -1);
+        if (valid) tg = tgtS[(int)task.first + lane];
+        if (DD == 1) {
+            if (valid) {
+                st_stream_f64(values + tg.x, acc[0]);
+                if (tg.y >= 0) st_stream_f64(values + tg.y, acc[0]);
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < DD; c++) myStage[lane * DD + c] = acc[c];
+            myTgt[lane] = tg.x;
+            __syncwarp();
+            flush_stage<DD>(values, myStage, myTgt, lane);
+            __syncwarp();
+#pragma unroll
+            for (int c = 0; c < DD; c++) myStage[lane * DD + (c % Op::D) * Op::D + c / Op::D] = acc[c];
+            myTgt[lane] = tg.y;
+            __syncwarp();
+            flush_stage<DD>(values, myStage, myTgt, lane);
+            __syncwarp();
+        }
+    } else {
+        /* 32 consecutive edges of the unit's own interval (diagonal lanes skipped) */
+        const int e = (int)task.first + lane;
+        const bool valid = e < u.edgeCount && !((task.mask >> lane) & 1u);
+        if (DD == 1) {
+            if (valid) st_stream_f64(values + u.edgeFirst + e, acc[0]);
+        } else {
+#pragma unroll
+            for (int c = 0; c < DD; c++) myStage[lane * DD + c] = acc[c];
+            myTgt[lane] = valid ? (int)(u.edgeFirst + e) : -1;
+            __syncwarp();
+            flush_stage<DD>(values, myStage, myTgt, lane);
+            __syncwarp();
+        }
+    }
+}
+
+/* The accumulation + output phase of one unit: warps take tasks from a shared counter (tasks are
+ * listed longest first). */
 template <class Op, int NW, bool SYM, class AfterFirst>
 __device__ __forceinline__ void run_tasks(const dc_unit_t &u, const dc_task_t *taskS, const uint16_t *itemS,
                                           const int2 *tgtS, const double *recs, int *nextTask, double *myStage,
                                           int *myTgt, const int *__restrict__ diagRel, double *__restrict__ values,
                                           int warp, int lane, AfterFirst afterFirst)
 {
-    constexpr int DD = UnitSmem<Op>::DD;
-    constexpr int RS = UnitSmem<Op>::RS;
     bool first = true;
     for (int t = warp; t < u.taskCount;) {
         if (!first) afterFirst();          /* runs once, between the warp's first and second task */
@@ -167,105 +275,7 @@ __device__ __forceinline__ void run_tasks(const dc_unit_t &u, const dc_task_t *t
             if (lane == 0) nxt = atomicAdd(nextTask, 1);
             t = __shfl_sync(0xffffffffu, nxt, 0);
         }
-        const uint16_t *it = itemS + task.itemRel + lane;
-        double acc[DD];
-#pragma unroll
-        for (int c = 0; c < DD; c++) acc[c] = 0.0;
-        if (SYM && task.kind == DC_TASK_OWNDIAG) {
-            /* diagonal edges only: one gradient per contribution, symmetric block.  The loop is
-             * software-pipelined: item two iterations ahead, operands one ahead (indices are
-             * clamped; padding items point at the all-zero record) */
-            const int iters = task.iters;
-            if (iters > 0) {
-                double nxt[Op::NOPS_DIAG], cur[Op::NOPS_DIAG];
-                uint32_t item = it[0];
-                Op::fetch_diag(recs + (item >> 4) * RS, item & 3u, nxt);
-                item = it[(iters > 1 ? 1 : 0) * 32];
-                for (int i = 0; i < iters; i++) {
-#pragma unroll
-                    for (int q = 0; q < Op::NOPS_DIAG; q++) cur[q] = nxt[q];
-                    Op::fetch_diag(recs + (item >> 4) * RS, item & 3u, nxt);
-                    item = it[(i + 2 < iters ? i + 2 : iters - 1) * 32];
-                    Op::apply_diag(cur, c_params, acc);
-                }
-            }
-            Op::mirror(acc);
-            const bool valid = (task.mask >> lane) & 1u;
-            int t0 = -1;
-            if (valid) t0 = tgtS[(int)task.first + lane].x;
-            if (DD == 1) {
-                if (valid) st_stream_f64(values + t0, acc[0]);
-            } else {
-#pragma unroll
-                for (int c = 0; c < DD; c++) myStage[lane * DD + c] = acc[c];
-                myTgt[lane] = t0;
-                __syncwarp();
-                flush_stage<DD>(values, myStage, myTgt, lane);
-                __syncwarp();
-            }
-            continue;
-        }
-        {
-            const int iters = task.iters;
-            if (iters > 0) {
-                double nxt[Op::NOPS], cur[Op::NOPS];
-                uint32_t item = it[0];
-                Op::fetch(recs + (item >> 4) * RS, item & 15u, nxt);
-                item = it[(iters > 1 ? 1 : 0) * 32];
-                for (int i = 0; i < iters; i++) {
-#pragma unroll
-                    for (int q = 0; q < Op::NOPS; q++) cur[q] = nxt[q];
-                    Op::fetch(recs + (item >> 4) * RS, item & 15u, nxt);
-                    item = it[(i + 2 < iters ? i + 2 : iters - 1) * 32];
-                    Op::apply(cur, c_params, acc);
-                }
-            }
-        }
-        if (task.kind == DC_TASK_DIAG) {
-            if ((task.mask >> lane) & 1u) {
-                const int d = __ldg(diagRel + u.nodeFirst + (int)task.first + lane);
-#pragma unroll
-                for (int c = 0; c < DD; c++) st_stream_f64(values + (u.edgeFirst + d) * DD + c, acc[c]);
-            }
-        } else if (SYM) {
-            /* owned edge: block to (row,col); upper edges also store the transpose at (col,row) */
-            const bool valid = (task.mask >> lane) & 1u;
-            int2 tg = make_int2(-1, -1);
-            if (valid) tg = tgtS[(int)task.first + lane];
-            if (DD == 1) {
-                if (valid) {
-                    st_stream_f64(values + tg.x, acc[0]);
-                    if (tg.y >= 0) st_stream_f64(values + tg.y, acc[0]);
-                }
-            } else {
-#pragma unroll
-                for (int c = 0; c < DD; c++) myStage[lane * DD + c] = acc[c];
-                myTgt[lane] = tg.x;
-                __syncwarp();
-                flush_stage<DD>(values, myStage, myTgt, lane);
-                __syncwarp();
-#pragma unroll
-                for (int c = 0; c < DD; c++) myStage[lane * DD + (c % Op::D) * Op::D + c / Op::D] = acc[c];
-                myTgt[lane] = tg.y;
-                __syncwarp();
-                flush_stage<DD>(values, myStage, myTgt, lane);
-                __syncwarp();
-            }
-        } else {
-            /* 32 consecutive edges of the unit's own interval (diagonal lanes skipped) */
-            const int e = (int)task.first + lane;
-            const bool valid = e < u.edgeCount && !((task.mask >> lane) & 1u);
-            if (DD == 1) {
-                if (valid) st_stream_f64(values + u.edgeFirst + e, acc[0]);
-            } else {
-#pragma unroll
-                for (int c = 0; c < DD; c++) myStage[lane * DD + c] = acc[c];
-                myTgt[lane] = valid ? (int)(u.edgeFirst + e) : -1;
-                __syncwarp();
-                flush_stage<DD>(values, myStage, myTgt, lane);
-                __syncwarp();
-            }
-        }
+        do_task<Op, SYM>(u, task, itemS, tgtS, recs, myStage, myTgt, diagRel, values, lane);
     }
 }
 

@@ -176,6 +176,39 @@ struct Selector {
         flush();
     }
 
+    /* Units of a fixed number of consecutive rows (cut short where the slot budget would be
+     * exceeded).  With 32 rows a unit has exactly one full diagonal task and about seven
+     * upper-edge tasks: one task per warp of a 256-thread CTA. */
+    void window_rows(int first, int last, int width)
+    {
+        const int tid = omp_get_thread_num();
+        std::vector<int> acc, trial;
+        int start = first;
+        while (start < last) {
+            int stop = start;
+            acc.clear();
+            while (stop < last && stop - start < width) {
+                trial.assign(acc.begin(), acc.end());
+                for (int64_t k = m.n2ePtr[stop]; k < m.n2ePtr[(size_t)stop + 1]; k++)
+                    trial.push_back(m.n2eVal[(size_t)k]);
+                std::sort(trial.begin(), trial.end());
+                trial.erase(std::unique(trial.begin(), trial.end()), trial.end());
+                if ((int)trial.size() > maxSlots) break;
+                acc.swap(trial);
+                stop++;
+            }
+            if (stop == start) {
+                bigT[tid].push_back(start);
+                start++;
+                continue;
+            }
+            UnitSeed s{start, stop - start, 0, 0, {}};
+            s.halo = acc;
+            seedsT[tid].push_back(std::move(s));
+            start = stop;
+        }
+    }
+
     /* take the subtree as one unit if it fits the slot budget, else descend */
     void select(int64_t idx)
     {
@@ -707,7 +740,14 @@ extern "C" int dc_plan_build(dc_plan_t *plan, const int *conn, int nbElem, int n
     if (treeRec && nbTreeRec > 0) {
         int64_t cursor = 0;
         index_tree(treeRec, nbTreeRec, cursor, sel.tree, true);
-        if (getenv("DC_PLAN_SUBTREE_UNITS")) {
+        const char *win = getenv("DC_PLAN_UNIT_NODES");
+        if (win && atoi(win) > 0) {
+            const int width = atoi(win);
+            const int chunk = width * 64;
+            #pragma omp parallel for schedule(dynamic, 1) num_threads(nt)
+            for (int c = 0; c < (nbNodes + chunk - 1) / chunk; c++)
+                sel.window_rows(c * chunk, std::min(nbNodes, (c + 1) * chunk), width);
+        } else if (getenv("DC_PLAN_SUBTREE_UNITS")) {
             #pragma omp parallel num_threads(nt)
             #pragma omp single
             sel.select(0);
