@@ -87,6 +87,13 @@ inline int launch_units(dc_launch_args *a, double *d_values, cudaStream_t s)
         const int64_t resident = (int64_t)perSm * a->smCount;
         if (resident < grid) grid = resident;
     }
+#ifdef DC_KO
+    {
+        const char *ko = getenv("DC_KO");
+        const int bits = ko ? atoi(ko) : 0;
+        cudaMemcpyToSymbolAsync(c_ko, &bits, sizeof(int), 0, cudaMemcpyHostToDevice, s);
+    }
+#endif
     kern<<<(unsigned)grid, THREADS, (size_t)L.total, s>>>(a->d_units, (int)a->nbUnits, a->d_tasks, a->d_items,
                                                            a->d_slotNodes, a->d_haloNodes, a->d_diagRel,
                                                            reinterpret_cast<const int2 *>(a->d_tgt), a->d_coord,

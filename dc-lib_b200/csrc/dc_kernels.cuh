@@ -70,6 +70,17 @@ __device__ __forceinline__ void st_stream_f64(double *addr, double v)
 #define DC_MAX_PARAMS 8
 __constant__ double c_params[DC_MAX_PARAMS];
 
+/* experiment builds only (make variant DEFS=-DDC_KO): knock-out bits from the environment variable
+ * DC_KO switch phases of the unit kernel off (wrong results) to measure what each one costs:
+ * 1 transposed stores, 2 direct stores, 4 diagonal tasks, 8 record build, 16 accumulation loops,
+ * 32 upper-edge tasks */
+#ifdef DC_KO
+__constant__ int c_ko;
+#define DC_KO_ON(bit) (c_ko & (bit))
+#else
+#define DC_KO_ON(bit) false
+#endif
+
 template <class Op>
 __device__ __forceinline__ void load_element(const int *__restrict__ conn, const double *__restrict__ coord,
                                              int64_t e, double *rec)
@@ -164,7 +175,8 @@ __device__ __forceinline__ void do_task(const dc_unit_t &u, const dc_task_t task
         /* diagonal edges only: one gradient per contribution, symmetric block.  The loop is
          * software-pipelined: item two iterations ahead, operands one ahead (indices are
          * clamped; padding items point at the all-zero record) */
-        const int iters = task.iters;
+        if (DC_KO_ON(4)) return;
+        const int iters = DC_KO_ON(16) ? 0 : task.iters;
         if (iters > 0) {
             double nxt[Op::NOPS_DIAG], cur[Op::NOPS_DIAG];
             uint32_t item = it[0];
@@ -182,6 +194,7 @@ __device__ __forceinline__ void do_task(const dc_unit_t &u, const dc_task_t task
         const bool valid = (task.mask >> lane) & 1u;
         int t0 = -1;
         if (valid) t0 = tgtS[(int)task.first + lane].x;
+        if (DC_KO_ON(2)) t0 = -1;
         if (DD == 1) {
             if (valid) st_stream_f64(values + t0, acc[0]);
         } else {
@@ -194,8 +207,9 @@ __device__ __forceinline__ void do_task(const dc_unit_t &u, const dc_task_t task
         }
         return;
     }
+    if (SYM && DC_KO_ON(32)) return;
     {
-        const int iters = task.iters;
+        const int iters = DC_KO_ON(16) ? 0 : task.iters;
         if (iters > 0) {
             double nxt[Op::NOPS], cur[Op::NOPS];
             uint32_t item = it[0];
@@ -221,6 +235,8 @@ __device__ __forceinline__ void do_task(const dc_unit_t &u, const dc_task_t task
         const bool valid = (task.mask >> lane) & 1u;
         int2 tg = make_int2(-1, -1);
         if (valid) tg = tgtS[(int)task.first + lane];
+        if (DC_KO_ON(2)) tg.x = -1;
+        if (DC_KO_ON(1)) tg.y = -1;
         if (DD == 1) {
             if (valid) {
                 st_stream_f64(values + tg.x, acc[0]);
@@ -231,13 +247,13 @@ __device__ __forceinline__ void do_task(const dc_unit_t &u, const dc_task_t task
             for (int c = 0; c < DD; c++) myStage[lane * DD + c] = acc[c];
             myTgt[lane] = tg.x;
             __syncwarp();
-            flush_stage<DD>(values, myStage, myTgt, lane);
+            if (!DC_KO_ON(2)) flush_stage<DD>(values, myStage, myTgt, lane);
             __syncwarp();
 #pragma unroll
             for (int c = 0; c < DD; c++) myStage[lane * DD + (c % Op::D) * Op::D + c / Op::D] = acc[c];
             myTgt[lane] = tg.y;
             __syncwarp();
-            flush_stage<DD>(values, myStage, myTgt, lane);
+            if (!DC_KO_ON(1)) flush_stage<DD>(values, myStage, myTgt, lane);
             __syncwarp();
         }
     } else {
@@ -259,16 +275,13 @@ __device__ __forceinline__ void do_task(const dc_unit_t &u, const dc_task_t task
 
 /* The accumulation + output phase of one unit: warps take tasks from a shared counter (tasks are
  * listed longest first). */
-template <class Op, int NW, bool SYM, class AfterFirst>
+template <class Op, int NW, bool SYM>
 __device__ __forceinline__ void run_tasks(const dc_unit_t &u, const dc_task_t *taskS, const uint16_t *itemS,
                                           const int2 *tgtS, const double *recs, int *nextTask, double *myStage,
                                           int *myTgt, const int *__restrict__ diagRel, double *__restrict__ values,
-                                          int warp, int lane, AfterFirst afterFirst)
+                                          int warp, int lane)
 {
-    bool first = true;
     for (int t = warp; t < u.taskCount;) {
-        if (!first) afterFirst();          /* runs once, between the warp's first and second task */
-        first = false;
         const dc_task_t task = taskS[t];
         {
             int nxt = 0;
@@ -287,7 +300,10 @@ __device__ __forceinline__ void run_tasks(const dc_unit_t &u, const dc_task_t *t
  *   records(u) | sync A | TMA mesh(u+1) ... accumulate + store(u), then halo gather(u+1) | sync B | TMA sched(u+1)
  *
  * The node-table region is dead after the records are built and the schedule region after
- * the accumulation, so nothing is double-buffered. */
+ * the accumulation, so nothing is double-buffered.  The warp that starts with the longest task
+ * (warp 0: tasks are listed longest first) is the critical path of a unit, so the bulk copies are
+ * issued by the last warp, and the halo coordinates are gathered by whichever warps run out of
+ * tasks first (chunks of 32 nodes from a shared counter). */
 template <class Op, int THREADS, int MINB, bool SYM>
 __global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *__restrict__ units, int nbUnits,
                                                               const dc_task_t *__restrict__ tasks,
@@ -309,6 +325,8 @@ __global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *_
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);   /* [0] mesh data, [1] schedule, [2] next descriptor */
     int *nextTask = reinterpret_cast<int *>(smem_raw + 24);           /* dynamic task counter */
+    int *nextHalo = reinterpret_cast<int *>(smem_raw + 28);           /* halo nodes of the next unit handed out so far */
+    constexpr int ISSUER = (NW - 1) * 32;                             /* thread that issues the bulk copies */
     dc_unit_t *descS = reinterpret_cast<dc_unit_t *>(smem_raw + 32);  /* descriptors of this and the next unit */
     uint2 *slotN = reinterpret_cast<uint2 *>(smem_raw + L.offSlotN);
     int *hnodeS = reinterpret_cast<int *>(smem_raw + L.offHnode);
@@ -361,6 +379,7 @@ __global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *_
         mbar_init(&bar[1], 1);
         mbar_init(&bar[2], 1);
         *nextTask = NW;
+        *nextHalo = 0;
         descS[0] = units[unit];
     }
     __syncthreads();
@@ -391,7 +410,7 @@ __global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *_
          * all-zero record: padding items point at it and add exact zeros, so the accumulation
          * loops need no test and can be software-pipelined */
         if (tid < RS) recs[nSlots * RS + tid] = 0.0;
-        for (int s0 = tid; s0 < nSlots; s0 += 2 * THREADS) {
+        for (int s0 = tid; s0 < (DC_KO_ON(8) ? 0 : nSlots); s0 += 2 * THREADS) {
             /* two elements per thread in flight: the dependent chain of one setup (cross products,
              * reciprocal, square root) overlaps the other's */
             const int s1 = s0 + THREADS;
@@ -420,53 +439,38 @@ __global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *_
         mbar_wait(&bar[1], k & 1);   /* this unit's schedule (every thread passes before the phase is re-armed) */
         __syncthreads();   /* A: records complete; node tables and coordinates are dead */
         DC_STAMP(unit, 2);
-        if (tid == 0 && hasNext) {
+        if (tid == ISSUER && hasNext) {
             mbar_wait(&bar[2], k & 1);
             issue_mesh(descS[(k + 1) & 1]);            /* lands while this unit accumulates */
+            if (L.schedStride) issue_sched(descS[(k + 1) & 1], k + 1);   /* into the other buffer */
         }
-        if (tid == 0 && hasNext && L.schedStride) issue_sched(descS[(k + 1) & 1], k + 1);   /* into the other buffer */
         DC_STAMP(unit, 3);
 
-        /* halo coordinates of the next unit: every thread loads its nodes into registers between
-         * the warp's first and second task (the bulk copy of the node ids has landed by then) and
-         * stores them after its last task, so the gather latency hides behind the accumulation */
-        constexpr int HN = (THREADS >= 256) ? 1 : 2;   /* halo nodes per thread kept in registers */
-        double hx[HN][3];
-        bool loaded = false;
-        auto load_halo = [&]() {
-            if (!hasNext || loaded) return;
-            loaded = true;
-            mbar_wait(&bar[0], (k + 1) & 1);
-            const int cnt = descS[(k + 1) & 1].hnodeCount;
-#pragma unroll
-            for (int j = 0; j < HN; j++) {
-                const int i = tid + j * THREADS;
-                if (i < cnt) {
-                    const double *src = coord + (int64_t)hnodeS[i] * 3;
-                    hx[j][0] = __ldg(src);
-                    hx[j][1] = __ldg(src + 1);
-                    hx[j][2] = __ldg(src + 2);
-                }
-            }
-        };
-        run_tasks<Op, NW, SYM>(u, taskS, itemS, tgtS, recs, nextTask, myStage, myTgt, diagRel, values, warp, lane,
-                               load_halo);
+        run_tasks<Op, NW, SYM>(u, taskS, itemS, tgtS, recs, nextTask, myStage, myTgt, diagRel, values, warp, lane);
         DC_STAMP(unit, 4);
+        /* halo coordinates of the next unit: one gather per node, done by the warps that have run
+         * out of tasks (the node ids have landed long before); every thread observes the bulk
+         * copies of the next unit's node tables here */
         if (hasNext) {
-            load_halo();                            /* warps with fewer than two tasks */
+            mbar_wait(&bar[0], (k + 1) & 1);
             const dc_unit_t &nx = descS[(k + 1) & 1];
             const int ownSpan = ((nx.nodeFirst + nx.nodeCount + 1) & ~1) - (nx.nodeFirst & ~1);
-#pragma unroll
-            for (int j = 0; j < HN; j++) {
-                const int i = tid + j * THREADS;
-                if (i < nx.hnodeCount) {
+            const int cnt = nx.hnodeCount;
+            for (;;) {
+                int c = 0;
+                if (lane == 0) c = atomicAdd(nextHalo, 32);
+                c = __shfl_sync(0xffffffffu, c, 0);
+                if (c >= cnt) break;
+                const int i = c + lane;
+                if (i < cnt) {
+                    const double *src = coord + (int64_t)hnodeS[i] * 3;
+                    const double x0 = __ldg(src), x1 = __ldg(src + 1), x2 = __ldg(src + 2);
                     double *dst = coordS + (ownSpan + i) * 3;
-                    dst[0] = hx[j][0];
-                    dst[1] = hx[j][1];
-                    dst[2] = hx[j][2];
+                    dst[0] = x0;
+                    dst[1] = x1;
+                    dst[2] = x2;
                 }
             }
-            gather_halo(nx, tid + HN * THREADS, THREADS);      /* the rare unit with more halo nodes */
         }
         DC_STAMP(unit, 5);
         __syncthreads();   /* B: accumulation finished everywhere; schedule region is dead */
@@ -474,6 +478,7 @@ __global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *_
         if (!hasNext) break;
         if (tid == 0) {
             *nextTask = NW;
+            *nextHalo = 0;
             if (!L.schedStride) issue_sched(descS[(k + 1) & 1], k + 1);
         }
         unit = next;
