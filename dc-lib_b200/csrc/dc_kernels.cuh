@@ -117,8 +117,8 @@ struct UnitSmem {
     /* record stride in doubles: an odd number of 8-byte words keeps 64-bit accesses of
      * different slots spread over the banks */
     static constexpr int RS = (Op::NS % 2 == 0) ? Op::NS + 1 : Op::NS;
-    /* per-warp staging: 32 blocks + 32 target edges */
-    static constexpr int STAGE = 32 * DD * 8 + 32 * 4;
+    /* per-warp staging: 32 blocks */
+    static constexpr int STAGE = 32 * DD * 8;
     static UnitLayout layout(int maxSlots, int maxHalo, int maxNodes, int maxTasks, int maxItems, int maxTgt,
                              int threads, bool doubleSched = false)
     {
@@ -143,16 +143,18 @@ struct UnitSmem {
 };
 
 /* store the 32 staged blocks of a warp: idx runs over the 32*DD doubles so that consecutive
- * lanes write consecutive addresses inside a block (and across blocks of consecutive edges) */
+ * lanes write consecutive addresses inside a block (and across blocks of consecutive edges).
+ * myTarget = the edge this lane's block goes to (-1: none); the target of the block a lane
+ * stores a piece of comes from its owner by shuffle, not through shared memory. */
 template <int DD>
-__device__ __forceinline__ void flush_stage(double *__restrict__ values, const double *stage, const int *tgt,
+__device__ __forceinline__ void flush_stage(double *__restrict__ values, const double *stage, int myTarget,
                                             int lane)
 {
 #pragma unroll
     for (int r = 0; r < DD; r++) {
         const int idx = r * 32 + lane;
         const int ent = idx / DD;
-        const int t = tgt[ent];
+        const int t = __shfl_sync(0xffffffffu, myTarget, ent);
         if (t >= 0) st_stream_f64(values + (int64_t)t * DD + (idx - ent * DD), stage[idx]);
     }
 }
@@ -162,7 +164,7 @@ __device__ __forceinline__ void flush_stage(double *__restrict__ values, const d
  * leaves through the warp's staging area as full-line streaming stores. */
 template <class Op, bool SYM>
 __device__ __forceinline__ void do_task(const dc_unit_t &u, const dc_task_t task, const uint16_t *itemS,
-                                        const int2 *tgtS, const double *recs, double *myStage, int *myTgt,
+                                        const int2 *tgtS, const double *recs, double *myStage,
                                         const int *__restrict__ diagRel, double *__restrict__ values, int lane)
 {
     constexpr int DD = UnitSmem<Op>::DD;
@@ -200,9 +202,8 @@ __device__ __forceinline__ void do_task(const dc_unit_t &u, const dc_task_t task
         } else {
 #pragma unroll
             for (int c = 0; c < DD; c++) myStage[lane * DD + c] = acc[c];
-            myTgt[lane] = t0;
             __syncwarp();
-            flush_stage<DD>(values, myStage, myTgt, lane);
+            flush_stage<DD>(values, myStage, t0, lane);
             __syncwarp();
         }
         return;
@@ -245,15 +246,13 @@ __device__ __forceinline__ void do_task(const dc_unit_t &u, const dc_task_t task
         } else {
 #pragma unroll
             for (int c = 0; c < DD; c++) myStage[lane * DD + c] = acc[c];
-            myTgt[lane] = tg.x;
             __syncwarp();
-            if (!DC_KO_ON(2)) flush_stage<DD>(values, myStage, myTgt, lane);
+            if (!DC_KO_ON(2)) flush_stage<DD>(values, myStage, tg.x, lane);
             __syncwarp();
 #pragma unroll
             for (int c = 0; c < DD; c++) myStage[lane * DD + (c % Op::D) * Op::D + c / Op::D] = acc[c];
-            myTgt[lane] = tg.y;
             __syncwarp();
-            if (!DC_KO_ON(1)) flush_stage<DD>(values, myStage, myTgt, lane);
+            if (!DC_KO_ON(1)) flush_stage<DD>(values, myStage, tg.y, lane);
             __syncwarp();
         }
     } else {
@@ -265,9 +264,8 @@ __device__ __forceinline__ void do_task(const dc_unit_t &u, const dc_task_t task
         } else {
 #pragma unroll
             for (int c = 0; c < DD; c++) myStage[lane * DD + c] = acc[c];
-            myTgt[lane] = valid ? (int)(u.edgeFirst + e) : -1;
             __syncwarp();
-            flush_stage<DD>(values, myStage, myTgt, lane);
+            flush_stage<DD>(values, myStage, valid ? (int)(u.edgeFirst + e) : -1, lane);
             __syncwarp();
         }
     }
@@ -278,7 +276,7 @@ __device__ __forceinline__ void do_task(const dc_unit_t &u, const dc_task_t task
 template <class Op, int NW, bool SYM>
 __device__ __forceinline__ void run_tasks(const dc_unit_t &u, const dc_task_t *taskS, const uint16_t *itemS,
                                           const int2 *tgtS, const double *recs, int *nextTask, double *myStage,
-                                          int *myTgt, const int *__restrict__ diagRel, double *__restrict__ values,
+                                          const int *__restrict__ diagRel, double *__restrict__ values,
                                           int warp, int lane)
 {
     for (int t = warp; t < u.taskCount;) {
@@ -288,7 +286,7 @@ __device__ __forceinline__ void run_tasks(const dc_unit_t &u, const dc_task_t *t
             if (lane == 0) nxt = atomicAdd(nextTask, 1);
             t = __shfl_sync(0xffffffffu, nxt, 0);
         }
-        do_task<Op, SYM>(u, task, itemS, tgtS, recs, myStage, myTgt, diagRel, values, lane);
+        do_task<Op, SYM>(u, task, itemS, tgtS, recs, myStage, diagRel, values, lane);
     }
 }
 
@@ -334,7 +332,6 @@ __global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *_
     double *recs = reinterpret_cast<double *>(smem_raw + L.offRecs);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double *myStage = reinterpret_cast<double *>(smem_raw + L.offStage + warp * UnitSmem<Op>::STAGE);
-    int *myTgt = reinterpret_cast<int *>(myStage + 32 * DD);
 
     /* bulk copies of a unit's inputs (thread 0).  The node table starts at the even node at or
      * below nodeFirst and spans an even number of nodes: 48-byte granules. */
@@ -446,7 +443,7 @@ __global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *_
         }
         DC_STAMP(unit, 3);
 
-        run_tasks<Op, NW, SYM>(u, taskS, itemS, tgtS, recs, nextTask, myStage, myTgt, diagRel, values, warp, lane);
+        run_tasks<Op, NW, SYM>(u, taskS, itemS, tgtS, recs, nextTask, myStage, diagRel, values, warp, lane);
         DC_STAMP(unit, 4);
         /* halo coordinates of the next unit: one gather per node, done by the warps that have run
          * out of tasks (the node ids have landed long before); every thread observes the bulk

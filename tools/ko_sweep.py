@@ -24,7 +24,7 @@ for w in windows:
     t0 = time.time()
     ctx, info = multigpu.setup_device_slabs(n, 0, 1, "cuda:0", builder="geometric", vec=0, slots=slots, dist=None)
     ctx.set_option("unit_threads", 256)
-    ctx.set_option("persistent", 1)
+    ctx.set_option("persistent", int(os.environ.get("DC_SWEEP_PERSISTENT", "1")))
     E, nnz, st = info["E"], info["nnz"], info["stats"]
     print(f"window={w or 'subtree'} n={n} E={E} units={st['units']} setups/elem={st['slots_total']/E:.3f} "
           f"item_eff={st['items_useful']/max(st['items'],1):.3f} setup {time.time()-t0:.1f}s", flush=True)
