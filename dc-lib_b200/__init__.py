@@ -130,6 +130,7 @@ def _declare(L):
     L.dc_get_time_.restype = c_double
     L.dc_create_tree_.argtypes = [vp, ip, ip, ip]
     L.dc_create_tree_geometric_.argtypes = [vp, ip, ip, ip, vp, ip]
+    L.dc_partition_mesh_.argtypes = [vp, ip, ip, ip, ip, vp, ip, vp]
     L.dc_finalize_tree_.argtypes = [vp, vp, vp, vp, vp, vp, ip, ip, ip, ip, ip]
     L.dc_store_tree_.argtypes = [c_char_p, ip, ip, ip, ip]
     L.dc_read_tree_.argtypes = [c_char_p, ip, ip, ip, ip]
@@ -190,6 +191,20 @@ def DC_create_tree_geometric(elemToNode, nbElem, dimElem, nbNodes, coord):
     assert elemToNode.dtype == np.int32 and elemToNode.flags.c_contiguous
     assert coord.dtype == np.float64 and coord.flags.c_contiguous
     lib().dc_create_tree_geometric_(_p(elemToNode), _i(nbElem), _i(dimElem), _i(nbNodes), _p(coord), _i(coord.shape[1]))
+
+
+def DC_partition_mesh(elemToNode, nbNodes, nbPart, coord=None):
+    """Element partition for nbPart devices: METIS on the nodal graph (coord None) or coordinate
+    bisection of the nodes; an element follows the majority of its nodes.  Returns int32[nbElem]."""
+    assert elemToNode.dtype == np.int32 and elemToNode.flags.c_contiguous
+    nbElem, dimElem = elemToNode.shape
+    part = np.zeros(nbElem, dtype=np.int32)
+    if coord is not None:
+        assert coord.dtype == np.float64 and coord.flags.c_contiguous
+    lib().dc_partition_mesh_(_p(elemToNode), _i(nbElem), _i(dimElem), _i(nbNodes), _i(nbPart),
+                             _p(coord) if coord is not None else None, _i(coord.shape[1] if coord is not None else 3),
+                             _p(part))
+    return part
 
 
 def DC_finalize_tree(nodeToNodeRow, elemToNode, nbElem, dimElem):

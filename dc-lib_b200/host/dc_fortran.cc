@@ -75,6 +75,12 @@ void dc_create_tree_geometric_ (int *elemToNode, int *nbElem, int *dimElem, int 
     DC_create_tree_geometric(elemToNode, *nbElem, *dimElem, *nbNodes, coord, *dimNode);
 }
 
+void dc_partition_mesh_ (int *elemToNode, int *nbElem, int *dimElem, int *nbNodes, int *nbPart, double *coord,
+                         int *dimNode, int *elemPart)
+{
+    DC_partition_mesh(elemToNode, *nbElem, *dimElem, *nbNodes, *nbPart, coord, *dimNode, elemPart);
+}
+
 void dc_set_vec_size_ (int *vecSize) { DC_set_vec_size(*vecSize); }
 void dc_set_max_elem_per_part_ (int *maxElem) { DC_set_max_elem_per_part(*maxElem); }
 void dc_set_num_threads_ (int *nbThreads) { DC_set_num_threads(*nbThreads); }

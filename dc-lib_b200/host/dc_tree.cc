@@ -443,6 +443,44 @@ void DC_finalize_tree (int *nodeToNodeRow, int *elemToNode, int nbNodes)
     DC_finalize_tree(nodeToNodeRow, elemToNode, nullptr, nullptr, nullptr, nullptr, 0, 0, 1, 0, 0);
 }
 
+/* Element partition of a mesh for nbPart devices: the NODES are cut into nbPart parts -- METIS
+ * recursive bisection of the nodal graph, exactly as DC_create_tree cuts them (reference:
+ * partitioning.cc:167-228), or recursive coordinate bisection when coord is given -- and an element
+ * goes to the part that holds most of its nodes (ties: the smallest part).  elemToNode is 1-based
+ * and is not modified. */
+void DC_partition_mesh (const int *elemToNode, int nbElem, int dimElem, int nbNodes, int nbPart,
+                        const double *coord, int dimNode, int *elemPart)
+{
+    if (nbPart < 1) dc::fatal("Error: DC_partition_mesh needs at least one part.");
+    std::vector<int> nodePart((size_t)(nbNodes > 0 ? nbNodes : 1), 0);
+    if (nbPart > 1 && coord) {
+        std::vector<int> idx((size_t)nbNodes);
+        for (int i = 0; i < nbNodes; i++) idx[(size_t)i] = i;
+        dc::Rcb rcb{coord, dimNode, nullptr, nodePart.data()};
+        #pragma omp parallel
+        #pragma omp single
+        rcb.split(idx.data(), nbNodes, 0, nbPart - 1);
+    } else if (nbPart > 1) {
+        std::vector<int> conn0((size_t)nbElem * dimElem);
+        for (int64_t k = 0; k < (int64_t)nbElem * dimElem; k++) conn0[(size_t)k] = elemToNode[k] - 1;
+        std::vector<int64_t> xadj, adjncy;
+        dc::build_nodal_graph(xadj, adjncy, conn0.data(), nbElem, dimElem, nbNodes);
+        dc::metis_recursive(nodePart, xadj, adjncy, nbNodes, nbPart);
+    }
+    #pragma omp parallel for schedule(static) if (nbElem > (1 << 16))
+    for (int e = 0; e < nbElem; e++) {
+        int best = -1, bestCount = 0;
+        for (int j = 0; j < dimElem; j++) {
+            const int p = nodePart[(size_t)(elemToNode[(int64_t)e * dimElem + j] - 1)];
+            int count = 0;
+            for (int k = 0; k < dimElem; k++)
+                if (nodePart[(size_t)(elemToNode[(int64_t)e * dimElem + k] - 1)] == p) count++;
+            if (count > bestCount || (count == bestCount && p < best)) { best = p; bestCount = count; }
+        }
+        elemPart[e] = best;
+    }
+}
+
 void DC_set_vec_size (int vecSize) { dc::options().vecSize = vecSize; }
 int  DC_get_vec_size () { return dc::options().vecSize; }
 void DC_set_max_elem_per_part (int maxElem) { if (maxElem > 0) dc::options().maxElemPerPart = maxElem; }

@@ -10,7 +10,7 @@ dc_cuda_unpack_add_edges.
 """
 import numpy as np
 
-from . import (DC_create_tree, DC_create_tree_geometric, DC_finalize_tree, DC_permute_double_2d_array,
+from . import (DC_create_tree, DC_create_tree_geometric, DC_finalize_tree, DC_partition_mesh, DC_permute_double_2d_array,
                DC_renumber_int_array, DC_set_num_threads, DC_set_vec_size, build_csr_fast, flatten_tree, get_node_perm,
                kuhn_cube_fast, pack_edges, unpack_add_edges)
 
@@ -78,6 +78,74 @@ def build_slab(n, rank, world, builder="geometric", vec=0, seed=12345, csr_devic
     gid_of_new[node_perm] = global_node_ids(n, rank)
     return dict(conn=conn, coord=coord, row=row, col=col, E=E, N=N, nnz=int(row[-1]), rec=rec, n=n,
                 intf=intf, gid_of_new=gid_of_new, node_perm=node_perm, rank=rank, world=world, csr_s=t_csr)
+
+
+def _pair_keys(conn_g, n_glob, keep):
+    """Sorted unique keys row*n_glob+col of the CSR entries (all 16 node pairs of every element,
+    diagonal included) whose two GLOBAL nodes both satisfy keep[node]."""
+    c = conn_g.astype(np.int64) - 1
+    c = c[keep[c].sum(axis=1) >= 1]
+    a = np.repeat(c, 4, axis=1).reshape(-1)
+    b = np.tile(c, (1, 4)).reshape(-1)
+    ok = keep[a] & keep[b]
+    return np.unique(a[ok] * np.int64(n_glob) + b[ok])
+
+
+def build_part(conn_g, coord_g, elem_part, rank, world, builder="metis", vec=0):
+    """Appendix-A driver for part `rank` of a GENERAL element partition (DC_partition_mesh) of one
+    global mesh (BASELINE config 4: an irregular mesh split over the GPUs): local renumbering, own
+    D&C tree, CSR pattern of the local elements, and per neighbouring rank the local CSR edges
+    that the neighbour holds too -- listed by ascending (global row, global column), so both sides
+    agree on the order.  Every rank holds the global connectivity here (host memory only); the
+    device only ever sees the local part.  Returns the same dictionary as build_slab."""
+    n_glob = coord_g.shape[0]
+    mine = np.flatnonzero(elem_part == rank)
+    conn_mine_g = conn_g[mine]
+    nodes = np.unique(conn_mine_g.astype(np.int64) - 1)                  # global ids of the local nodes, ascending
+    conn = np.ascontiguousarray(np.searchsorted(nodes, conn_mine_g.astype(np.int64) - 1) + 1, dtype=np.int32)
+    coord = np.ascontiguousarray(coord_g[nodes])
+    E, N = conn.shape[0], nodes.shape[0]
+    DC_set_vec_size(vec)
+    if builder == "geometric":
+        DC_create_tree_geometric(conn, E, 4, N, coord)
+    else:
+        DC_create_tree(conn, E, 4, N)
+    node_perm = get_node_perm(N)
+    DC_permute_double_2d_array(coord, N, 3)
+    DC_renumber_int_array(conn.reshape(-1), 4 * E)
+    row, col = build_csr_fast(conn, N)
+    DC_finalize_tree(row, conn, E, 4)
+    rec = flatten_tree()
+    gid_of_new = np.empty(N, dtype=np.int64)
+    gid_of_new[node_perm] = nodes
+    # local CSR entries keyed by global (row, col)
+    rows = np.repeat(np.arange(N, dtype=np.int64), np.diff(row))
+    key_local = gid_of_new[rows] * np.int64(n_glob) + gid_of_new[col]
+    order = np.argsort(key_local, kind="stable")
+    key_sorted = key_local[order]
+    mine_nodes = np.zeros(n_glob, dtype=bool)
+    mine_nodes[nodes] = True
+    intf = {}
+    for q in range(world):
+        if q == rank:
+            continue
+        theirs = conn_g[elem_part == q]
+        if theirs.shape[0] == 0:
+            continue
+        shared = np.zeros(n_glob, dtype=bool)
+        shared[np.unique(theirs.astype(np.int64) - 1)] = True
+        shared &= mine_nodes
+        if not shared.any():
+            continue
+        common = np.intersect1d(_pair_keys(conn_mine_g, n_glob, shared), _pair_keys(theirs, n_glob, shared),
+                                assume_unique=True)
+        if common.shape[0] == 0:
+            continue
+        pos = np.searchsorted(key_sorted, common)
+        assert np.array_equal(key_sorted[pos], common)
+        intf[q] = np.ascontiguousarray(order[pos], dtype=np.int64)
+    return dict(conn=conn, coord=coord, row=row, col=col, E=E, N=N, nnz=int(row[-1]), rec=rec, intf=intf,
+                gid_of_new=gid_of_new, node_perm=node_perm, rank=rank, world=world, elems=mine)
 
 
 class InterfaceExchange:

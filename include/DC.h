@@ -139,6 +139,11 @@ int  DC_get_max_elem_per_part ();
  * original numbering) in place of METIS -- same tree invariants, usable at 10^8 elements. */
 void DC_create_tree_geometric (int *elemToNode, int nbElem, int dimElem, int nbNodes,
                                const double *coord, int dimNode);
+/* Element partition for nbPart devices (BASELINE config 4 "METIS-split"): nodes cut
+ * by METIS recursive bisection of the nodal graph as in partitioning.cc:167-228 (coord == nullptr)
+ * or by coordinate bisection; an element follows the majority of its nodes.  elemPart: [nbElem]. */
+void DC_partition_mesh (const int *elemToNode, int nbElem, int dimElem, int nbNodes, int nbPart,
+                        const double *coord, int dimNode, int *elemPart);
 /* Worker threads for DC_tree_traversal / DC_assembly host callbacks (0 = all). */
 void DC_set_num_threads (int nbThreads);
 /* Root of the current tree (nullptr before create/read). */

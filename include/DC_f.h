@@ -38,6 +38,8 @@ extern "C" {
     /* additions */
     void dc_create_tree_geometric_ (int *elemToNode, int *nbElem, int *dimElem, int *nbNodes,
                                     double *coord, int *dimNode);
+    void dc_partition_mesh_ (int *elemToNode, int *nbElem, int *dimElem, int *nbNodes, int *nbPart,
+                             double *coord, int *dimNode, int *elemPart);
     void dc_set_vec_size_ (int *vecSize);
     void dc_set_max_elem_per_part_ (int *maxElem);
     void dc_set_num_threads_ (int *nbThreads);

@@ -221,6 +221,56 @@ def test_two_logical_ranks_on_one_gpu(tmp_path):
         assert np.abs(got - want[pos]).max() <= REL_TOL * np.abs(want).max()
 
 
+def test_metis_split_irregular_mesh_on_one_gpu(tmp_path):
+    """BASELINE config 4 at test size: a graded / relabelled / shuffled mesh cut by DC_partition_mesh
+    (METIS) into four parts; every part is assembled on this GPU by the unit kernel (bit-exact against
+    the oracle on the part), the interface partial sums are combined on the device with the pack /
+    unpack-add kernels, and every local entry then equals the single-domain oracle within 1e-12."""
+    import torch
+    from dc_lib_b200 import multigpu
+    from test_multirank_gloo import _irregular_mesh
+    n, world, dim = 8, 4, 3
+    conn_g, coord_g = _irregular_mesh(n)
+    N_glob = coord_g.shape[0]
+    part = dc.DC_partition_mesh(conn_g, N_glob, world)
+    assert np.bincount(part, minlength=world).min() > 0
+    parts, vals, ctxs = [], [], []
+    for r in range(world):
+        p = multigpu.build_part(conn_g, coord_g, part, r, world, builder="metis")
+        plan = dc.HostPlan(p["conn"], p["N"], p["row"], p["col"], 0, p["rec"], 320)
+        ctx = dc.Context(0)
+        ctx.set_mesh(p["conn"], p["coord"], p["row"], p["col"], 0)
+        ctx.upload_plan(plan)
+        v = torch.empty(p["nnz"] * 9, dtype=torch.float64, device="cuda:0")
+        ctx.assemble(dc.OP_ELASTICITY, [LAMBDA, MU], dc.MODE_DETERMINISTIC, v)
+        assert v.cpu().numpy().tobytes() == oracle_serial(p, 3).tobytes()        # local partial sums, bit for bit
+        parts.append(p); vals.append(v); ctxs.append(ctx)
+    bufs = {}
+    for r in range(world):
+        for nb, edges in parts[r]["intf"].items():
+            b = torch.empty(edges.shape[0] * 9, dtype=torch.float64, device="cuda:0")
+            dc.pack_edges(vals[r], torch.from_numpy(edges).cuda(), 9, b)
+            bufs[(r, nb)] = b
+    torch.cuda.synchronize()
+    for r in range(world):
+        for nb, edges in parts[r]["intf"].items():
+            assert bufs[(nb, r)].numel() == edges.shape[0] * 9
+            dc.unpack_add_edges(vals[r], torch.from_numpy(edges).cuda(), 9, bufs[(nb, r)])
+    torch.cuda.synchronize()
+    row, col = dc.build_csr(conn_g, N_glob)
+    mesh = dict(conn=conn_g, coord=coord_g, row=row, col=col, E=conn_g.shape[0], N=N_glob, nnz=int(row[-1]))
+    want = oracle_serial(mesh, dim).reshape(-1, 9)
+    key_ref = np.repeat(np.arange(N_glob, dtype=np.int64), np.diff(row)) * N_glob + col
+    for r in range(world):
+        p = parts[r]
+        rows = np.repeat(np.arange(p["N"]), np.diff(p["row"]))
+        key = p["gid_of_new"][rows] * N_glob + p["gid_of_new"][p["col"]]
+        pos = np.searchsorted(key_ref, key)
+        assert np.array_equal(key_ref[pos], key)
+        got = vals[r].cpu().numpy().reshape(-1, 9)
+        assert np.abs(got - want[pos]).max() <= REL_TOL * np.abs(want).max()
+
+
 def test_device_resident_setup_path(tmp_path):
     """setup_device_slabs (mesh + schedule adopted from device tensors, coordinates permuted by
     the CUDA permute kernel) gives the same bits as the host-upload path."""

@@ -82,3 +82,70 @@ def test_two_rank_interface_exchange(tmp_path, n, dim):
         # edge must now carry the global value
         scale = np.abs(want).max()
         assert np.abs(d["vals"] - want[pos]).max() <= 1e-12 * scale
+
+
+# ---- general element partition (BASELINE config 4: irregular mesh, METIS-split) --------------
+
+def _irregular_mesh(n):
+    """Graded, relabelled, shuffled cube (config C4's shape at test size), original numbering."""
+    import common
+    import dc_lib_b200 as dc
+    conn, _ = dc.kuhn_cube(n)
+    coord = dc.jitter_coords(n)
+    return common.scramble_mesh(conn, coord)
+
+
+def _part_worker(rank, world, n, dim, method, port, out):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import common
+    import dc_lib_b200 as dc
+    from dc_lib_b200 import multigpu
+    conn_g, coord_g = _irregular_mesh(n)
+    part = dc.DC_partition_mesh(conn_g, coord_g.shape[0], world, coord_g if method == "geometric" else None)
+    p = multigpu.build_part(conn_g, coord_g, part, rank, world, builder="metis")
+    vals = torch.from_numpy(common.oracle_serial(p, dim))               # local partial sums
+    before = vals.clone()
+    multigpu.InterfaceExchange(p["intf"], dim * dim, "cpu", dist).run(vals)
+    rows = np.repeat(np.arange(p["N"]), np.diff(p["row"]))
+    torch.save(dict(grow=p["gid_of_new"][rows], gcol=p["gid_of_new"][p["col"]], vals=vals.numpy().reshape(p["nnz"], dim * dim),
+                    changed=int((vals != before).sum()), nb=sorted(p["intf"]), E=p["E"],
+                    lens={q: int(e.shape[0]) for q, e in p["intf"].items()}),
+               os.path.join(out, f"rank{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n,dim,method", [(2, 6, 3, "metis"), (3, 6, 1, "metis"), (2, 5, 3, "geometric")])
+def test_general_partition_interface_exchange(tmp_path, world, n, dim, method):
+    """An irregular mesh cut by DC_partition_mesh into `world` parts: every rank assembles its own
+    elements, the interface exchange sums the partial values of the edges several ranks hold, and
+    every local CSR entry then carries the value of the single-domain assembly (<= 1e-12)."""
+    port = 29500 + ((os.getpid() + 7 * world + n) % 500)
+    mp.spawn(_part_worker, args=(world, n, dim, method, port, str(tmp_path)), nprocs=world, join=True)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import common
+    import dc_lib_b200 as dc
+    conn_g, coord_g = _irregular_mesh(n)
+    N_glob = coord_g.shape[0]
+    row, col = dc.build_csr(conn_g, N_glob)
+    mesh = dict(conn=conn_g, coord=coord_g, row=row, col=col, E=conn_g.shape[0], N=N_glob, nnz=int(row[-1]))
+    want = common.oracle_serial(mesh, dim).reshape(mesh["nnz"], dim * dim)
+    key_ref = np.repeat(np.arange(N_glob, dtype=np.int64), np.diff(row)) * N_glob + col
+    scale = np.abs(want).max()
+    total, lens = 0, {}
+    for r in range(world):
+        d = torch.load(os.path.join(str(tmp_path), f"rank{r}.pt"), weights_only=False)
+        assert d["changed"] > 0 and d["nb"]
+        total += d["E"]
+        lens[r] = d["lens"]
+        key = d["grow"] * N_glob + d["gcol"]
+        pos = np.searchsorted(key_ref, key)
+        assert np.array_equal(key_ref[pos], key)
+        assert np.abs(d["vals"] - want[pos]).max() <= 1e-12 * scale
+    assert total == conn_g.shape[0]                                   # every element assembled exactly once
+    for r in range(world):
+        for q, ln in lens[r].items():
+            assert lens[q][r] == ln                                   # both sides list the same edges
