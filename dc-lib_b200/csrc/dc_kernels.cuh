@@ -103,6 +103,7 @@ struct UnitLayout {
     int offSlotN;    /* per slot: 4 uint16 indices into the unit's node table (TMA target)    */
     int offHnode;    /* halo node ids (TMA target)                                           */
     int offCoord;    /* coordinates of the node table: own interval (TMA target) + halo nodes */
+    int coordStride; /* halo node ids + coordinates are double-buffered, second copy this far away */
     int offTasks;    /* dc_task_t records                                                    */
     int offTgt;      /* symmetric schedule: (edge, transposed edge) pairs                    */
     int offItems;    /* uint16 items                                                         */
@@ -124,11 +125,12 @@ struct UnitSmem {
     {
         auto up = [](int v) { return (v + 15) & ~15; };
         UnitLayout L;
-        L.offStage = 32 + 2 * (int)sizeof(dc_unit_t);      /* barriers, task counter, two unit descriptors */
+        L.offStage = 48 + 4 * (int)sizeof(dc_unit_t);      /* barriers, counters, four unit descriptors */
         L.offSlotN = L.offStage + up((threads / 32) * STAGE);
         L.offHnode = L.offSlotN + up(((maxSlots + 1) & ~1) * 8);
         L.offCoord = L.offHnode + up(maxHalo * 4);
-        L.offTasks = L.offCoord + up((maxNodes + maxHalo) * 24);
+        L.coordStride = up(maxHalo * 4) + up((maxNodes + maxHalo) * 24);
+        L.offTasks = L.offHnode + 2 * L.coordStride;
         L.offTgt = L.offTasks + up(maxTasks * 16);
         L.offItems = L.offTgt + up(maxTgt * 8);
         L.offRecs = L.offItems + up(maxItems * 2);
@@ -198,7 +200,7 @@ __device__ __forceinline__ void do_task(const dc_unit_t &u, const dc_task_t task
         if (valid) t0 = tgtS[(int)task.first + lane].x;
         if (DC_KO_ON(2)) t0 = -1;
         if (DD == 1) {
-            if (valid) st_stream_f64(values + t0, acc[0]);
+            if (valid && t0 >= 0) st_stream_f64(values + t0, acc[0]);
         } else {
 #pragma unroll
             for (int c = 0; c < DD; c++) myStage[lane * DD + c] = acc[c];
@@ -240,7 +242,7 @@ __device__ __forceinline__ void do_task(const dc_unit_t &u, const dc_task_t task
         if (DC_KO_ON(1)) tg.y = -1;
         if (DD == 1) {
             if (valid) {
-                st_stream_f64(values + tg.x, acc[0]);
+                if (tg.x >= 0) st_stream_f64(values + tg.x, acc[0]);
                 if (tg.y >= 0) st_stream_f64(values + tg.y, acc[0]);
             }
         } else {
@@ -292,16 +294,23 @@ __device__ __forceinline__ void run_tasks(const dc_unit_t &u, const dc_task_t *t
 
 /* One CTA processes units blockIdx.x, blockIdx.x + gridDim.x, ... (a persistent grid of
  * SMs x resident CTAs, or one CTA per unit when the grid equals the unit count).  The fixed
- * latencies of a unit -- its descriptor, the bulk copies of its node tables and coordinates,
- * the gather of its halo coordinates -- are issued while the previous unit accumulates:
+ * latencies of a unit are taken off the path of the unit before it (iteration k = unit k of the CTA):
  *
- *   records(u) | sync A | TMA mesh(u+1) ... accumulate + store(u), then halo gather(u+1) | sync B | TMA sched(u+1)
+ *   top of k     request descriptor k+2; bulk copy of halo node ids + own coordinates of unit k+1
+ *                into the OTHER coordinate buffer (descriptor k+1 was requested an iteration ago)
+ *   records(k)   from the slot -> node table and the coordinate buffer of unit k
+ *   sync A       records complete, the slot -> node table is dead: bulk copy of the table of unit
+ *                k+1 (and of its schedule when that is double-buffered)
+ *   halo(k+1)    every thread loads the coordinates of one halo node of unit k+1 into registers
+ *                (the ids landed while the records were built) ...
+ *   tasks(k)     accumulate + store
+ *                ... and writes them to the coordinate buffer of unit k+1 afterwards; nodes beyond
+ *                the CTA size are gathered by the warps that run out of tasks first
+ *   sync B       the schedule region is dead
  *
- * The node-table region is dead after the records are built and the schedule region after
- * the accumulation, so nothing is double-buffered.  The warp that starts with the longest task
- * (warp 0: tasks are listed longest first) is the critical path of a unit, so the bulk copies are
- * issued by the last warp, and the halo coordinates are gathered by whichever warps run out of
- * tasks first (chunks of 32 nodes from a shared counter). */
+ * so no bulk-copy or gather latency sits between the tasks of one unit and the records of the
+ * next.  The warp that starts with the longest task (warp 0: tasks are listed longest first) is
+ * the critical path of a unit, so the bulk copies are issued by the last warp. */
 template <class Op, int THREADS, int MINB, bool SYM>
 __global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *__restrict__ units, int nbUnits,
                                                               const dc_task_t *__restrict__ tasks,
@@ -321,30 +330,33 @@ __global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *_
     constexpr int RS = UnitSmem<Op>::RS;
     constexpr int NW = THREADS / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);   /* [0] mesh data, [1] schedule, [2] next descriptor */
-    int *nextTask = reinterpret_cast<int *>(smem_raw + 24);           /* dynamic task counter */
-    int *nextHalo = reinterpret_cast<int *>(smem_raw + 28);           /* halo nodes of the next unit handed out so far */
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);   /* [0] slot table, [1] schedule, [2] descriptor, [3] coordinates */
+    int *nextTask = reinterpret_cast<int *>(smem_raw + 32);           /* dynamic task counter */
+    int *nextHalo = reinterpret_cast<int *>(smem_raw + 36);           /* halo nodes of the next unit handed out so far */
     constexpr int ISSUER = (NW - 1) * 32;                             /* thread that issues the bulk copies */
-    dc_unit_t *descS = reinterpret_cast<dc_unit_t *>(smem_raw + 32);  /* descriptors of this and the next unit */
+    dc_unit_t *descS = reinterpret_cast<dc_unit_t *>(smem_raw + 48);  /* descriptor of unit k of this CTA at k & 3 */
     uint2 *slotN = reinterpret_cast<uint2 *>(smem_raw + L.offSlotN);
-    int *hnodeS = reinterpret_cast<int *>(smem_raw + L.offHnode);
-    double *coordS = reinterpret_cast<double *>(smem_raw + L.offCoord);
     double *recs = reinterpret_cast<double *>(smem_raw + L.offRecs);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double *myStage = reinterpret_cast<double *>(smem_raw + L.offStage + warp * UnitSmem<Op>::STAGE);
+    auto hnode_of = [&](int k) { return reinterpret_cast<int *>(smem_raw + L.offHnode + (k & 1) * L.coordStride); };
+    auto coord_of = [&](int k) { return reinterpret_cast<double *>(smem_raw + L.offCoord + (k & 1) * L.coordStride); };
 
-    /* bulk copies of a unit's inputs (thread 0).  The node table starts at the even node at or
+    /* bulk copies of a unit's inputs (one thread).  The node table starts at the even node at or
      * below nodeFirst and spans an even number of nodes: 48-byte granules. */
-    auto issue_mesh = [&](const dc_unit_t &d) {
-        const int nSl = d.ownElemCount + d.haloCount;
+    auto issue_coords = [&](const dc_unit_t &d, int k) {
         const int alignedFirst = d.nodeFirst & ~1;
         const int ownSpan = ((d.nodeFirst + d.nodeCount + 1) & ~1) - alignedFirst;
-        const uint32_t slotBytes = (uint32_t)((nSl + 1) & ~1) * 8u, hnodeBytes = (uint32_t)d.hnodeCount * 4u;
-        const uint32_t coordBytes = (uint32_t)ownSpan * 24u;
-        mbar_expect_tx(&bar[0], slotBytes + hnodeBytes + coordBytes);
+        const uint32_t hnodeBytes = (uint32_t)d.hnodeCount * 4u, coordBytes = (uint32_t)ownSpan * 24u;
+        mbar_expect_tx(&bar[3], hnodeBytes + coordBytes);
+        if (hnodeBytes) tma_bulk_g2s(hnode_of(k), haloNodes + d.hnodeFirst, hnodeBytes, &bar[3]);
+        if (coordBytes) tma_bulk_g2s(coord_of(k), coord + (int64_t)alignedFirst * 3, coordBytes, &bar[3]);
+    };
+    auto issue_slots = [&](const dc_unit_t &d) {
+        const int nSl = d.ownElemCount + d.haloCount;
+        const uint32_t slotBytes = (uint32_t)((nSl + 1) & ~1) * 8u;
+        mbar_expect_tx(&bar[0], slotBytes);
         if (slotBytes) tma_bulk_g2s(slotN, slotNodes + d.slotFirst * 4, slotBytes, &bar[0]);
-        if (hnodeBytes) tma_bulk_g2s(hnodeS, haloNodes + d.hnodeFirst, hnodeBytes, &bar[0]);
-        if (coordBytes) tma_bulk_g2s(coordS, coord + (int64_t)alignedFirst * 3, coordBytes, &bar[0]);
     };
     /* schedule of iteration `iter` (double-buffered when the layout has room for it) */
     auto issue_sched = [&](const dc_unit_t &d, int iter) {
@@ -356,56 +368,72 @@ __global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *_
         if (itemBytes) tma_bulk_g2s(base + L.offItems, items + d.itemFirst, itemBytes, &bar[1]);
         if (tgtBytes) tma_bulk_g2s(base + L.offTgt, tgtPairs + d.tgtFirst, tgtBytes, &bar[1]);
     };
-    /* coordinates of a unit's halo nodes: one gather per node (not per element) */
-    auto gather_halo = [&](const dc_unit_t &d, int first, int stride) {
-        const int ownSpan = ((d.nodeFirst + d.nodeCount + 1) & ~1) - (d.nodeFirst & ~1);
-        for (int i = first; i < d.hnodeCount; i += stride) {
-            const double *src = coord + (int64_t)hnodeS[i] * 3;
-            double *dst = coordS + (ownSpan + i) * 3;
-            dst[0] = __ldg(src);
-            dst[1] = __ldg(src + 1);
-            dst[2] = __ldg(src + 2);
-        }
-    };
 
     int unit = blockIdx.x;
     if (unit >= nbUnits) return;
+    const int stride = (int)gridDim.x;
     DC_STAMP(unit, 0);
     if (tid == 0) {
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
         mbar_init(&bar[2], 1);
+        mbar_init(&bar[3], 1);
         *nextTask = NW;
-        *nextHalo = 0;
+        *nextHalo = THREADS;
         descS[0] = units[unit];
+        if (unit + stride < nbUnits) descS[1] = units[unit + stride];
     }
     __syncthreads();
     if (tid == 0) {
-        issue_mesh(descS[0]);
+        issue_slots(descS[0]);
+        issue_coords(descS[0], 0);
         issue_sched(descS[0], 0);
     }
-    mbar_wait(&bar[0], 0);
-    gather_halo(descS[0], tid, THREADS);
+    mbar_wait(&bar[3], 0);
+    {
+        /* coordinates of the first unit's halo nodes: one gather per node (not per element) */
+        const dc_unit_t &d = descS[0];
+        const int ownSpan = ((d.nodeFirst + d.nodeCount + 1) & ~1) - (d.nodeFirst & ~1);
+        const int *hn = hnode_of(0);
+        double *cs = coord_of(0);
+        for (int i = tid; i < d.hnodeCount; i += THREADS) {
+            const double *src = coord + (int64_t)hn[i] * 3;
+            double *dst = cs + (ownSpan + i) * 3;
+            dst[0] = __ldg(src);
+            dst[1] = __ldg(src + 1);
+            dst[2] = __ldg(src + 2);
+        }
+    }
     __syncthreads();
 
     for (int k = 0;; k++) {
-        const dc_unit_t u = descS[k & 1];
+        const dc_unit_t u = descS[k & 3];
         const dc_task_t *taskS = reinterpret_cast<const dc_task_t *>(smem_raw + (k & 1) * L.schedStride + L.offTasks);
         const int2 *tgtS = reinterpret_cast<const int2 *>(smem_raw + (k & 1) * L.schedStride + L.offTgt);
         const uint16_t *itemS = reinterpret_cast<const uint16_t *>(smem_raw + (k & 1) * L.schedStride + L.offItems);
+        const double *coordS = coord_of(k);
         const int nSlots = u.ownElemCount + u.haloCount;
-        const int next = unit + (int)gridDim.x;
+        const int next = unit + stride;
         const bool hasNext = next < nbUnits;
-        /* descriptor of the next unit: bulk copy requested now, needed after the records are built */
-        if (tid == 0 && hasNext) {
-            mbar_expect_tx(&bar[2], (uint32_t)sizeof(dc_unit_t));
-            tma_bulk_g2s(&descS[(k + 1) & 1], units + next, (uint32_t)sizeof(dc_unit_t), &bar[2]);
+        /* descriptor k+1 was requested at the top of iteration k-1 (k = 0: loaded directly); its
+         * halo node ids and own coordinates go to the other coordinate buffer now, descriptor k+2
+         * is requested for the next iteration.  One thread waits and re-arms bar[2], in this order
+         * (phase k of bar[2] = descriptor k+2; the last two iterations arm nothing and wait for
+         * nothing that was not armed). */
+        if (tid == ISSUER && hasNext) {
+            if (k >= 1) mbar_wait(&bar[2], (uint32_t)(k - 1) & 1u);
+            if (next + stride < nbUnits) {
+                mbar_expect_tx(&bar[2], (uint32_t)sizeof(dc_unit_t));
+                tma_bulk_g2s(&descS[(k + 2) & 3], units + next + stride, (uint32_t)sizeof(dc_unit_t), &bar[2]);
+            }
+            issue_coords(descS[(k + 1) & 3], k + 1);
         }
         DC_STAMP(unit, 1);
 
         /* P1b: one record per touched element, everything from shared memory; slot nSlots is an
          * all-zero record: padding items point at it and add exact zeros, so the accumulation
          * loops need no test and can be software-pipelined */
+        mbar_wait(&bar[0], (uint32_t)k & 1u);          /* this unit's slot -> node table */
         if (tid < RS) recs[nSlots * RS + tid] = 0.0;
         for (int s0 = tid; s0 < (DC_KO_ON(8) ? 0 : nSlots); s0 += 2 * THREADS) {
             /* two elements per thread in flight: the dependent chain of one setup (cross products,
@@ -434,38 +462,58 @@ __global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *_
             }
         }
         mbar_wait(&bar[1], k & 1);   /* this unit's schedule (every thread passes before the phase is re-armed) */
-        __syncthreads();   /* A: records complete; node tables and coordinates are dead */
+        __syncthreads();   /* A: records complete; the slot -> node table is dead */
         DC_STAMP(unit, 2);
         if (tid == ISSUER && hasNext) {
-            mbar_wait(&bar[2], k & 1);
-            issue_mesh(descS[(k + 1) & 1]);            /* lands while this unit accumulates */
-            if (L.schedStride) issue_sched(descS[(k + 1) & 1], k + 1);   /* into the other buffer */
+            issue_slots(descS[(k + 1) & 3]);                             /* lands while this unit accumulates */
+            if (L.schedStride) issue_sched(descS[(k + 1) & 3], k + 1);   /* into the other buffer */
+        }
+        /* halo coordinates of the next unit: the node ids landed while the records were built;
+         * one node per thread goes to registers now and to shared memory after the tasks */
+        double hx0 = 0.0, hx1 = 0.0, hx2 = 0.0;
+        int hCnt = 0, hSpan = 0;
+        if (hasNext) {
+            mbar_wait(&bar[3], (uint32_t)(k + 1) & 1u);
+            const dc_unit_t &nx = descS[(k + 1) & 3];
+            hCnt = nx.hnodeCount;
+            hSpan = ((nx.nodeFirst + nx.nodeCount + 1) & ~1) - (nx.nodeFirst & ~1);
+            if (tid < hCnt) {
+                const double *src = coord + (int64_t)hnode_of(k + 1)[tid] * 3;
+                hx0 = __ldg(src);
+                hx1 = __ldg(src + 1);
+                hx2 = __ldg(src + 2);
+            }
         }
         DC_STAMP(unit, 3);
 
         run_tasks<Op, NW, SYM>(u, taskS, itemS, tgtS, recs, nextTask, myStage, diagRel, values, warp, lane);
         DC_STAMP(unit, 4);
-        /* halo coordinates of the next unit: one gather per node, done by the warps that have run
-         * out of tasks (the node ids have landed long before); every thread observes the bulk
-         * copies of the next unit's node tables here */
         if (hasNext) {
-            mbar_wait(&bar[0], (k + 1) & 1);
-            const dc_unit_t &nx = descS[(k + 1) & 1];
-            const int ownSpan = ((nx.nodeFirst + nx.nodeCount + 1) & ~1) - (nx.nodeFirst & ~1);
-            const int cnt = nx.hnodeCount;
-            for (;;) {
-                int c = 0;
-                if (lane == 0) c = atomicAdd(nextHalo, 32);
-                c = __shfl_sync(0xffffffffu, c, 0);
-                if (c >= cnt) break;
-                const int i = c + lane;
-                if (i < cnt) {
-                    const double *src = coord + (int64_t)hnodeS[i] * 3;
-                    const double x0 = __ldg(src), x1 = __ldg(src + 1), x2 = __ldg(src + 2);
-                    double *dst = coordS + (ownSpan + i) * 3;
-                    dst[0] = x0;
-                    dst[1] = x1;
-                    dst[2] = x2;
+            double *cn = coord_of(k + 1);
+            if (tid < hCnt) {
+                double *dst = cn + (hSpan + tid) * 3;
+                dst[0] = hx0;
+                dst[1] = hx1;
+                dst[2] = hx2;
+            }
+            /* the rare unit with more halo nodes than threads: chunks of 32, taken by the warps
+             * that run out of tasks first */
+            if (hCnt > THREADS) {
+                const int *hn = hnode_of(k + 1);
+                for (;;) {
+                    int c = 0;
+                    if (lane == 0) c = atomicAdd(nextHalo, 32);
+                    c = __shfl_sync(0xffffffffu, c, 0);
+                    if (c >= hCnt) break;
+                    const int i = c + lane;
+                    if (i < hCnt) {
+                        const double *src = coord + (int64_t)hn[i] * 3;
+                        const double x0 = __ldg(src), x1 = __ldg(src + 1), x2 = __ldg(src + 2);
+                        double *dst = cn + (hSpan + i) * 3;
+                        dst[0] = x0;
+                        dst[1] = x1;
+                        dst[2] = x2;
+                    }
                 }
             }
         }
@@ -475,8 +523,8 @@ __global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *_
         if (!hasNext) break;
         if (tid == 0) {
             *nextTask = NW;
-            *nextHalo = 0;
-            if (!L.schedStride) issue_sched(descS[(k + 1) & 1], k + 1);
+            *nextHalo = THREADS;
+            if (!L.schedStride) issue_sched(descS[(k + 1) & 3], k + 1);
         }
         unit = next;
     }
