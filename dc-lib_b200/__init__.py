@@ -116,6 +116,7 @@ def _declare(L):
     L.dcx_kuhn_slab.restype = None
     L.dc_get_node_perm.argtypes = [vp, c_int]
     L.dc_get_elem_perm.argtypes = [vp, c_int]
+    L.dc_cuda_spmv.argtypes = [vp, c_int, vp, vp, vp, vp]
     L.dc_cuda_pack_edges.argtypes = [vp, vp, c_int64, c_int, vp, vp]
     L.dc_cuda_unpack_add_edges.argtypes = [vp, vp, c_int64, c_int, vp, vp]
     L.dc_cuda_csr_begin.argtypes = [vp, c_int, c_int, vp, POINTER(c_int64), POINTER(c_void_p), vp]
@@ -398,6 +399,10 @@ class Context:
                  "dc_cuda_assemble")
         self._ck(lib().dc_cuda_download_values(self.h, dim, _p(out), stream), "dc_cuda_download_values")
         self._ck(lib().dc_cuda_sync(stream), "dc_cuda_sync")
+
+    def spmv(self, dim, values, x, y, stream=None):
+        """y = A x with the assembled block-CSR values (torch CUDA tensors)."""
+        self._ck(lib().dc_cuda_spmv(self.h, dim, _p(values), _p(x), _p(y), stream), "dc_cuda_spmv")
 
     def set_option(self, name, value):
         self._ck(lib().dc_cuda_set_option(self.h, name.encode(), int(value)), "dc_cuda_set_option")

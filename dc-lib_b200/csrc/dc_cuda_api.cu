@@ -429,6 +429,26 @@ extern "C" int dc_cuda_unpack_add_edges(double *d_values, const int64_t *d_edge,
     return 0;
 }
 
+/* y = A x with the assembled block-CSR values (dim = 1 or 3) and the context's CSR pattern */
+extern "C" int dc_cuda_spmv(dc_cuda_ctx *c, int dim, const double *d_values, const double *d_x, double *d_y,
+                            void *stream)
+{
+    if (!c || !c->d_row || !c->d_col) return fail(-1, "dc_cuda_spmv: no CSR pattern on the device");
+    if (!d_values || !d_x || !d_y) return fail(-1, "dc_cuda_spmv: null argument");
+    CK(cudaSetDevice(c->device));
+    if (c->nbNodes <= 0) return 0;
+    const unsigned grid = grid_for((int64_t)c->nbNodes * dim, 256);
+    if (dim == 1)
+        bsr_spmv<1><<<grid, 256, 0, (cudaStream_t)stream>>>(c->d_row, c->d_col, c->colBase, d_values, d_x, d_y, c->nbNodes);
+    else if (dim == 3)
+        bsr_spmv<3><<<grid, 256, 0, (cudaStream_t)stream>>>(c->d_row, c->d_col, c->colBase, d_values, d_x, d_y, c->nbNodes);
+    else
+        return fail(-9, "dc_cuda_spmv: dim must be 1 or 3");
+    CK(cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+
 /* debug: enable per-unit phase stamps; the next assembly fills h_out[nbUnits][8] on request */
 extern "C" int dc_cuda_debug_phases(dc_cuda_ctx *c, long long *h_out)
 {

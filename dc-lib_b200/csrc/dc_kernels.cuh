@@ -49,6 +49,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         "r"(parity)
         : "memory");
 }
+/* non-blocking: has the phase with this parity completed? */
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return done != 0;
+}
 /* TMA bulk copy global -> shared, completion signalled on an mbarrier (UBLKCP) */
 __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
 {
@@ -468,16 +481,15 @@ __global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *_
             issue_slots(descS[(k + 1) & 3]);                             /* lands while this unit accumulates */
             if (L.schedStride) issue_sched(descS[(k + 1) & 3], k + 1);   /* into the other buffer */
         }
-        /* halo coordinates of the next unit: the node ids landed while the records were built;
-         * one node per thread goes to registers now and to shared memory after the tasks */
+        /* halo coordinates of the next unit: the node ids have normally landed while the records
+         * were built; then one node per thread goes to registers now and to shared memory after
+         * the tasks.  A thread that finds the copy still in flight does not wait here: it loads
+         * its node after the tasks. */
         double hx0 = 0.0, hx1 = 0.0, hx2 = 0.0;
-        int hCnt = 0, hSpan = 0;
-        if (hasNext) {
-            mbar_wait(&bar[3], (uint32_t)(k + 1) & 1u);
+        const bool early = hasNext && mbar_test(&bar[3], (uint32_t)(k + 1) & 1u);
+        if (early) {
             const dc_unit_t &nx = descS[(k + 1) & 3];
-            hCnt = nx.hnodeCount;
-            hSpan = ((nx.nodeFirst + nx.nodeCount + 1) & ~1) - (nx.nodeFirst & ~1);
-            if (tid < hCnt) {
+            if (tid < nx.hnodeCount) {
                 const double *src = coord + (int64_t)hnode_of(k + 1)[tid] * 3;
                 hx0 = __ldg(src);
                 hx1 = __ldg(src + 1);
@@ -489,8 +501,18 @@ __global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *_
         run_tasks<Op, NW, SYM>(u, taskS, itemS, tgtS, recs, nextTask, myStage, diagRel, values, warp, lane);
         DC_STAMP(unit, 4);
         if (hasNext) {
+            if (!early) mbar_wait(&bar[3], (uint32_t)(k + 1) & 1u);
+            const dc_unit_t &nx = descS[(k + 1) & 3];
+            const int hCnt = nx.hnodeCount;
+            const int hSpan = ((nx.nodeFirst + nx.nodeCount + 1) & ~1) - (nx.nodeFirst & ~1);
             double *cn = coord_of(k + 1);
             if (tid < hCnt) {
+                if (!early) {
+                    const double *src = coord + (int64_t)hnode_of(k + 1)[tid] * 3;
+                    hx0 = __ldg(src);
+                    hx1 = __ldg(src + 1);
+                    hx2 = __ldg(src + 2);
+                }
                 double *dst = cn + (hSpan + tid) * 3;
                 dst[0] = hx0;
                 dst[1] = hx1;
@@ -670,6 +692,33 @@ __global__ void __launch_bounds__(256) unpack_add_edges(double *__restrict__ val
         const int64_t k = w / perEdge;
         double *dst = values + __ldg(edge + k) * perEdge + (w - k * perEdge);
         *dst = __dadd_rn(*dst, buf[w]);
+    }
+}
+
+/* ---- consumer of the assembled matrix -------------------------- */
+
+/* y = A x for the block-CSR matrix the assembly leaves on the device (D x D row-major block per
+ * edge, x and y with D components per node): one thread per (row, component), blocks of the row
+ * in ascending edge order, one fma per entry -- a fixed summation order.  The three threads of a
+ * row read the 72 contiguous bytes of a block between them; the values are streamed (read once). */
+template <int D>
+__global__ void __launch_bounds__(256) bsr_spmv(const int *__restrict__ row, const int *__restrict__ col, int colBase,
+                                                const double *__restrict__ values, const double *__restrict__ x,
+                                                double *__restrict__ y, int64_t nbRows)
+{
+    const int64_t total = nbRows * D, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        const int64_t r = t / D;
+        const int i = (int)(t - r * D);
+        const int k0 = __ldg(row + r), k1 = __ldg(row + r + 1);
+        double acc = 0.0;
+        for (int k = k0; k < k1; k++) {
+            const int64_t c = __ldg(col + k) - colBase;
+            const double *v = values + ((int64_t)k * D + i) * D;
+#pragma unroll
+            for (int j = 0; j < D; j++) acc = __fma_rn(__ldcs(v + j), __ldg(x + c * D + j), acc);
+        }
+        y[t] = acc;
     }
 }
 

@@ -107,6 +107,12 @@ int  dc_cuda_pack_edges(const double *d_values, const int64_t *d_edge, int64_t n
 int  dc_cuda_unpack_add_edges(double *d_values, const int64_t *d_edge, int64_t nbEdges, int perEdge,
                               const double *d_buf, void *stream);
 
+/* Consumer of the assembled matrix (what the reference's user, Mini-FEM, does next;
+ * README.md:32): y = A x for the D x D-block CSR values the assembly left on the device, with the
+ * context's CSR pattern; x and y hold D doubles per node (dim = 1 or 3).  Fixed summation order
+ * (ascending edge, then column component, one fma per entry). */
+int  dc_cuda_spmv(dc_cuda_ctx *ctx, int dim, const double *d_values, const double *d_x, double *d_y, void *stream);
+
 /* CSR pattern of the renumbered mesh, built on the device.  In the reference this is the user's
  * step between DC_renumber_int_array and DC_finalize_tree (the library only ships the node ->
  * element helper DC_create_nodeToElem, src/coloring.cc:79-112); at 10^8 elements the host build

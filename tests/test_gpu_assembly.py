@@ -381,3 +381,38 @@ def test_user_cpp_program_on_the_device_path(tmp_path):
     out = subprocess.check_output([exe, "12", os.path.join(str(tmp_path), "dev")]).decode()
     vals = dict(kv.split("=") for kv in out.split() if "=" in kv)
     assert float(vals["device_vs_host_rel"]) <= REL_TOL and float(vals["elasticity_rowsum_rel"]) <= REL_TOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dim", [1, 3])
+def test_spmv_on_the_assembled_matrix(tmp_path, dim):
+    """dc_cuda_spmv (the consumer step after the assembly): y = A x with the block-CSR values left
+    on the device, against a float64 numpy evaluation of the same sums (tolerance 1e-13 of the
+    largest term: the device uses one fma per entry); constants are in the kernel of both operators."""
+    import torch
+    mesh = prepare_mesh(MineLib(0), 10, tmp_path)
+    plan = dc.HostPlan(mesh["conn"], mesh["N"], mesh["row"], mesh["col"], 0, tree_records(mesh), 400)
+    ctx = dc.Context(0)
+    ctx.set_mesh(mesh["conn"], mesh["coord"], mesh["row"], mesh["col"], 0)
+    ctx.upload_plan(plan)
+    N, nnz = mesh["N"], mesh["nnz"]
+    op, prm = (dc.OP_ELASTICITY, [LAMBDA, MU]) if dim == 3 else (dc.OP_LAPLACIAN, None)
+    vals = torch.empty(nnz * dim * dim, dtype=torch.float64, device="cuda:0")
+    ctx.assemble(op, prm, dc.MODE_DETERMINISTIC, vals)
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal((N, dim))
+    y = torch.full((N * dim,), float("nan"), dtype=torch.float64, device="cuda:0")
+    ctx.spmv(dim, vals, torch.from_numpy(x).cuda(), y)
+    torch.cuda.synchronize()
+    v = vals.cpu().numpy().reshape(nnz, dim, dim)
+    rows = np.repeat(np.arange(N), np.diff(mesh["row"]))
+    want = np.zeros((N, dim))
+    np.add.at(want, rows, np.einsum("kij,kj->ki", v, x[mesh["col"]]))
+    got = y.cpu().numpy().reshape(N, dim)
+    scale = np.abs(v).max() * np.abs(x).max() * np.diff(mesh["row"]).max() * dim
+    assert np.abs(got - want).max() <= 1e-13 * scale
+    ones = torch.ones(N * dim, dtype=torch.float64, device="cuda:0")
+    ctx.spmv(dim, vals, ones, y)
+    torch.cuda.synchronize()
+    assert float(y.abs().max()) <= 1e-10 * np.abs(v).max()            # K * (rigid translation) = 0
+    ctx.close()
