@@ -194,18 +194,21 @@ __device__ __forceinline__ void do_task(const dc_unit_t &u, const dc_task_t task
          * clamped; padding items point at the all-zero record) */
         if (DC_KO_ON(4)) return;
         const int iters = DC_KO_ON(16) ? 0 : task.iters;
-        if (iters > 0) {
+        /* lanes without an edge (the last task of a class is partial) stay out of the loop, so a
+         * half-warp without edges costs no shared-memory wavefronts */
+        if (iters > 0 && ((task.mask >> lane) & 1u)) {
             double nxt[Op::NOPS_DIAG], cur[Op::NOPS_DIAG];
             uint32_t item = it[0];
             Op::fetch_diag(recs + (item >> 4) * RS, item & 3u, nxt);
             item = it[(iters > 1 ? 1 : 0) * 32];
-            for (int i = 0; i < iters; i++) {
+            for (int i = 0; i + 1 < iters; i++) {
 #pragma unroll
                 for (int q = 0; q < Op::NOPS_DIAG; q++) cur[q] = nxt[q];
                 Op::fetch_diag(recs + (item >> 4) * RS, item & 3u, nxt);
                 item = it[(i + 2 < iters ? i + 2 : iters - 1) * 32];
                 Op::apply_diag(cur, c_params, acc);
             }
+            Op::apply_diag(nxt, c_params, acc);        /* the last contribution: nothing left to fetch */
         }
         Op::mirror(acc);
         const bool valid = (task.mask >> lane) & 1u;
@@ -226,18 +229,20 @@ __device__ __forceinline__ void do_task(const dc_unit_t &u, const dc_task_t task
     if (SYM && DC_KO_ON(32)) return;
     {
         const int iters = DC_KO_ON(16) ? 0 : task.iters;
-        if (iters > 0) {
+        const bool holdsEdge = task.kind != DC_TASK_UPPER || ((task.mask >> lane) & 1u);
+        if (iters > 0 && holdsEdge) {
             double nxt[Op::NOPS], cur[Op::NOPS];
             uint32_t item = it[0];
             Op::fetch(recs + (item >> 4) * RS, item & 15u, nxt);
             item = it[(iters > 1 ? 1 : 0) * 32];
-            for (int i = 0; i < iters; i++) {
+            for (int i = 0; i + 1 < iters; i++) {
 #pragma unroll
                 for (int q = 0; q < Op::NOPS; q++) cur[q] = nxt[q];
                 Op::fetch(recs + (item >> 4) * RS, item & 15u, nxt);
                 item = it[(i + 2 < iters ? i + 2 : iters - 1) * 32];
                 Op::apply(cur, c_params, acc);
             }
+            Op::apply(nxt, c_params, acc);             /* the last contribution: nothing left to fetch */
         }
     }
     if (task.kind == DC_TASK_DIAG) {
@@ -450,28 +455,39 @@ __global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *_
         if (tid < RS) recs[nSlots * RS + tid] = 0.0;
         for (int s0 = tid; s0 < (DC_KO_ON(8) ? 0 : nSlots); s0 += 2 * THREADS) {
             /* two elements per thread in flight: the dependent chain of one setup (cross products,
-             * reciprocal, square root) overlaps the other's */
+             * reciprocal, square root) overlaps the other's.  With 512-thread CTAs whole rounds have
+             * no second slot (1536 slots: the third round), so those build one record per thread;
+             * with smaller CTAs the few threads without a second slot repeat their first one (a
+             * branch there costs more than it saves, measured). */
             const int s1 = s0 + THREADS;
             const bool two = s1 < nSlots;
-            const uint2 la = slotN[s0], lb = slotN[two ? s1 : s0];
+            const uint2 la = slotN[s0];
             const uint32_t na[4] = {la.x & 0xFFFFu, la.x >> 16, la.y & 0xFFFFu, la.y >> 16};
-            const uint32_t nb[4] = {lb.x & 0xFFFFu, lb.x >> 16, lb.y & 0xFFFFu, lb.y >> 16};
-            double xa[4][3], xb[4][3];
+            double xa[4][3], ra[Op::NS];
 #pragma unroll
             for (int a = 0; a < 4; a++)
 #pragma unroll
-                for (int q = 0; q < 3; q++) {
-                    xa[a][q] = coordS[na[a] * 3 + q];
-                    xb[a][q] = coordS[nb[a] * 3 + q];
+                for (int q = 0; q < 3; q++) xa[a][q] = coordS[na[a] * 3 + q];
+            if (THREADS < 512 || two) {
+                const uint2 lb = slotN[two ? s1 : s0];
+                const uint32_t nb[4] = {lb.x & 0xFFFFu, lb.x >> 16, lb.y & 0xFFFFu, lb.y >> 16};
+                double xb[4][3], rb[Op::NS];
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int q = 0; q < 3; q++) xb[a][q] = coordS[nb[a] * 3 + q];
+                Op::setup(xa, c_params, ra);
+                Op::setup(xb, c_params, rb);
+#pragma unroll
+                for (int i = 0; i < Op::NS; i++) recs[s0 * RS + i] = ra[i];
+                if (two) {
+#pragma unroll
+                    for (int i = 0; i < Op::NS; i++) recs[s1 * RS + i] = rb[i];
                 }
-            double ra[Op::NS], rb[Op::NS];
-            Op::setup(xa, c_params, ra);
-            Op::setup(xb, c_params, rb);
+            } else {
+                Op::setup(xa, c_params, ra);
 #pragma unroll
-            for (int i = 0; i < Op::NS; i++) recs[s0 * RS + i] = ra[i];
-            if (two) {
-#pragma unroll
-                for (int i = 0; i < Op::NS; i++) recs[s1 * RS + i] = rb[i];
+                for (int i = 0; i < Op::NS; i++) recs[s0 * RS + i] = ra[i];
             }
         }
         mbar_wait(&bar[1], k & 1);   /* this unit's schedule (every thread passes before the phase is re-armed) */
