@@ -455,10 +455,9 @@ __global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *_
         if (tid < RS) recs[nSlots * RS + tid] = 0.0;
         for (int s0 = tid; s0 < (DC_KO_ON(8) ? 0 : nSlots); s0 += 2 * THREADS) {
             /* two elements per thread in flight: the dependent chain of one setup (cross products,
-             * reciprocal, square root) overlaps the other's.  With 512-thread CTAs whole rounds have
-             * no second slot (1536 slots: the third round), so those build one record per thread;
-             * with smaller CTAs the few threads without a second slot repeat their first one (a
-             * branch there costs more than it saves, measured). */
+             * reciprocal, square root) overlaps the other's.  A warp in which no thread has a second
+             * slot builds one record per thread; in a mixed warp the threads without one repeat
+             * their first (a divergent branch there costs more than it saves, measured). */
             const int s1 = s0 + THREADS;
             const bool two = s1 < nSlots;
             const uint2 la = slotN[s0];
@@ -468,7 +467,7 @@ __global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *_
             for (int a = 0; a < 4; a++)
 #pragma unroll
                 for (int q = 0; q < 3; q++) xa[a][q] = coordS[na[a] * 3 + q];
-            if (THREADS < 512 || two) {
+            if (__any_sync(__activemask(), two)) {
                 const uint2 lb = slotN[two ? s1 : s0];
                 const uint32_t nb[4] = {lb.x & 0xFFFFu, lb.x >> 16, lb.y & 0xFFFFu, lb.y >> 16};
                 double xb[4][3], rb[Op::NS];
