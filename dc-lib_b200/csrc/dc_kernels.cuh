@@ -174,6 +174,23 @@ __device__ __forceinline__ void flush_stage(double *__restrict__ values, const d
     }
 }
 
+/* the same for the TRANSPOSED blocks, from the blocks already staged: a lane reads the staged word
+ * it would read for the block itself (consecutive, conflict-free) and stores it at the transposed
+ * position of the target block -- the 32 stores of an instruction cover the same lines either way */
+template <int DD, int D>
+__device__ __forceinline__ void flush_stage_transposed(double *__restrict__ values, const double *stage,
+                                                       int myTarget, int lane)
+{
+#pragma unroll
+    for (int r = 0; r < DD; r++) {
+        const int idx = r * 32 + lane;
+        const int ent = idx / DD;
+        const int comp = idx - ent * DD;
+        const int t = __shfl_sync(0xffffffffu, myTarget, ent);
+        if (t >= 0) st_stream_f64(values + (int64_t)t * DD + (comp % D) * D + comp / D, stage[idx]);
+    }
+}
+
 /* One task (P2): a lane owns one CSR edge and adds its contributions in ascending element order
  * (the order of the item rows); the block -- and, in the symmetric schedule, its transpose --
  * leaves through the warp's staging area as full-line streaming stores. */
@@ -268,11 +285,7 @@ __device__ __forceinline__ void do_task(const dc_unit_t &u, const dc_task_t task
             for (int c = 0; c < DD; c++) myStage[lane * DD + c] = acc[c];
             __syncwarp();
             if (!DC_KO_ON(2)) flush_stage<DD>(values, myStage, tg.x, lane);
-            __syncwarp();
-#pragma unroll
-            for (int c = 0; c < DD; c++) myStage[lane * DD + (c % Op::D) * Op::D + c / Op::D] = acc[c];
-            __syncwarp();
-            if (!DC_KO_ON(1)) flush_stage<DD>(values, myStage, tg.y, lane);
+            if (!DC_KO_ON(1)) flush_stage_transposed<DD, Op::D>(values, myStage, tg.y, lane);
             __syncwarp();
         }
     } else {
