@@ -174,23 +174,6 @@ __device__ __forceinline__ void flush_stage(double *__restrict__ values, const d
     }
 }
 
-/* the same for the TRANSPOSED blocks, from the blocks already staged: a lane reads the staged word
- * it would read for the block itself (consecutive, conflict-free) and stores it at the transposed
- * position of the target block -- the 32 stores of an instruction cover the same lines either way */
-template <int DD, int D>
-__device__ __forceinline__ void flush_stage_transposed(double *__restrict__ values, const double *stage,
-                                                       int myTarget, int lane)
-{
-#pragma unroll
-    for (int r = 0; r < DD; r++) {
-        const int idx = r * 32 + lane;
-        const int ent = idx / DD;
-        const int comp = idx - ent * DD;
-        const int t = __shfl_sync(0xffffffffu, myTarget, ent);
-        if (t >= 0) st_stream_f64(values + (int64_t)t * DD + (comp % D) * D + comp / D, stage[idx]);
-    }
-}
-
 /* One task (P2): a lane owns one CSR edge and adds its contributions in ascending element order
  * (the order of the item rows); the block -- and, in the symmetric schedule, its transpose --
  * leaves through the warp's staging area as full-line streaming stores. */
@@ -284,8 +267,24 @@ __device__ __forceinline__ void do_task(const dc_unit_t &u, const dc_task_t task
 #pragma unroll
             for (int c = 0; c < DD; c++) myStage[lane * DD + c] = acc[c];
             __syncwarp();
-            if (!DC_KO_ON(2)) flush_stage<DD>(values, myStage, tg.x, lane);
-            if (!DC_KO_ON(1)) flush_stage_transposed<DD, Op::D>(values, myStage, tg.y, lane);
+            {
+                /* the block and its transpose leave from ONE pass over the staged words: a lane reads
+                 * the word it would store for the block and also stores it at the transposed position
+                 * of the transposed edge's block (the 32 stores of an instruction cover the same lines
+                 * either way) */
+                const int tgx = DC_KO_ON(2) ? -1 : tg.x, tgy = DC_KO_ON(1) ? -1 : tg.y;
+#pragma unroll
+                for (int r = 0; r < DD; r++) {
+                    const int idx = r * 32 + lane;
+                    const int ent = idx / DD;
+                    const int comp = idx - ent * DD;
+                    const int tx = __shfl_sync(0xffffffffu, tgx, ent);
+                    const int ty = __shfl_sync(0xffffffffu, tgy, ent);
+                    const double v = myStage[idx];
+                    if (tx >= 0) st_stream_f64(values + (int64_t)tx * DD + comp, v);
+                    if (ty >= 0) st_stream_f64(values + (int64_t)ty * DD + (comp % Op::D) * Op::D + comp / Op::D, v);
+                }
+            }
             __syncwarp();
         }
     } else {
