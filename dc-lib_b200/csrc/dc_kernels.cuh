@@ -70,6 +70,15 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+/* asynchronous 8-byte copy global -> shared (LDGSTS): no register holds the value in flight */
+__device__ __forceinline__ void cp_async_8(void *dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.wait_all;" ::: "memory");
+}
 __device__ __forceinline__ void red_add_f64(double *addr, double v)
 {
     asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
@@ -509,62 +518,41 @@ __global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *_
             if (L.schedStride) issue_sched(descS[(k + 1) & 3], k + 1);   /* into the other buffer */
         }
         /* halo coordinates of the next unit: the node ids have normally landed while the records
-         * were built; then one node per thread goes to registers now and to shared memory after
-         * the tasks.  A thread that finds the copy still in flight does not wait here: it loads
-         * its node after the tasks. */
-        double hx0 = 0.0, hx1 = 0.0, hx2 = 0.0;
-        const bool early = hasNext && mbar_test(&bar[3], (uint32_t)(k + 1) & 1u);
-        if (early) {
+         * were built; then every thread starts the asynchronous copy of one node's coordinates
+         * into the other coordinate buffer now and it completes behind the tasks.  A thread that
+         * finds the bulk copy still in flight does not wait here: it copies its node after the
+         * tasks. */
+        auto copy_halo_node = [&](int i) {
             const dc_unit_t &nx = descS[(k + 1) & 3];
-            if (tid < nx.hnodeCount) {
-                const double *src = coord + (int64_t)hnode_of(k + 1)[tid] * 3;
-                hx0 = __ldg(src);
-                hx1 = __ldg(src + 1);
-                hx2 = __ldg(src + 2);
-            }
-        }
+            const int hSpan = ((nx.nodeFirst + nx.nodeCount + 1) & ~1) - (nx.nodeFirst & ~1);
+            const double *src = coord + (int64_t)hnode_of(k + 1)[i] * 3;
+            double *dst = coord_of(k + 1) + (hSpan + i) * 3;
+            cp_async_8(dst, src);
+            cp_async_8(dst + 1, src + 1);
+            cp_async_8(dst + 2, src + 2);
+        };
+        const bool early = hasNext && mbar_test(&bar[3], (uint32_t)(k + 1) & 1u);
+        if (early && tid < descS[(k + 1) & 3].hnodeCount) copy_halo_node(tid);
         DC_STAMP(unit, 3);
 
         run_tasks<Op, NW, SYM>(u, taskS, itemS, tgtS, recs, nextTask, myStage, diagRel, values, warp, lane);
         DC_STAMP(unit, 4);
         if (hasNext) {
             if (!early) mbar_wait(&bar[3], (uint32_t)(k + 1) & 1u);
-            const dc_unit_t &nx = descS[(k + 1) & 3];
-            const int hCnt = nx.hnodeCount;
-            const int hSpan = ((nx.nodeFirst + nx.nodeCount + 1) & ~1) - (nx.nodeFirst & ~1);
-            double *cn = coord_of(k + 1);
-            if (tid < hCnt) {
-                if (!early) {
-                    const double *src = coord + (int64_t)hnode_of(k + 1)[tid] * 3;
-                    hx0 = __ldg(src);
-                    hx1 = __ldg(src + 1);
-                    hx2 = __ldg(src + 2);
-                }
-                double *dst = cn + (hSpan + tid) * 3;
-                dst[0] = hx0;
-                dst[1] = hx1;
-                dst[2] = hx2;
-            }
+            const int hCnt = descS[(k + 1) & 3].hnodeCount;
+            if (!early && tid < hCnt) copy_halo_node(tid);
             /* the rare unit with more halo nodes than threads: chunks of 32, taken by the warps
              * that run out of tasks first */
             if (hCnt > THREADS) {
-                const int *hn = hnode_of(k + 1);
                 for (;;) {
                     int c = 0;
                     if (lane == 0) c = atomicAdd(nextHalo, 32);
                     c = __shfl_sync(0xffffffffu, c, 0);
                     if (c >= hCnt) break;
-                    const int i = c + lane;
-                    if (i < hCnt) {
-                        const double *src = coord + (int64_t)hn[i] * 3;
-                        const double x0 = __ldg(src), x1 = __ldg(src + 1), x2 = __ldg(src + 2);
-                        double *dst = cn + (hSpan + i) * 3;
-                        dst[0] = x0;
-                        dst[1] = x1;
-                        dst[2] = x2;
-                    }
+                    if (c + lane < hCnt) copy_halo_node(c + lane);
                 }
             }
+            cp_async_wait_all();
         }
         DC_STAMP(unit, 5);
         __syncthreads();   /* B: accumulation finished everywhere; schedule region is dead */
