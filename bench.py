@@ -333,7 +333,7 @@ def main():
         line["config"]["parallelism"] = (f"{world} slabs (one cube per GPU, stacked along x), interface-edge partial sums "
                                          "exchanged with NCCL send/recv and added by the unpack-add kernel")
         line["interface_bytes_per_step_per_gpu"] = exch.bytes_per_step
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # the CPU arm is reported at N = 1 only
         base = cpu_reference(dim, 3, 1)
         base.pop("ms_per_step")
         line["cpu_baseline"] = base
