@@ -340,11 +340,12 @@ __device__ __forceinline__ void run_tasks(const dc_unit_t &u, const dc_task_t *t
  *   records(k)   from the slot -> node table and the coordinate buffer of unit k
  *   sync A       records complete, the slot -> node table is dead: bulk copy of the table of unit
  *                k+1 (and of its schedule when that is double-buffered)
- *   halo(k+1)    every thread loads the coordinates of one halo node of unit k+1 into registers
- *                (the ids landed while the records were built) ...
+ *   halo(k+1)    every thread starts the asynchronous copy (cp.async) of one halo node's coordinates
+ *                of unit k+1 into the other coordinate buffer (the ids landed while the records
+ *                were built) ...
  *   tasks(k)     accumulate + store
- *                ... and writes them to the coordinate buffer of unit k+1 afterwards; nodes beyond
- *                the CTA size are gathered by the warps that run out of tasks first
+ *                ... which completes behind the tasks; nodes beyond the CTA size are copied by the
+ *                warps that run out of tasks first
  *   sync B       the schedule region is dead
  *
  * so no bulk-copy or gather latency sits between the tasks of one unit and the records of the
