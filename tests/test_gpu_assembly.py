@@ -416,3 +416,15 @@ def test_spmv_on_the_assembled_matrix(tmp_path, dim):
     torch.cuda.synchronize()
     assert float(y.abs().max()) <= 1e-10 * np.abs(v).max()            # K * (rigid translation) = 0
     ctx.close()
+
+
+def test_more_halo_nodes_than_threads(tmp_path):
+    """Large units on small CTAs: a unit's halo-node list is longer than the CTA (832-slot units,
+    128 threads), so the coordinates of the next unit are copied by the per-thread asynchronous copies
+    AND by the chunk loop of the warps that run out of tasks; several units per resident CTA."""
+    mesh = prepare_mesh(MineLib(0, geometric=True), 32, tmp_path)
+    ctx, plan = _ctx(mesh, slots=832)
+    assert plan.c.maxHalo > 128 and plan.c.nbUnits > 2 * 148
+    ctx.set_option("unit_threads", 128)
+    for dim in (3, 1):
+        assert _run(ctx, mesh, dim, dc.MODE_DETERMINISTIC).tobytes() == oracle_serial(mesh, dim).tobytes()
