@@ -96,7 +96,7 @@ def build_workload(dc, n, vec, builder, rank=0):
                 tree_s=t1 - t0, setup_s=time.time() - t0)
 
 
-def cpu_reference(dim, steps, warmup, n=128):
+def cpu_reference(dim, steps, warmup, n=int(os.environ.get("DC_BENCH_CPU_SAMPLE", "128"))):
     """The reference's own CPU path (oracle/_ref: the unmodified DC_tree_traversal, OpenMP tasks, all
     host threads) with the oracle's callbacks on a bounded sample of the workload: the n^3 jittered
     Kuhn cube, same operator, same tree builder as the GPU arm.  The tree is built by the product's
