@@ -416,6 +416,45 @@ struct BankOpt {
     }
 };
 
+/* int -> int map with open addressing for the per-unit lookups (element -> slot, column -> edge,
+ * node -> table entity): a few hundred keys, cleared per use */
+struct IntMap {
+    std::vector<int> key, val;
+    uint32_t mask = 0;
+    void reset(size_t n)
+    {
+        size_t cap = 16;
+        while (cap < 2 * n + 2) cap <<= 1;
+        if (key.size() != cap) { key.assign(cap, -1); val.resize(cap); }
+        else std::fill(key.begin(), key.end(), -1);
+        mask = (uint32_t)cap - 1;
+    }
+    static inline uint32_t hash(int k) { return (uint32_t)k * 2654435761u >> 7; }
+    /* slot of k: either holds k or is free (key -1) */
+    inline size_t probe(int k) const
+    {
+        size_t h = hash(k) & mask;
+        while (key[h] != k && key[h] != -1) h = (h + 1) & mask;
+        return h;
+    }
+    inline void put(int k, int v) { const size_t h = probe(k); key[h] = k; val[h] = v; }
+    inline int get(int k) const { const size_t h = probe(k); return key[h] == k ? val[h] : -1; }
+};
+
+/* per-thread work arrays of build_unit */
+struct Scratch {
+    IntMap elemSlot, colEdge, nodeEnt;
+    std::vector<int> pairK;            /* contributions in visiting order: edge (relative) ... */
+    std::vector<uint16_t> pairItem;    /* ... and item */
+    std::vector<int> edgePtr;          /* items of edge k: edgeItems[edgePtr[k] .. edgePtr[k+1]) */
+    std::vector<uint16_t> edgeItems;
+    std::vector<int> fill;
+    std::vector<char> isDiag;
+    std::vector<int> outside, nodeOf, fixedCls, cls, tableIdx, newSlot;
+    inline int count(int k) const { return edgePtr[(size_t)k + 1] - edgePtr[(size_t)k]; }
+    inline const uint16_t *items(int k) const { return edgeItems.data() + edgePtr[(size_t)k]; }
+};
+
 /* edge index of (rowNode, colNode) */
 inline int find_edge(const Mesh &m, int rowNode, int colNode)
 {
@@ -433,40 +472,53 @@ inline int slot_of(const UnitSeed &s, int e)
 
 /* items of every edge of the unit, grouped per edge in ascending element order */
 void build_tasks(const Mesh &m, const UnitSeed &s, int32_t *diagRel, UnitOut &out,
-                 std::vector<std::vector<uint16_t>> &perEdge, int &error, bool symmetric)
+                 Scratch &w, int &error, bool symmetric)
 {
     const int64_t edgeFirst = m.row[s.nodeFirst];
     const int edgeCount = m.row[s.nodeFirst + s.nodeCount] - (int)edgeFirst;
-    if ((int)perEdge.size() < edgeCount) perEdge.resize((size_t)edgeCount);
-    for (int k = 0; k < edgeCount; k++) perEdge[k].clear();
-    std::vector<char> isDiag((size_t)edgeCount, 0);
+    w.isDiag.assign((size_t)edgeCount, 0);
+    w.edgePtr.assign((size_t)edgeCount + 1, 0);
+    w.pairK.clear();
+    w.pairItem.clear();
     /* padding of the item rows: slot nSlots is the kernel's all-zero record */
     const uint16_t padItem = (uint16_t)((s.ownCount + (int)s.halo.size()) << 4);
+    w.elemSlot.reset(s.halo.size());
+    for (size_t h = 0; h < s.halo.size(); h++) w.elemSlot.put(s.halo[h], s.ownCount + (int)h);
 
+    /* a row is visited once, its incident elements in ascending order: the contributions of an
+     * edge come out in ascending element order */
     for (int n = s.nodeFirst; n < s.nodeFirst + s.nodeCount; n++) {
         const int r0 = m.row[n], r1 = m.row[n + 1];
         diagRel[n] = -1;
+        w.colEdge.reset((size_t)(r1 - r0));
+        for (int k = r1 - 1; k >= r0; k--) {               /* the first of equal columns wins, as a forward search would */
+            const int c = m.col[k] - m.colBase;
+            w.colEdge.put(c, (int)(k - edgeFirst));
+            if (c == n) w.isDiag[(size_t)(k - edgeFirst)] = 1;
+        }
         for (int k = r0; k < r1; k++)
-            if (m.col[k] - m.colBase == n) {
-                diagRel[n] = (int)(k - edgeFirst);
-                isDiag[(size_t)(k - edgeFirst)] = 1;
-            }
+            if (m.col[k] - m.colBase == n) diagRel[n] = (int)(k - edgeFirst);
         for (int64_t q = m.n2ePtr[n]; q < m.n2ePtr[(size_t)n + 1]; q++) {
             const int e = m.n2eVal[(size_t)q];
             const int *c = m.conn + (int64_t)e * 4;
             int a = 0;
             while (a < 4 && c[a] - 1 != n) a++;
-            const int slot = slot_of(s, e);
+            const int slot = (e >= s.ownFirst && e < s.ownFirst + s.ownCount) ? e - s.ownFirst : w.elemSlot.get(e);
             for (int b = 0; b < 4; b++) {
                 if (symmetric && c[b] - 1 < n) continue;  /* lower edges are written as transposes */
-                const int target = c[b] - 1 + m.colBase;
-                int k = r0;
-                while (k < r1 && m.col[k] != target) k++;
-                if (k == r1) { error = 1; continue; }    /* pattern lacks an element edge */
-                perEdge[(size_t)(k - edgeFirst)].push_back((uint16_t)((slot << 4) | (a << 2) | b));
+                const int rel = w.colEdge.get(c[b] - 1);
+                if (rel < 0) { error = 1; continue; }     /* pattern lacks an element edge */
+                w.pairK.push_back(rel);
+                w.pairItem.push_back((uint16_t)((slot << 4) | (a << 2) | b));
+                w.edgePtr[(size_t)rel + 1]++;
             }
         }
     }
+    for (int k = 0; k < edgeCount; k++) w.edgePtr[(size_t)k + 1] += w.edgePtr[(size_t)k];
+    w.edgeItems.resize(w.pairK.size());
+    w.fill.assign(w.edgePtr.begin(), w.edgePtr.end() - 1);
+    for (size_t i = 0; i < w.pairK.size(); i++) w.edgeItems[(size_t)w.fill[(size_t)w.pairK[i]]++] = w.pairItem[i];
+    const std::vector<char> &isDiag = w.isDiag;
     if (symmetric) {
         /* owned edges = diagonal + upper edges (col > row) of the unit's rows.  Each becomes one
          * lane; an upper-edge lane also owns the transposed edge (col,row), wherever that row
@@ -485,7 +537,7 @@ void build_tasks(const Mesh &m, const UnitSeed &s, int32_t *diagRel, UnitOut &ou
                     if (kt < 0) { error = 1; continue; }      /* pattern is not structurally symmetric */
                 }
                 const int rel = (int)(k - edgeFirst);
-                owned.push_back(Owned{rel, k, kt, (int)perEdge[(size_t)rel].size()});
+                owned.push_back(Owned{rel, k, kt, w.count(rel)});
             }
         /* diagonals first (their own task kind: only one gradient per contribution, symmetric
          * block), then upper edges; inside each class by descending contribution count */
@@ -520,9 +572,10 @@ void build_tasks(const Mesh &m, const UnitSeed &s, int32_t *diagRel, UnitOut &ou
             out.items.resize(out.items.size() + iters * 32, padItem);
             uint16_t *dst = out.items.data() + t.itemRel;
             for (size_t l = 0; l < 32 && base + l < classEnd; l++) {
-                const std::vector<uint16_t> &v = perEdge[(size_t)owned[base + l].rel];
-                for (size_t i = 0; i < v.size(); i++) dst[i * 32 + l] = v[i];
-                out.useful += (int64_t)v.size();
+                const int rel = owned[base + l].rel, nv = w.count(rel);
+                const uint16_t *v = w.items(rel);
+                for (int i = 0; i < nv; i++) dst[(size_t)i * 32 + l] = v[i];
+                out.useful += nv;
             }
             out.tasks.push_back(t);
             if (diagTask && base + 32 > nbDiag) base = nbDiag - 32;      /* next task begins at the boundary */
@@ -538,20 +591,20 @@ void build_tasks(const Mesh &m, const UnitSeed &s, int32_t *diagRel, UnitOut &ou
         t.mask = 0;
         t.itemRel = (uint32_t)out.items.size();
         size_t iters = 0;
-        for (int l = 0; l < 32 && base + l < edgeCount; l++) iters = std::max(iters, perEdge[(size_t)(base + l)].size());
         for (int l = 0; l < 32 && base + l < edgeCount; l++)
             if (isDiag[(size_t)(base + l)]) t.mask |= 1u << l;
         iters = 0;
         for (int l = 0; l < 32 && base + l < edgeCount; l++)
-            if (!((t.mask >> l) & 1u)) iters = std::max(iters, perEdge[(size_t)(base + l)].size());
+            if (!((t.mask >> l) & 1u)) iters = std::max(iters, (size_t)w.count(base + l));
         t.iters = (uint16_t)iters;
         out.items.resize(out.items.size() + iters * 32, padItem);
         uint16_t *dst = out.items.data() + t.itemRel;
         for (int l = 0; l < 32 && base + l < edgeCount; l++) {
             if ((t.mask >> l) & 1u) continue;
-            const std::vector<uint16_t> &v = perEdge[(size_t)(base + l)];
-            for (size_t i = 0; i < v.size(); i++) dst[i * 32 + l] = v[i];
-            out.useful += (int64_t)v.size();
+            const int nv = w.count(base + l);
+            const uint16_t *v = w.items(base + l);
+            for (int i = 0; i < nv; i++) dst[(size_t)i * 32 + l] = v[i];
+            out.useful += nv;
         }
         out.tasks.push_back(t);
     }
@@ -568,16 +621,17 @@ void build_tasks(const Mesh &m, const UnitSeed &s, int32_t *diagRel, UnitOut &ou
             int d = diagRel[s.nodeFirst + base + l];
             if (d < 0) continue;
             t.mask |= 1u << l;
-            iters = std::max(iters, perEdge[(size_t)d].size());
+            iters = std::max(iters, (size_t)w.count(d));
         }
         t.iters = (uint16_t)iters;
         out.items.resize(out.items.size() + iters * 32, padItem);
         uint16_t *dst = out.items.data() + t.itemRel;
         for (int l = 0; l < 32 && base + l < s.nodeCount; l++) {
             if (!((t.mask >> l) & 1u)) continue;
-            const std::vector<uint16_t> &v = perEdge[(size_t)diagRel[s.nodeFirst + base + l]];
-            for (size_t i = 0; i < v.size(); i++) dst[i * 32 + l] = v[i];
-            out.useful += (int64_t)v.size();
+            const int d = diagRel[s.nodeFirst + base + l], nv = w.count(d);
+            const uint16_t *v = w.items(d);
+            for (int i = 0; i < nv; i++) dst[(size_t)i * 32 + l] = v[i];
+            out.useful += nv;
         }
         if (t.mask) diagTasks.push_back(t); else out.items.resize(t.itemRel);
     }
@@ -590,13 +644,12 @@ void build_tasks(const Mesh &m, const UnitSeed &s, int32_t *diagRel, UnitOut &ou
  * below nodeFirst, padded to an even count so that the block of coordinates is a 16-byte granule
  * copy), then the halo nodes; slotNodes in slot order */
 void build_unit(const Mesh &m, const UnitSeed &s, int32_t *diagRel, UnitOut &out,
-                std::vector<std::vector<uint16_t>> &perEdge, int &error, bool symmetric, BankOpt &opt,
-                bool bankAware)
+                Scratch &w, int &error, bool symmetric, BankOpt &opt, bool bankAware)
 {
-    build_tasks(m, s, diagRel, out, perEdge, error, symmetric);
+    build_tasks(m, s, diagRel, out, w, error, symmetric);
     if (error) return;
     const int nSlots = s.ownCount + (int)s.halo.size();
-    std::vector<int> newSlot;
+    std::vector<int> &newSlot = w.newSlot;
     if (bankAware) opt.run(out, nSlots, newSlot);
     else { newSlot.resize((size_t)nSlots); for (int q = 0; q < nSlots; q++) newSlot[(size_t)q] = q; }
     for (uint16_t &it : out.items) {
@@ -609,30 +662,39 @@ void build_unit(const Mesh &m, const UnitSeed &s, int32_t *diagRel, UnitOut &out
             sl < s.ownCount ? s.ownFirst + sl : s.halo[(size_t)(sl - s.ownCount)];
     const int alignedFirst = s.nodeFirst & ~1;
     const int ownSpan = ((s.nodeFirst + s.nodeCount + 1) & ~1) - alignedFirst;
-    std::vector<int> outside;
+    /* distinct nodes outside the own interval, ascending */
+    std::vector<int> &outside = w.outside;
+    outside.clear();
+    w.nodeEnt.reset((size_t)nSlots * 2 + 16);
     for (int sl = 0; sl < nSlots; sl++) {
         const int e = out.slotElems[(size_t)sl];
         for (int j = 0; j < 4; j++) {
             const int nd = m.conn[(int64_t)e * 4 + j] - 1;
-            if (nd < s.nodeFirst || nd >= s.nodeFirst + s.nodeCount) outside.push_back(nd);
+            if (nd >= s.nodeFirst && nd < s.nodeFirst + s.nodeCount) continue;
+            const size_t h = w.nodeEnt.probe(nd);
+            if (w.nodeEnt.key[h] == nd) continue;
+            w.nodeEnt.key[h] = nd;
+            outside.push_back(nd);
         }
     }
     std::sort(outside.begin(), outside.end());
-    outside.erase(std::unique(outside.begin(), outside.end()), outside.end());
     const int nHalo = (int)outside.size();
     if (ownSpan + nHalo > 65535) { error = 1; return; }
+    for (int x = 0; x < nHalo; x++) w.nodeEnt.val[w.nodeEnt.probe(outside[(size_t)x])] = ownSpan + x;
     /* entity = own node (table index fixed) or halo node (position chosen for the banks) */
-    std::vector<int> nodeOf((size_t)nSlots * 4), fixedCls((size_t)(ownSpan + nHalo), -1), cls;
+    std::vector<int> &nodeOf = w.nodeOf, &fixedCls = w.fixedCls, &cls = w.cls, &tableIdx = w.tableIdx;
+    nodeOf.resize((size_t)nSlots * 4);
+    fixedCls.assign((size_t)(ownSpan + nHalo), -1);
     for (int x = 0; x < ownSpan; x++) fixedCls[(size_t)x] = (16 - (x & 15)) & 15;
     for (int sl = 0; sl < nSlots; sl++) {
         const int e = out.slotElems[(size_t)sl];
         for (int j = 0; j < 4; j++) {
             const int nd = m.conn[(int64_t)e * 4 + j] - 1;
             if (nd >= s.nodeFirst && nd < s.nodeFirst + s.nodeCount) nodeOf[(size_t)sl * 4 + j] = nd - alignedFirst;
-            else nodeOf[(size_t)sl * 4 + j] = ownSpan + (int)(std::lower_bound(outside.begin(), outside.end(), nd) - outside.begin());
+            else nodeOf[(size_t)sl * 4 + j] = w.nodeEnt.get(nd);
         }
     }
-    std::vector<int> tableIdx((size_t)(ownSpan + nHalo));
+    tableIdx.resize((size_t)(ownSpan + nHalo));
     for (int x = 0; x < ownSpan + nHalo; x++) tableIdx[(size_t)x] = x;
     if (bankAware && nHalo > 16) {
         opt.run_nodes(nodeOf, nSlots, ownSpan + nHalo, fixedCls, ownSpan, nHalo, cls);
@@ -804,7 +866,7 @@ extern "C" int dc_plan_build(dc_plan_t *plan, const int *conn, int nbElem, int n
         const int tid = omp_get_thread_num();
         UnitOut out;
         BankOpt opt;
-        std::vector<std::vector<uint16_t>> perEdge;
+        Scratch work;
         #pragma omp for schedule(dynamic, 64)
         for (int64_t u = 0; u < nbUnits; u++) {
             const UnitSeed &s = seeds[(size_t)u];
@@ -815,7 +877,7 @@ extern "C" int dc_plan_build(dc_plan_t *plan, const int *conn, int nbElem, int n
             out.haloNodes.clear();
             out.slotElems.clear();
             out.useful = 0;
-            build_unit(m, s, diagRel.data(), out, perEdge, error, symmetric != 0, opt, bankAware);
+            build_unit(m, s, diagRel.data(), out, work, error, symmetric != 0, opt, bankAware);
             const int32_t nbUpper = (int32_t)(out.tgt.size() / 2);
             while (out.tgt.size() % 4) out.tgt.push_back(0);      /* 16-byte granules for the bulk copy */
             dc_unit_t &d = units[(size_t)u];
