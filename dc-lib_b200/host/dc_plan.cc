@@ -24,6 +24,31 @@ struct Mesh {
     std::vector<int> n2eVal;   /* incident elements of each node, ascending */
 };
 
+/* int -> int map with open addressing for the per-unit lookups (element -> slot, column -> edge,
+ * node -> table entity): a few hundred keys, cleared per use */
+struct IntMap {
+    std::vector<int> key, val;
+    uint32_t mask = 0;
+    void reset(size_t n)
+    {
+        size_t cap = 16;
+        while (cap < 2 * n + 2) cap <<= 1;
+        if (key.size() != cap) { key.assign(cap, -1); val.resize(cap); }
+        else std::fill(key.begin(), key.end(), -1);
+        mask = (uint32_t)cap - 1;
+    }
+    static inline uint32_t hash(int k) { return (uint32_t)k * 2654435761u >> 7; }
+    /* slot of k: either holds k or is free (key -1) */
+    inline size_t probe(int k) const
+    {
+        size_t h = hash(k) & mask;
+        while (key[h] != k && key[h] != -1) h = (h + 1) & mask;
+        return h;
+    }
+    inline void put(int k, int v) { const size_t h = probe(k); key[h] = k; val[h] = v; }
+    inline int get(int k) const { const size_t h = probe(k); return key[h] == k ? val[h] : -1; }
+};
+
 void build_node_to_elem(Mesh &m)
 {
     const int64_t nc = (int64_t)m.nbElem * 4;
@@ -98,23 +123,33 @@ struct Selector {
     std::vector<TreeIdx> tree;
     std::vector<std::vector<UnitSeed>> seedsT;
     std::vector<std::vector<int>> bigT;
+    std::vector<IntMap> seenT;
 
-    /* rows [nodeFirst, nodeFirst+nodeCount) without a usable subtree: cut greedily */
+    /* rows [nodeFirst, nodeFirst+nodeCount) without a usable subtree: cut greedily -- a piece takes
+     * rows while the distinct elements they touch fit the slot budget */
     void split_rows(int nodeFirst, int nodeCount)
     {
         const int tid = omp_get_thread_num();
+        IntMap &seen = seenT[(size_t)tid];
         int start = nodeFirst, end = nodeFirst + nodeCount;
+        std::vector<int> acc;
         while (start < end) {
             int stop = start;
-            std::vector<int> acc;
+            acc.clear();
+            seen.reset((size_t)maxSlots);
             while (stop < end) {
-                std::vector<int> trial(acc);
-                for (int64_t k = m.n2ePtr[stop]; k < m.n2ePtr[(size_t)stop + 1]; k++)
-                    trial.push_back(m.n2eVal[(size_t)k]);
-                std::sort(trial.begin(), trial.end());
-                trial.erase(std::unique(trial.begin(), trial.end()), trial.end());
-                if ((int)trial.size() > maxSlots) break;
-                acc.swap(trial);
+                const size_t before = acc.size();
+                for (int64_t k = m.n2ePtr[stop]; k < m.n2ePtr[(size_t)stop + 1] && (int)acc.size() <= maxSlots; k++) {
+                    const int e = m.n2eVal[(size_t)k];
+                    const size_t h = seen.probe(e);
+                    if (seen.key[h] == e) continue;
+                    seen.key[h] = e;
+                    acc.push_back(e);
+                }
+                if ((int)acc.size() > maxSlots) {              /* the row does not fit: the piece ends before it */
+                    acc.resize(before);
+                    break;
+                }
                 stop++;
             }
             if (stop == start) {           /* a single row exceeds the slot budget */
@@ -122,8 +157,9 @@ struct Selector {
                 start++;
                 continue;
             }
+            std::sort(acc.begin(), acc.end());
             UnitSeed s{start, stop - start, 0, 0, {}};
-            s.halo.swap(acc);
+            s.halo = acc;
             seedsT[tid].push_back(std::move(s));
             start = stop;
         }
@@ -414,31 +450,6 @@ struct BankOpt {
         for (int p = 0; p < nHalo; p++) cap[(16 - ((ownSpan + p) & 15)) & 15]++;
         greedy(nEnt, nbGroups, fixedCls.data(), cap, cls);
     }
-};
-
-/* int -> int map with open addressing for the per-unit lookups (element -> slot, column -> edge,
- * node -> table entity): a few hundred keys, cleared per use */
-struct IntMap {
-    std::vector<int> key, val;
-    uint32_t mask = 0;
-    void reset(size_t n)
-    {
-        size_t cap = 16;
-        while (cap < 2 * n + 2) cap <<= 1;
-        if (key.size() != cap) { key.assign(cap, -1); val.resize(cap); }
-        else std::fill(key.begin(), key.end(), -1);
-        mask = (uint32_t)cap - 1;
-    }
-    static inline uint32_t hash(int k) { return (uint32_t)k * 2654435761u >> 7; }
-    /* slot of k: either holds k or is free (key -1) */
-    inline size_t probe(int k) const
-    {
-        size_t h = hash(k) & mask;
-        while (key[h] != k && key[h] != -1) h = (h + 1) & mask;
-        return h;
-    }
-    inline void put(int k, int v) { const size_t h = probe(k); key[h] = k; val[h] = v; }
-    inline int get(int k) const { const size_t h = probe(k); return key[h] == k ? val[h] : -1; }
 };
 
 /* per-thread work arrays of build_unit */
@@ -796,9 +807,10 @@ extern "C" int dc_plan_build(dc_plan_t *plan, const int *conn, int nbElem, int n
 
     lap("node->elem");
     const int nt = nbThreads > 0 ? nbThreads : omp_get_max_threads();
-    Selector sel{m, maxSlots, {}, {}, {}};
+    Selector sel{m, maxSlots, {}, {}, {}, {}};
     sel.seedsT.resize((size_t)nt);
     sel.bigT.resize((size_t)nt);
+    sel.seenT.resize((size_t)nt);
     if (treeRec && nbTreeRec > 0) {
         int64_t cursor = 0;
         index_tree(treeRec, nbTreeRec, cursor, sel.tree, true);
