@@ -96,7 +96,19 @@ def build_workload(dc, n, vec, builder, rank=0):
                 tree_s=t1 - t0, setup_s=time.time() - t0)
 
 
-def cpu_reference(dim, steps, warmup, n=int(os.environ.get("DC_BENCH_CPU_SAMPLE", "128"))):
+def leaf_capacity(n, leaf_nodes):
+    """MAX_ELEM_PER_PART (the reference's leaf capacity, DC.h:24, a tuning constant of the tree) that
+    makes the D&C leaves of the n^3 Kuhn cube hold about leaf_nodes nodes: DC_create_tree cuts the
+    nodes into ceil(E / capacity) parts and stops the recursion at two parts per leaf.  The north
+    star asks for CTA-sized leaves: a 62-node leaf splits evenly into two 512-slot work units of at
+    most 32 rows, i.e. exactly one 32-lane diagonal task each (host/dc_plan.cc split_leaf).
+    leaf_nodes = 0 keeps the reference's default of 200."""
+    if leaf_nodes <= 0:
+        return 200
+    return max(8, int(leaf_nodes / 2 * (6 * n ** 3) / (n + 1) ** 3))
+
+
+def cpu_reference(dim, steps, warmup, n=int(os.environ.get("DC_BENCH_CPU_SAMPLE", "128")), leaf_nodes=0):
     """The reference's own CPU path (oracle/_ref: the unmodified DC_tree_traversal, OpenMP tasks, all
     host threads) with the oracle's callbacks on a bounded sample of the workload: the n^3 jittered
     Kuhn cube, same operator, same tree builder as the GPU arm.  The tree is built by the product's
@@ -118,6 +130,7 @@ def cpu_reference(dim, steps, warmup, n=int(os.environ.get("DC_BENCH_CPU_SAMPLE"
     conn, coord, N = dc.kuhn_cube_fast(n)
     E = conn.shape[0]
     dc.DC_set_vec_size(0)
+    dc.DC_set_max_elem_per_part(leaf_capacity(n, leaf_nodes))      # same kind of tree as the GPU arm
     dc.DC_create_tree_geometric(conn, E, 4, N, coord)
     dc.DC_permute_double_2d_array(coord, N, 3)
     dc.DC_renumber_int_array(conn.reshape(-1), 4 * E)
@@ -152,7 +165,8 @@ def cpu_reference(dim, steps, warmup, n=int(os.environ.get("DC_BENCH_CPU_SAMPLE"
     return {"value": E / (ms * 1e-3), "unit": "elements/s", "cores": cores, "kind": kind,
             "sample": f"{n}^3 jittered Kuhn cube ({E} tets), operatorDim {dim}, "
                       f"{'unmodified reference DC_tree_traversal (OpenMP tasks)' if kind == 'reference' else 'oracle serial loop'} "
-                      f"with the oracle's callbacks over a coordinate-bisection D&C tree handed over as a tree file, "
+                      f"with the oracle's callbacks over a coordinate-bisection D&C tree (leaf capacity "
+                      f"{leaf_capacity(n, leaf_nodes)}) handed over as a tree file, "
                       f"traversal only, mean of {steps} after {warmup} warm-up", "ms_per_step": ms}
 
 
@@ -167,6 +181,9 @@ def main():
                     help="element slots per work unit; 0 = the measured best for the operator")
     ap.add_argument("--threads", type=int, default=int(os.environ.get("DC_BENCH_THREADS", "0")),
                     help="threads per CTA of the unit kernel; 0 = the measured best for the operator")
+    ap.add_argument("--leaf-nodes", type=int, default=int(os.environ.get("DC_BENCH_LEAF_NODES", "-1")),
+                    help="nodes per D&C leaf (sets the tree's leaf capacity, see leaf_capacity()); 0 = the reference's "
+                         "default capacity of 200 elements; -1 = 62 for elasticity on coordinate-bisection trees, else 0")
     ap.add_argument("--persistent", type=int, default=int(os.environ.get("DC_BENCH_PERSISTENT", "1")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verify", action="store_true",
@@ -180,6 +197,9 @@ def main():
     best_slots, best_threads = (512, 256) if dim == 3 else (1536, 512)
     args.slots = args.slots or best_slots
     args.threads = args.threads or best_threads
+    if args.leaf_nodes < 0:
+        args.leaf_nodes = 62 if (dim == 3 and builder == "geometric") else 0
+    capacity = leaf_capacity(n, args.leaf_nodes)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -189,13 +209,14 @@ def main():
                           f"({'METIS node partitions' if builder == 'metis' else 'coordinate-bisection node partitions'}), "
                           "reset + assembly per step",
               "mode": "deterministic", "unit_slots": args.slots, "unit_threads": args.threads,
+              "max_elem_per_part": capacity,
               "l2": "value arrays larger than L2 (no flush needed)" if 6 * n ** 3 * 2.5 * dim * dim * 8 > 2.5e8
                     else "working set fits L2; see roofline note"}
 
     if args.impl == "reference":
         if rank != 0:
             return
-        base = cpu_reference(dim, max(args.steps, 1), max(args.warmup, 1))
+        base = cpu_reference(dim, max(args.steps, 1), max(args.warmup, 1), leaf_nodes=args.leaf_nodes)
         line = {"impl": "reference", "metric": "assembled elements/s (fp64, CSR scatter-add)", "value": base["value"],
                 "unit": "elements/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": base.pop("ms_per_step"), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -220,6 +241,7 @@ def main():
     device = f"cuda:{local}"
 
     # one slab (cube) per GPU; rank 0 builds tree / CSR / schedule, the others get them over NCCL
+    dc.DC_set_max_elem_per_part(capacity)
     ctx, info = multigpu.setup_device_slabs(n, rank, world, device, builder=builder, vec=vec, slots=args.slots, dist=dist)
     ctx.set_option("unit_threads", args.threads)
     ctx.set_option("persistent", args.persistent)
@@ -334,7 +356,7 @@ def main():
                                          "exchanged with NCCL send/recv and added by the unpack-add kernel")
         line["interface_bytes_per_step_per_gpu"] = exch.bytes_per_step
     if not args.no_cpu_baseline and world == 1:      # the CPU arm is reported at N = 1 only
-        base = cpu_reference(dim, 3, 1)
+        base = cpu_reference(dim, 3, 1, leaf_nodes=args.leaf_nodes)
         base.pop("ms_per_step")
         line["cpu_baseline"] = base
     print(json.dumps(line), flush=True)

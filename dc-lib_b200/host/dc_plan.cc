@@ -124,6 +124,7 @@ struct Selector {
     std::vector<std::vector<UnitSeed>> seedsT;
     std::vector<std::vector<int>> bigT;
     std::vector<IntMap> seenT;
+    bool evenSplit = true;
 
     /* rows [nodeFirst, nodeFirst+nodeCount) without a usable subtree: cut greedily -- a piece takes
      * rows while the distinct elements they touch fit the slot budget */
@@ -165,6 +166,33 @@ struct Selector {
         }
     }
 
+    /* A leaf that is too big for one unit.  The greedy cut fills the first pieces and leaves a short
+     * last one; a piece of more than 32 rows needs a second diagonal task that is mostly padding
+     * (24 iterations for a few lanes).  When the same number of pieces can be had with at most 32
+     * rows each, cut evenly instead: every piece then has exactly one diagonal task. */
+    void split_leaf(int nodeFirst, int nodeCount)
+    {
+        const int tid = omp_get_thread_num();
+        const size_t seeds0 = seedsT[tid].size(), big0 = bigT[tid].size();
+        split_rows(nodeFirst, nodeCount);
+        const int k = (int)(seedsT[tid].size() - seeds0);
+        if (!evenSplit || bigT[tid].size() != big0 || k < 2 || (nodeCount + k - 1) / k > 32) return;
+        std::vector<UnitSeed> pieces;
+        int start = nodeFirst;
+        for (int p = 0; p < k; p++) {
+            const int cnt = nodeCount / k + (p < nodeCount % k ? 1 : 0);
+            UnitSeed s{start, cnt, 0, 0, {}};
+            s.halo.assign(m.n2eVal.begin() + m.n2ePtr[start], m.n2eVal.begin() + m.n2ePtr[(size_t)start + cnt]);
+            std::sort(s.halo.begin(), s.halo.end());
+            s.halo.erase(std::unique(s.halo.begin(), s.halo.end()), s.halo.end());
+            if ((int)s.halo.size() > maxSlots) return;         /* an even piece does not fit: keep the greedy cut */
+            pieces.push_back(std::move(s));
+            start += cnt;
+        }
+        seedsT[tid].resize(seeds0);
+        for (UnitSeed &s : pieces) seedsT[tid].push_back(std::move(s));
+    }
+
     /* Pack consecutive non-separator leaves (their node intervals are adjacent, in ascending
      * node order) into units until the slot budget is full.  Unlike whole subtrees, whose sizes
      * jump by factors of two, this fills the budget, which lowers the halo ratio. */
@@ -191,7 +219,7 @@ struct Selector {
             leafSet.erase(std::unique(leafSet.begin(), leafSet.end()), leafSet.end());
             if ((int)leafSet.size() > maxSlots) {          /* a leaf too big on its own: cut by rows */
                 flush();
-                split_rows(nf, nc);
+                split_leaf(nf, nc);
                 continue;
             }
             if (curCount > 0 && curFirst + curCount == nf) {
@@ -263,7 +291,7 @@ struct Selector {
             }
         }
         if (t.isLeaf) {
-            if (nodes > 0) split_rows(t.firstNode, nodes);
+            if (nodes > 0) split_leaf(t.firstNode, nodes);
             return;
         }
         #pragma omp task default(shared) if (own > 20000)
@@ -807,10 +835,11 @@ extern "C" int dc_plan_build(dc_plan_t *plan, const int *conn, int nbElem, int n
 
     lap("node->elem");
     const int nt = nbThreads > 0 ? nbThreads : omp_get_max_threads();
-    Selector sel{m, maxSlots, {}, {}, {}, {}};
+    Selector sel{m, maxSlots, {}, {}, {}, {}, true};
     sel.seedsT.resize((size_t)nt);
     sel.bigT.resize((size_t)nt);
     sel.seenT.resize((size_t)nt);
+    if (const char *g = getenv("DC_PLAN_GREEDY_SPLIT")) sel.evenSplit = !(*g && *g != '0');
     if (treeRec && nbTreeRec > 0) {
         int64_t cursor = 0;
         index_tree(treeRec, nbTreeRec, cursor, sel.tree, true);

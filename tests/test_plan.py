@@ -25,6 +25,44 @@ def test_plan_covers_every_contribution_once(tmp_path, n, vec, slots, hub, sym):
     mesh = prepare_mesh(MineLib(vec), n, tmp_path, hub=hub)
     rec = tree_records(mesh)
     plan = dc.HostPlan(mesh["conn"], mesh["N"], mesh["row"], mesh["col"], 0, rec, slots, symmetric=sym)
+    check_plan(mesh, plan, slots, sym)
+
+
+@pytest.mark.parametrize("sym", [True, False])
+def test_leaves_sized_for_the_unit_budget_split_evenly(tmp_path, sym):
+    """bench.py's elasticity trees: leaf capacity chosen so that a leaf has about 62 nodes (two node
+    parts); such a leaf exceeds the 512-slot budget and is cut into two pieces of at most 32 rows --
+    one full diagonal task per unit in the symmetric schedule -- instead of a greedy 40 + 22."""
+    import bench
+    n = 20
+    dc.DC_set_max_elem_per_part(bench.leaf_capacity(n, 62))
+    try:
+        mesh = prepare_mesh(MineLib(0, geometric=True), n, tmp_path)
+    finally:
+        dc.DC_set_max_elem_per_part(200)
+    rec = tree_records(mesh)
+    plan = dc.HostPlan(mesh["conn"], mesh["N"], mesh["row"], mesh["col"], 0, rec, 512, symmetric=sym)
+    check_plan(mesh, plan, 512, sym)
+    units, tasks, _, _ = _plan_arrays(plan)
+    leaves = rec[(rec[:, 6] != 0) & (rec[:, 5] == 0)]
+    assert ((leaves[:, 4] - leaves[:, 3] + 1) <= 64).mean() > 0.9          # the capacity does what bench.py wants
+    rows = np.array([u.nodeCount for u in units])
+    assert (rows <= 32).mean() > 0.9
+    if sym:
+        diag_tasks = sum(1 for t in tasks if t.kind == 3)
+        assert diag_tasks <= 1.1 * len(units)
+    # the greedy cut (DC_PLAN_GREEDY_SPLIT=1) is still a valid schedule, with more padding
+    import os
+    os.environ["DC_PLAN_GREEDY_SPLIT"] = "1"
+    try:
+        greedy = dc.HostPlan(mesh["conn"], mesh["N"], mesh["row"], mesh["col"], 0, rec, 512, symmetric=sym)
+    finally:
+        del os.environ["DC_PLAN_GREEDY_SPLIT"]
+    if sym:
+        assert greedy.c.nbItems > plan.c.nbItems and greedy.c.nbItemsUseful == plan.c.nbItemsUseful
+
+
+def check_plan(mesh, plan, slots, sym):
     units, tasks, items, slot_elems = _plan_arrays(plan)
     tgt = np.ctypeslib.as_array(plan.c.tgt, shape=(max(plan.c.nbTgt, 1), 2))
     slotNodes = np.ctypeslib.as_array(plan.c.slotNodes, shape=(max(plan.c.nbSlotNodes, 1),))

@@ -86,8 +86,12 @@ def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 32
     slots = int(sys.argv[2]) if len(sys.argv) > 2 else 512
     dim = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+    # optional: tree builder ("metis" as the reference, "geometric" as the bench) and leaf capacity
+    builder = sys.argv[4] if len(sys.argv) > 4 else "metis"
+    if len(sys.argv) > 5:
+        dc.DC_set_max_elem_per_part(int(sys.argv[5]))
     with tempfile.TemporaryDirectory() as tmp:
-        mesh = common.prepare_mesh(common.MineLib(0), n, tmp)
+        mesh = common.prepare_mesh(common.MineLib(0, geometric=builder == "geometric"), n, tmp)
     rec = common.tree_records(mesh)
     plan = dc.HostPlan(mesh["conn"], mesh["N"], mesh["row"], mesh["col"], 0, rec, slots, symmetric=True)
     A = plan.arrays()
