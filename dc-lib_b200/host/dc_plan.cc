@@ -969,32 +969,30 @@ extern "C" int dc_plan_build(dc_plan_t *plan, const int *conn, int nbElem, int n
     plan->nbHaloNodes = hnodeBase[nt];
     plan->haloNodes = (int32_t *)malloc(sizeof(int32_t) * (size_t)(plan->nbHaloNodes ? plan->nbHaloNodes : 1));
     plan->slotElems = (int32_t *)malloc(sizeof(int32_t) * (size_t)(slotBase[nt] ? slotBase[nt] : 1));
+    plan->tgt = (int32_t *)malloc(sizeof(int32_t) * 2 * (size_t)(tgtBase[nt] ? tgtBase[nt] : 1));
+    plan->tasks = (dc_task_t *)malloc(sizeof(dc_task_t) * (size_t)(taskBase[nt] ? taskBase[nt] : 1));
+    plan->items = (uint16_t *)malloc(sizeof(uint16_t) * (size_t)(itemBase[nt] ? itemBase[nt] : 1));
+    /* every thread's pieces go to their place in the final arrays (disjoint ranges: copied in parallel) */
+    #pragma omp parallel for schedule(static, 1) num_threads(nt)
     for (int t = 0; t < nt; t++) {
         if (!tSlot[t].empty()) memcpy(plan->slotNodes + 4 * slotBase[t], tSlot[t].data(), sizeof(uint16_t) * tSlot[t].size());
         if (!tSlotElem[t].empty()) memcpy(plan->slotElems + slotBase[t], tSlotElem[t].data(), sizeof(int32_t) * tSlotElem[t].size());
-        std::vector<int32_t>().swap(tSlotElem[t]);
         if (!tHnode[t].empty()) memcpy(plan->haloNodes + hnodeBase[t], tHnode[t].data(), sizeof(int32_t) * tHnode[t].size());
-        std::vector<uint16_t>().swap(tSlot[t]);
-        std::vector<int32_t>().swap(tHnode[t]);
-    }
-    plan->symmetric = symmetric ? 1 : 0;
-    plan->nbTgt = tgtBase[nt];
-    plan->tgt = (int32_t *)malloc(sizeof(int32_t) * 2 * (size_t)(plan->nbTgt ? plan->nbTgt : 1));
-    for (int t = 0; t < nt; t++) {
         if (!tTgt[t].empty()) memcpy(plan->tgt + 2 * tgtBase[t], tTgt[t].data(), sizeof(int32_t) * tTgt[t].size());
-        std::vector<int32_t>().swap(tTgt[t]);
-    }
-    if (taskBase[nt] >= INT32_MAX) return -4;
-    plan->nbTasks = taskBase[nt];
-    plan->nbItems = itemBase[nt];
-    plan->tasks = (dc_task_t *)malloc(sizeof(dc_task_t) * (size_t)(plan->nbTasks ? plan->nbTasks : 1));
-    plan->items = (uint16_t *)malloc(sizeof(uint16_t) * (size_t)(plan->nbItems ? plan->nbItems : 1));
-    for (int t = 0; t < nt; t++) {
         if (!tTasks[t].empty()) memcpy(plan->tasks + taskBase[t], tTasks[t].data(), sizeof(dc_task_t) * tTasks[t].size());
         if (!tItems[t].empty()) memcpy(plan->items + itemBase[t], tItems[t].data(), sizeof(uint16_t) * tItems[t].size());
+        std::vector<int32_t>().swap(tSlotElem[t]);
+        std::vector<uint16_t>().swap(tSlot[t]);
+        std::vector<int32_t>().swap(tHnode[t]);
+        std::vector<int32_t>().swap(tTgt[t]);
         std::vector<dc_task_t>().swap(tTasks[t]);
         std::vector<uint16_t>().swap(tItems[t]);
     }
+    plan->symmetric = symmetric ? 1 : 0;
+    plan->nbTgt = tgtBase[nt];
+    if (taskBase[nt] >= INT32_MAX) return -4;
+    plan->nbTasks = taskBase[nt];
+    plan->nbItems = itemBase[nt];
     int64_t haloTotal = 0, slotsTotal = 0;
     int maxUsed = 0, maxHalo = 0, maxTasks = 0, maxItems = 0, maxTgt = 0, maxNodes = 0;
     for (int64_t u = 0; u < nbUnits; u++) {

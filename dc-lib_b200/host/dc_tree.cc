@@ -325,18 +325,24 @@ void TreeBuilder::sep_partitioning(tree_t *&tree, int firstSepElem, int lastSepE
     }
     /* separator-local node numbers in order of first appearance */
     std::vector<int> sepToNode((size_t)n * dimElem), localToGlobal;
-    std::unordered_map<int, int> localId;
-    localId.reserve((size_t)n * 2);
+    /* open-addressing table node -> local id (at most 4n keys, load <= 1/2) */
+    size_t cap = 16;
+    while (cap < (size_t)n * dimElem * 2) cap <<= 1;
+    std::vector<int> key(cap, -1), val(cap);
+    const size_t hmask = cap - 1;
     const int *rows = conn + (int64_t)firstSepElem * dimElem;
     for (int64_t k = 0; k < (int64_t)n * dimElem; k++) {
-        auto it = localId.find(rows[k]);
-        if (it == localId.end()) {
-            it = localId.emplace(rows[k], (int)localId.size()).first;
-            localToGlobal.push_back(rows[k]);
+        const int node = rows[k];
+        size_t h = ((uint32_t)node * 2654435761u >> 5) & hmask;
+        while (key[h] != node && key[h] != -1) h = (h + 1) & hmask;
+        if (key[h] == -1) {
+            key[h] = node;
+            val[h] = (int)localToGlobal.size();
+            localToGlobal.push_back(node);
         }
-        sepToNode[(size_t)k] = it->second;
+        sepToNode[(size_t)k] = val[h];
     }
-    const int nbSepNodes = (int)localId.size();
+    const int nbSepNodes = (int)localToGlobal.size();
 
     std::vector<int> nodePart;
     partition_nodes(nodePart, sepToNode.data(), n, nbSepNodes, nbSepPart, localToGlobal.data());
