@@ -489,7 +489,8 @@ struct Scratch {
     std::vector<uint16_t> edgeItems;
     std::vector<int> fill;
     std::vector<char> isDiag;
-    std::vector<int> outside, nodeOf, fixedCls, cls, tableIdx, newSlot;
+    std::vector<int> outside, nodeOf, fixedCls, cls, tableIdx, newSlot, regroup;
+    std::vector<int32_t> movedElems;
     inline int count(int k) const { return edgePtr[(size_t)k + 1] - edgePtr[(size_t)k]; }
     inline const uint16_t *items(int k) const { return edgeItems.data() + edgePtr[(size_t)k]; }
 };
@@ -683,7 +684,7 @@ void build_tasks(const Mesh &m, const UnitSeed &s, int32_t *diagRel, UnitOut &ou
  * below nodeFirst, padded to an even count so that the block of coordinates is a 16-byte granule
  * copy), then the halo nodes; slotNodes in slot order */
 void build_unit(const Mesh &m, const UnitSeed &s, int32_t *diagRel, UnitOut &out,
-                Scratch &w, int &error, bool symmetric, BankOpt &opt, bool bankAware)
+                Scratch &w, int &error, bool symmetric, BankOpt &opt, bool bankAware, int regroupPasses)
 {
     build_tasks(m, s, diagRel, out, w, error, symmetric);
     if (error) return;
@@ -691,10 +692,6 @@ void build_unit(const Mesh &m, const UnitSeed &s, int32_t *diagRel, UnitOut &out
     std::vector<int> &newSlot = w.newSlot;
     if (bankAware) opt.run(out, nSlots, newSlot);
     else { newSlot.resize((size_t)nSlots); for (int q = 0; q < nSlots; q++) newSlot[(size_t)q] = q; }
-    for (uint16_t &it : out.items) {
-        const int slot = it >> 4;
-        if (slot < nSlots) it = (uint16_t)((newSlot[(size_t)slot] << 4) | (it & 15));
-    }
     out.slotElems.assign((size_t)nSlots, -1);
     for (int sl = 0; sl < nSlots; sl++)
         out.slotElems[(size_t)newSlot[(size_t)sl]] =
@@ -722,29 +719,92 @@ void build_unit(const Mesh &m, const UnitSeed &s, int32_t *diagRel, UnitOut &out
     for (int x = 0; x < nHalo; x++) w.nodeEnt.val[w.nodeEnt.probe(outside[(size_t)x])] = ownSpan + x;
     /* entity = own node (table index fixed) or halo node (position chosen for the banks) */
     std::vector<int> &nodeOf = w.nodeOf, &fixedCls = w.fixedCls, &cls = w.cls, &tableIdx = w.tableIdx;
-    nodeOf.resize((size_t)nSlots * 4);
     fixedCls.assign((size_t)(ownSpan + nHalo), -1);
     for (int x = 0; x < ownSpan; x++) fixedCls[(size_t)x] = (16 - (x & 15)) & 15;
-    for (int sl = 0; sl < nSlots; sl++) {
-        const int e = out.slotElems[(size_t)sl];
-        for (int j = 0; j < 4; j++) {
-            const int nd = m.conn[(int64_t)e * 4 + j] - 1;
-            if (nd >= s.nodeFirst && nd < s.nodeFirst + s.nodeCount) nodeOf[(size_t)sl * 4 + j] = nd - alignedFirst;
-            else nodeOf[(size_t)sl * 4 + j] = w.nodeEnt.get(nd);
+    /* entities of the four nodes of every slot, in the current slot order */
+    auto entities = [&]() {
+        nodeOf.resize((size_t)nSlots * 4);
+        for (int sl = 0; sl < nSlots; sl++) {
+            const int e = out.slotElems[(size_t)sl];
+            for (int j = 0; j < 4; j++) {
+                const int nd = m.conn[(int64_t)e * 4 + j] - 1;
+                if (nd >= s.nodeFirst && nd < s.nodeFirst + s.nodeCount) nodeOf[(size_t)sl * 4 + j] = nd - alignedFirst;
+                else nodeOf[(size_t)sl * 4 + j] = w.nodeEnt.get(nd);
+            }
         }
-    }
-    tableIdx.resize((size_t)(ownSpan + nHalo));
-    for (int x = 0; x < ownSpan + nHalo; x++) tableIdx[(size_t)x] = x;
-    if (bankAware && nHalo > 16) {
-        opt.run_nodes(nodeOf, nSlots, ownSpan + nHalo, fixedCls, ownSpan, nHalo, cls);
-        /* positions ownSpan + p with (ownSpan + p) mod 16 == (16 - class) mod 16, in node order */
-        int nextPos[16];
-        for (int r = 0; r < 16; r++) nextPos[r] = ((r - ownSpan) % 16 + 16) % 16;      /* first p with that residue */
-        for (int x = ownSpan; x < ownSpan + nHalo; x++) {
-            const int r = (16 - cls[(size_t)x]) & 15;
-            tableIdx[(size_t)x] = ownSpan + nextPos[r];
-            nextPos[r] += 16;
+    };
+    /* table positions of the halo nodes for the current slot order */
+    auto place_halo = [&]() {
+        tableIdx.resize((size_t)(ownSpan + nHalo));
+        for (int x = 0; x < ownSpan + nHalo; x++) tableIdx[(size_t)x] = x;
+        if (bankAware && nHalo > 16) {
+            opt.run_nodes(nodeOf, nSlots, ownSpan + nHalo, fixedCls, ownSpan, nHalo, cls);
+            /* positions ownSpan + p with (ownSpan + p) mod 16 == (16 - class) mod 16, in node order */
+            int nextPos[16];
+            for (int r = 0; r < 16; r++) nextPos[r] = ((r - ownSpan) % 16 + 16) % 16;      /* first p with that residue */
+            for (int x = ownSpan; x < ownSpan + nHalo; x++) {
+                const int r = (16 - cls[(size_t)x]) & 15;
+                tableIdx[(size_t)x] = ownSpan + nextPos[r];
+                nextPos[r] += 16;
+            }
         }
+    };
+    entities();
+    place_halo();
+    if (bankAware && nHalo > 16 && nSlots > 32)
+        for (int pass = 0; pass < regroupPasses; pass++) {
+            /* The record reads fix a slot's CLASS (slot mod 16), not its rank inside the class, and
+             * the record build reads the coordinates of 16 consecutive slots -- one of every class
+             * -- per instruction.  Re-deal the ranks: group after group, every class contributes,
+             * out of its next few slots in element order (neighbouring elements share nodes, which
+             * are broadcasts), the one whose four nodes collide least with the table positions the
+             * group already reads; then the halo nodes are placed again for the new groups. */
+            std::vector<int> &perm = w.regroup;           /* current slot -> new slot */
+            perm.assign((size_t)nSlots, -1);
+            int head[16];
+            for (int c = 0; c < 16; c++) head[c] = c;      /* first slot of the class not yet dealt */
+            const int window = 8;
+            for (int base = 0; base < nSlots; base += 16) {
+                /* distinct table entities the group reads per node position j and bank residue */
+                int occ[4][16][16], nocc[4][16];
+                for (int j = 0; j < 4; j++)
+                    for (int r = 0; r < 16; r++) nocc[j][r] = 0;
+                for (int c = 0; c < 16 && base + c < nSlots; c++) {
+                    while (head[c] < nSlots && perm[(size_t)head[c]] >= 0) head[c] += 16;
+                    int best = -1, bestCost = 1 << 30, seen = 0;
+                    for (int cand = head[c]; cand < nSlots && seen < window; cand += 16) {
+                        if (perm[(size_t)cand] >= 0) continue;
+                        seen++;
+                        int cost = 0;
+                        for (int j = 0; j < 4; j++) {
+                            const int ent = nodeOf[(size_t)cand * 4 + j], r = tableIdx[(size_t)ent] & 15;
+                            bool present = false;
+                            for (int q = 0; q < nocc[j][r]; q++) present |= occ[j][r][q] == ent;
+                            if (!present) cost += nocc[j][r];       /* one more address on a bank that has nocc already */
+                        }
+                        if (cost < bestCost) { bestCost = cost; best = cand; }
+                        if (cost == 0) break;
+                    }
+                    perm[(size_t)best] = base + c;
+                    for (int j = 0; j < 4; j++) {
+                        const int ent = nodeOf[(size_t)best * 4 + j], r = tableIdx[(size_t)ent] & 15;
+                        bool present = false;
+                        for (int q = 0; q < nocc[j][r]; q++) present |= occ[j][r][q] == ent;
+                        if (!present) occ[j][r][nocc[j][r]++] = ent;
+                    }
+                }
+            }
+            std::vector<int32_t> &moved = w.movedElems;
+            moved.assign((size_t)nSlots, -1);
+            for (int sl = 0; sl < nSlots; sl++) moved[(size_t)perm[(size_t)sl]] = out.slotElems[(size_t)sl];
+            out.slotElems.swap(moved);
+            for (int sl = 0; sl < nSlots; sl++) newSlot[(size_t)sl] = perm[(size_t)newSlot[(size_t)sl]];
+            entities();
+            place_halo();
+        }
+    for (uint16_t &it : out.items) {
+        const int slot = it >> 4;
+        if (slot < nSlots) it = (uint16_t)((newSlot[(size_t)slot] << 4) | (it & 15));
     }
     out.haloNodes.assign((size_t)nHalo, 0);
     for (int x = ownSpan; x < ownSpan + nHalo; x++) out.haloNodes[(size_t)(tableIdx[(size_t)x] - ownSpan)] = outside[(size_t)(x - ownSpan)];
@@ -897,6 +957,11 @@ extern "C" int dc_plan_build(dc_plan_t *plan, const int *conn, int nbElem, int n
     std::vector<std::vector<int32_t>> tSlotElem((size_t)nt);
     const char *noBank = getenv("DC_PLAN_NO_BANK_NUMBERING");
     const bool bankAware = !(noBank && *noBank && *noBank != '0');
+    /* passes of the rank re-deal for the record build (DC_PLAN_REGROUP=0: slots keep the element
+     * order inside a class).  Modelled on the plan (tools/smem_model.py, 64^3 elasticity): coordinate
+     * reads of the record build 3.10 -> 2.81 wavefronts per element with one pass, no gain from more. */
+    const char *rg = getenv("DC_PLAN_REGROUP");
+    const int regroupPasses = rg ? atoi(rg) : 1;
     std::vector<std::vector<int32_t>> tHnode((size_t)nt);
     std::vector<int> unitThread((size_t)nbUnits);
     int error = 0;
@@ -918,7 +983,7 @@ extern "C" int dc_plan_build(dc_plan_t *plan, const int *conn, int nbElem, int n
             out.haloNodes.clear();
             out.slotElems.clear();
             out.useful = 0;
-            build_unit(m, s, diagRel.data(), out, work, error, symmetric != 0, opt, bankAware);
+            build_unit(m, s, diagRel.data(), out, work, error, symmetric != 0, opt, bankAware, regroupPasses);
             const int32_t nbUpper = (int32_t)(out.tgt.size() / 2);
             while (out.tgt.size() % 4) out.tgt.push_back(0);      /* 16-byte granules for the bulk copy */
             dc_unit_t &d = units[(size_t)u];
