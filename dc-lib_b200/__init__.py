@@ -105,6 +105,8 @@ def _declare(L):
     L.dc_cuda_sync.argtypes = [vp]
     L.dc_cuda_set_option.argtypes = [vp, c_char_p, c_int]
     L.dc_plan_build.argtypes = [POINTER(Plan), vp, c_int, c_int, vp, vp, c_int, vp, c_int64, c_int, c_int, c_int]
+    L.dc_plan_set_bank_model.argtypes = [c_int]
+    L.dc_plan_set_bank_model.restype = None
     L.dc_contrib_build.argtypes = [POINTER(ContribList), vp, c_int, c_int, vp, vp, c_int, vp, c_int64, c_int]
     L.dc_plan_free.argtypes = [POINTER(Plan)]
     L.dc_plan_free.restype = None
@@ -270,15 +272,22 @@ def flatten_tree():
 class HostPlan:
     """Owns a dc_plan_t built by dc_plan_build()."""
 
-    def __init__(self, conn, nbNodes, row, col, colBase, treeRec, maxSlots=400, nbThreads=0, symmetric=True):
-        """symmetric=True: every off-diagonal block is computed once, by the lane of the upper edge
+    def __init__(self, conn, nbNodes, row, col, colBase, treeRec, maxSlots=400, nbThreads=0, symmetric=True,
+                 bank_model=0):
+        """bank_model: record layout the slot numbering is optimised for (dc_plan_set_bank_model):
+        0 = node gradients (elasticity, default), 1 = 4x4 symmetric entries (P1 Laplacian).
+        symmetric=True: every off-diagonal block is computed once, by the lane of the upper edge
         (row < col), which also stores its transpose (operators with bitwise symmetric element
         matrices); False: one lane per edge, every unit writes exactly its own edge interval."""
         self.c = Plan()
         conn = np.ascontiguousarray(conn, dtype=np.int32)
         nrec = 0 if treeRec is None else treeRec.shape[0]
-        rc = lib().dc_plan_build(byref(self.c), _p(conn), conn.shape[0], nbNodes, _p(row), _p(col), colBase,
-                                 _p(treeRec), nrec, maxSlots, nbThreads, 1 if symmetric else 0)
+        lib().dc_plan_set_bank_model(int(bank_model))
+        try:
+            rc = lib().dc_plan_build(byref(self.c), _p(conn), conn.shape[0], nbNodes, _p(row), _p(col), colBase,
+                                     _p(treeRec), nrec, maxSlots, nbThreads, 1 if symmetric else 0)
+        finally:
+            lib().dc_plan_set_bank_model(0)
         if rc:
             raise RuntimeError(f"dc_plan_build failed with code {rc}")
 

@@ -117,6 +117,11 @@ int  dc_plan_build(dc_plan_t *plan, const int *conn, int nbElem, int nbNodes, co
 int  dc_contrib_build(dc_contrib_list_t *out, const int *conn, int nbElem, int nbNodes,
                       const int *row, const int *col, int colBase, const int *rows,
                       int64_t nbRows, int symmetric);
+/* Record layout the slot numbering of the following dc_plan_build calls is optimised for (shared-memory
+ * banks of the accumulation reads): 0 = four 3-word node gradients in 13-word records (elasticity, default),
+ * 1 = the 10 entries of a symmetric 4x4 element matrix in 11-word records (P1 Laplacian).  Any schedule is
+ * valid for any operator; the model only decides how many bank conflicts the record reads have. */
+void dc_plan_set_bank_model(int model);
 void dc_plan_free(dc_plan_t *plan);
 void dc_contrib_free(dc_contrib_list_t *c);
 #ifdef __cplusplus

@@ -321,6 +321,12 @@ struct UnitOut {
  * seen so far (one greedy pass; class sizes are fixed by the slot count, so no slot is wasted).
  * Measured on the plan (tools/smem_model.py): 2.5 -> 1.65 wavefronts per access. */
 struct BankOpt {
+    /* which record layout the slot classes are chosen for: 0 = 13-word records of four 3-word node
+     * gradients (bank key (a - slot) mod 16, two reads per off-diagonal contribution: elasticity and
+     * the default); 1 = 11-word records of the 10 entries of a symmetric 4x4 element matrix, one read
+     * of entry q(a,b) per contribution (P1 Laplacian): bank = 11*slot + q = q - 5*slot (mod 16) */
+    int model = 0;
+    int nOff = 4;                   /* offsets an entity can be read at (4 nodes / 10 entries) */
     std::vector<int> incPtr, incGroup, order, fill;
     std::vector<uint8_t> incNode, cnt, gmax;
 
@@ -333,11 +339,12 @@ struct BankOpt {
     template <class F>
     int visit(const UnitOut &out, int nSlots, F &&f)
     {
-        stamp.assign((size_t)nSlots * 4, -1);
+        static const unsigned char entry[16] = {0, 1, 2, 3, 1, 4, 5, 6, 2, 5, 7, 8, 3, 6, 8, 9};
+        stamp.assign((size_t)nSlots * 16, -1);
         int g = 0;
         for (const dc_task_t &t : out.tasks) {
             const uint16_t *it = out.items.data() + t.itemRel;
-            const int sides = t.kind == DC_TASK_OWNDIAG ? 1 : 2;
+            const int sides = (model == 1 || t.kind == DC_TASK_OWNDIAG) ? 1 : 2;
             for (int half = 0; half < 2; half++)
                 for (int side = 0; side < sides; side++)
                     for (int r = 0; r < (int)t.iters; r++, g++) {
@@ -346,8 +353,9 @@ struct BankOpt {
                             const uint32_t item = row[l];
                             const int slot = (int)(item >> 4);
                             if (slot >= nSlots) continue;
-                            const int node = side ? (int)(item & 3u) : (int)((item >> 2) & 3u);
-                            int &st = stamp[(size_t)slot * 4 + node];
+                            const int node = model == 1 ? (int)entry[item & 15u]
+                                                        : side ? (int)(item & 3u) : (int)((item >> 2) & 3u);
+                            int &st = stamp[(size_t)slot * 16 + node];
                             if (st == g) continue;
                             st = g;
                             f(g, slot, node);
@@ -387,20 +395,21 @@ struct BankOpt {
         for (int x : order) {
             /* cost of every class at once: per offset, the sum over the entity's groups of
              * (entries already on that key) + 64 if one more raises the group's maximum */
-            uint16_t w[4][16];
-            for (int o = 0; o < 4; o++)
+            uint16_t w[16][16];
+            for (int o = 0; o < nOff; o++)
                 for (int k = 0; k < 16; k++) w[o][k] = 0;
             for (int q = incPtr[(size_t)x]; q < incPtr[(size_t)x + 1]; q++) {
                 const uint8_t *row = cnt.data() + (size_t)incGroup[(size_t)q] * 16;
                 const uint8_t mx = gmax[(size_t)incGroup[(size_t)q]];
-                uint16_t *dst = w[incNode[(size_t)q] & 3];
+                uint16_t *dst = w[incNode[(size_t)q] & 15];
                 #pragma omp simd
                 for (int k = 0; k < 16; k++) dst[k] = (uint16_t)(dst[k] + row[k] + (row[k] >= mx ? 64 : 0));
             }
             int bestC = -1, bestV = 0;
             for (int c = 0; c < 16; c++) {
                 if (used[c] >= cap[c]) continue;
-                const int v = w[0][(0 - c) & 15] + w[1][(1 - c) & 15] + w[2][(2 - c) & 15] + w[3][(3 - c) & 15];
+                int v = 0;
+                for (int o = 0; o < nOff; o++) v += w[o][(o - c) & 15];
                 if (bestC < 0 || v < bestV) { bestC = c; bestV = v; }
             }
             used[bestC]++;
@@ -436,14 +445,17 @@ struct BankOpt {
         for (int s = 0; s < nSlots; s++) newSlot[(size_t)s] = s;
         if (nSlots <= 16) return;
         const int nbGroups = collect(nSlots, [&](auto &&f) { return visit(out, nSlots, f); });
+        /* the greedy works on keys (offset - class) mod 16; model 1 reads bank q - 5*slot, so its
+         * class is 5*(slot mod 16) and the slot residue of a class is 13*class (5*13 = 1 mod 16) */
+        const int mul = model == 1 ? 13 : 1;
         int cap[16], used[16];
-        for (int c = 0; c < 16; c++) { used[c] = 0; cap[c] = (nSlots - c + 15) / 16; }
+        for (int c = 0; c < 16; c++) { used[c] = 0; cap[c] = (nSlots - ((mul * c) & 15) + 15) / 16; }
         greedy(nSlots, nbGroups, nullptr, cap, newSlot);
         /* inside a class, keep the incoming (element) order: the 16 consecutive slots that one
          * half-warp turns into records then hold elements close to each other, which share nodes
          * (their coordinate reads are broadcasts) */
         for (int s = 0; s < nSlots; s++) {
-            const int c = newSlot[(size_t)s];
+            const int c = (mul * newSlot[(size_t)s]) & 15;
             newSlot[(size_t)s] = c + 16 * used[c]++;
         }
     }
@@ -476,7 +488,10 @@ struct BankOpt {
         int cap[16];
         for (int c = 0; c < 16; c++) cap[c] = 0;
         for (int p = 0; p < nHalo; p++) cap[(16 - ((ownSpan + p) & 15)) & 15]++;
+        const int keep = nOff;
+        nOff = 1;                                   /* every entity is read at offset 0 */
         greedy(nEnt, nbGroups, fixedCls.data(), cap, cls);
+        nOff = keep;
     }
 };
 
@@ -815,6 +830,8 @@ void build_unit(const Mesh &m, const UnitSeed &s, int32_t *diagRel, UnitOut &out
     while (out.haloNodes.size() % 4) out.haloNodes.push_back(0);
 }
 
+int g_bankModel = 0;
+
 template <typename T>
 T *dup(const std::vector<T> &v)
 {
@@ -972,6 +989,8 @@ extern "C" int dc_plan_build(dc_plan_t *plan, const int *conn, int nbElem, int n
         const int tid = omp_get_thread_num();
         UnitOut out;
         BankOpt opt;
+        opt.model = g_bankModel;
+        opt.nOff = g_bankModel == 1 ? 10 : 4;
         Scratch work;
         #pragma omp for schedule(dynamic, 64)
         for (int64_t u = 0; u < nbUnits; u++) {
@@ -1097,6 +1116,8 @@ extern "C" int dc_plan_build(dc_plan_t *plan, const int *conn, int nbElem, int n
     }
     return 0;
 }
+
+extern "C" void dc_plan_set_bank_model(int model) { g_bankModel = model == 1 ? 1 : 0; }
 
 extern "C" void dc_contrib_free(dc_contrib_list_t *c)
 {

@@ -190,7 +190,7 @@ class InterfaceExchange:
 
 
 def setup_device_slabs(n, rank, world, device, builder="geometric", vec=0, slots=400, dist=None, seed=12345,
-                       symmetric=True):
+                       symmetric=True, bank_model=0):
     """Device-resident slab for this rank.  Every slab of the bar has the same topology, so
     rank 0 builds tree, CSR pattern and schedule once on its host cores and broadcasts the
     arrays GPU-to-GPU (NCCL over NVLink); each rank generates its own coordinates and permutes
@@ -211,7 +211,8 @@ def setup_device_slabs(n, rank, world, device, builder="geometric", vec=0, slots
         node_perm = slab["node_perm"]
         t_tree = time.time() - t0
         t1 = time.time()
-        plan = HostPlan(slab["conn"], slab["N"], slab["row"], slab["col"], 0, slab["rec"], slots, symmetric=symmetric)
+        plan = HostPlan(slab["conn"], slab["N"], slab["row"], slab["col"], 0, slab["rec"], slots, symmetric=symmetric,
+                        bank_model=bank_model)
         t_plan = time.time() - t1
         arr = plan.arrays()
         if arr["bigEdges"]:

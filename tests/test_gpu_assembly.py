@@ -21,11 +21,12 @@ OPS = {1: (dc.OP_LAPLACIAN, None), 3: (dc.OP_ELASTICITY, [LAMBDA, MU])}
 REL_TOL = 1e-12
 
 
-def _ctx(mesh, slots=832, lists=False, with_tree=True, sym=True):
+def _ctx(mesh, slots=832, lists=False, with_tree=True, sym=True, bank_model=0):
     ctx = dc.Context(0)
     ctx.set_mesh(mesh["conn"], mesh["coord"], mesh["row"], mesh["col"], 0)
     rec = tree_records(mesh) if with_tree else None
-    plan = dc.HostPlan(mesh["conn"], mesh["N"], mesh["row"], mesh["col"], 0, rec, slots, symmetric=sym)
+    plan = dc.HostPlan(mesh["conn"], mesh["N"], mesh["row"], mesh["col"], 0, rec, slots, symmetric=sym,
+                       bank_model=bank_model)
     ctx.upload_plan(plan)
     if lists:
         ctx.upload_lists(mesh["conn"], mesh["N"], mesh["row"], mesh["col"], 0)
@@ -108,7 +109,7 @@ def test_bench_unit_geometry_bit_exact(tmp_path, dim, slots, threads):
         mesh = prepare_mesh(MineLib(0, geometric=True), n, tmp_path)
     finally:
         dc.DC_set_max_elem_per_part(200)
-    ctx, plan = _ctx(mesh, slots=slots)
+    ctx, plan = _ctx(mesh, slots=slots, bank_model=1 if dim == 1 else 0)
     ctx.set_option("unit_threads", threads)
     assert plan.c.big.nbEdges == 0
     got = _run(ctx, mesh, dim, dc.MODE_DETERMINISTIC)

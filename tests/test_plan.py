@@ -157,6 +157,20 @@ def check_plan(mesh, plan, slots, sym):
     assert plan.c.nbItemsUseful + big.nbItems == (10 if sym else 16) * E
 
 
+@pytest.mark.parametrize("sym", [True, False])
+def test_plan_numbered_for_the_laplacian_records(tmp_path, sym):
+    """bank_model=1 (11-word records of 4x4 symmetric entries): same units and contributions, other slot numbers."""
+    mesh = prepare_mesh(MineLib(0), 10, tmp_path)
+    rec = tree_records(mesh)
+    plan = dc.HostPlan(mesh["conn"], mesh["N"], mesh["row"], mesh["col"], 0, rec, 832, symmetric=sym, bank_model=1)
+    check_plan(mesh, plan, 832, sym)
+    ref = dc.HostPlan(mesh["conn"], mesh["N"], mesh["row"], mesh["col"], 0, rec, 832, symmetric=sym)
+    assert plan.c.nbUnits == ref.c.nbUnits and plan.c.nbItems == ref.c.nbItems
+    a, b = plan.arrays(), ref.arrays()
+    assert not np.array_equal(a["items"], b["items"])
+    assert np.array_equal(a["items"] & 15, b["items"] & 15)            # same (a, b) pairs, other slots
+
+
 def test_plan_without_tree_uses_row_blocks(tmp_path):
     mesh = prepare_mesh(MineLib(0), 8, tmp_path)
     plan = dc.HostPlan(mesh["conn"], mesh["N"], mesh["row"], mesh["col"], 0, None, 300, symmetric=False)

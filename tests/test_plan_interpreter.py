@@ -123,7 +123,9 @@ def test_schedule_reproduces_reference_bits(tmp_path, n, vec, slots, hub, geomet
         mesh = prepare_mesh(MineLib(vec, geometric=geometric), n, tmp_path, hub=hub)
     finally:
         dc.DC_set_max_elem_per_part(200)
-    plan = dc.HostPlan(mesh["conn"], mesh["N"], mesh["row"], mesh["col"], 0, tree_records(mesh), slots, symmetric=sym)
+    # the slot numbering is chosen for the operator's record layout, as bench.py does
+    plan = dc.HostPlan(mesh["conn"], mesh["N"], mesh["row"], mesh["col"], 0, tree_records(mesh), slots, symmetric=sym,
+                       bank_model=1 if dim == 1 else 0)
     got = run_schedule(mesh, plan, dim)
     want = oracle_serial(mesh, dim)
     assert got.tobytes() == want.tobytes()

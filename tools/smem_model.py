@@ -93,7 +93,8 @@ def main():
     with tempfile.TemporaryDirectory() as tmp:
         mesh = common.prepare_mesh(common.MineLib(0, geometric=builder == "geometric"), n, tmp)
     rec = common.tree_records(mesh)
-    plan = dc.HostPlan(mesh["conn"], mesh["N"], mesh["row"], mesh["col"], 0, rec, slots, symmetric=True)
+    bank_model = int(os.environ.get("DC_BANK_MODEL", "1" if dim == 1 else "0"))
+    plan = dc.HostPlan(mesh["conn"], mesh["N"], mesh["row"], mesh["col"], 0, rec, slots, symmetric=True, bank_model=bank_model)
     A = plan.arrays()
     units = np.frombuffer(A["units"].tobytes(), dtype=np.dtype(
         [("edgeFirst", "i8"), ("itemFirst", "i8"), ("tgtFirst", "i8"), ("slotFirst", "i8"), ("hnodeFirst", "i8"),
