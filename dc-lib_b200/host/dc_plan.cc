@@ -506,6 +506,7 @@ struct Scratch {
     std::vector<char> isDiag;
     std::vector<int> outside, nodeOf, fixedCls, cls, tableIdx, newSlot, regroup;
     std::vector<int32_t> movedElems;
+    std::vector<uint8_t> residue;
     inline int count(int k) const { return edgePtr[(size_t)k + 1] - edgePtr[(size_t)k]; }
     inline const uint16_t *items(int k) const { return edgeItems.data() + edgePtr[(size_t)k]; }
 };
@@ -749,10 +750,10 @@ void build_unit(const Mesh &m, const UnitSeed &s, int32_t *diagRel, UnitOut &out
         }
     };
     /* table positions of the halo nodes for the current slot order */
-    auto place_halo = [&]() {
+    auto place_halo = [&](bool optimise) {
         tableIdx.resize((size_t)(ownSpan + nHalo));
         for (int x = 0; x < ownSpan + nHalo; x++) tableIdx[(size_t)x] = x;
-        if (bankAware && nHalo > 16) {
+        if (optimise && bankAware && nHalo > 16) {
             opt.run_nodes(nodeOf, nSlots, ownSpan + nHalo, fixedCls, ownSpan, nHalo, cls);
             /* positions ownSpan + p with (ownSpan + p) mod 16 == (16 - class) mod 16, in node order */
             int nextPos[16];
@@ -764,9 +765,10 @@ void build_unit(const Mesh &m, const UnitSeed &s, int32_t *diagRel, UnitOut &out
             }
         }
     };
+    const bool regroup = bankAware && nHalo > 16 && nSlots > 32 && regroupPasses > 0;
     entities();
-    place_halo();
-    if (bankAware && nHalo > 16 && nSlots > 32)
+    place_halo(!regroup);          /* the re-deal starts from the natural halo positions; they are optimised after it */
+    if (regroup)
         for (int pass = 0; pass < regroupPasses; pass++) {
             /* The record reads fix a slot's CLASS (slot mod 16), not its rank inside the class, and
              * the record build reads the coordinates of 16 consecutive slots -- one of every class
@@ -779,6 +781,9 @@ void build_unit(const Mesh &m, const UnitSeed &s, int32_t *diagRel, UnitOut &out
             int head[16];
             for (int c = 0; c < 16; c++) head[c] = c;      /* first slot of the class not yet dealt */
             const int window = 8;
+            std::vector<uint8_t> &res = w.residue;        /* bank residue of the table position of every (slot, j) */
+            res.resize((size_t)nSlots * 4);
+            for (size_t q = 0; q < (size_t)nSlots * 4; q++) res[q] = (uint8_t)(tableIdx[(size_t)nodeOf[q]] & 15);
             for (int base = 0; base < nSlots; base += 16) {
                 /* distinct table entities the group reads per node position j and bank residue */
                 int occ[4][16][16], nocc[4][16];
@@ -792,17 +797,19 @@ void build_unit(const Mesh &m, const UnitSeed &s, int32_t *diagRel, UnitOut &out
                         seen++;
                         int cost = 0;
                         for (int j = 0; j < 4; j++) {
-                            const int ent = nodeOf[(size_t)cand * 4 + j], r = tableIdx[(size_t)ent] & 15;
+                            const int r = res[(size_t)cand * 4 + j], have = nocc[j][r];
+                            if (!have) continue;
+                            const int ent = nodeOf[(size_t)cand * 4 + j];
                             bool present = false;
-                            for (int q = 0; q < nocc[j][r]; q++) present |= occ[j][r][q] == ent;
-                            if (!present) cost += nocc[j][r];       /* one more address on a bank that has nocc already */
+                            for (int q = 0; q < have; q++) present |= occ[j][r][q] == ent;
+                            if (!present) cost += have;             /* one more address on a bank that has `have` already */
                         }
                         if (cost < bestCost) { bestCost = cost; best = cand; }
                         if (cost == 0) break;
                     }
                     perm[(size_t)best] = base + c;
                     for (int j = 0; j < 4; j++) {
-                        const int ent = nodeOf[(size_t)best * 4 + j], r = tableIdx[(size_t)ent] & 15;
+                        const int ent = nodeOf[(size_t)best * 4 + j], r = res[(size_t)best * 4 + j];
                         bool present = false;
                         for (int q = 0; q < nocc[j][r]; q++) present |= occ[j][r][q] == ent;
                         if (!present) occ[j][r][nocc[j][r]++] = ent;
@@ -815,7 +822,7 @@ void build_unit(const Mesh &m, const UnitSeed &s, int32_t *diagRel, UnitOut &out
             out.slotElems.swap(moved);
             for (int sl = 0; sl < nSlots; sl++) newSlot[(size_t)sl] = perm[(size_t)newSlot[(size_t)sl]];
             entities();
-            place_halo();
+            place_halo(true);
         }
     for (uint16_t &it : out.items) {
         const int slot = it >> 4;
