@@ -507,6 +507,7 @@ struct Scratch {
     std::vector<int> outside, nodeOf, fixedCls, cls, tableIdx, newSlot, regroup;
     std::vector<int32_t> movedElems;
     std::vector<uint8_t> residue;
+    double phase[8] = {0, 0, 0, 0, 0, 0, 0, 0};   /* seconds per build_unit phase (DC_PLAN_VERBOSE) */
     inline int count(int k) const { return edgePtr[(size_t)k + 1] - edgePtr[(size_t)k]; }
     inline const uint16_t *items(int k) const { return edgeItems.data() + edgePtr[(size_t)k]; }
 };
@@ -702,12 +703,16 @@ void build_tasks(const Mesh &m, const UnitSeed &s, int32_t *diagRel, UnitOut &ou
 void build_unit(const Mesh &m, const UnitSeed &s, int32_t *diagRel, UnitOut &out,
                 Scratch &w, int &error, bool symmetric, BankOpt &opt, bool bankAware, int regroupPasses)
 {
+    double tp = omp_get_wtime();
+    auto lap = [&](int phase) { const double t = omp_get_wtime(); w.phase[phase] += t - tp; tp = t; };
     build_tasks(m, s, diagRel, out, w, error, symmetric);
     if (error) return;
+    lap(0);
     const int nSlots = s.ownCount + (int)s.halo.size();
     std::vector<int> &newSlot = w.newSlot;
     if (bankAware) opt.run(out, nSlots, newSlot);
     else { newSlot.resize((size_t)nSlots); for (int q = 0; q < nSlots; q++) newSlot[(size_t)q] = q; }
+    lap(1);
     out.slotElems.assign((size_t)nSlots, -1);
     for (int sl = 0; sl < nSlots; sl++)
         out.slotElems[(size_t)newSlot[(size_t)sl]] =
@@ -767,6 +772,7 @@ void build_unit(const Mesh &m, const UnitSeed &s, int32_t *diagRel, UnitOut &out
     };
     const bool regroup = bankAware && nHalo > 16 && nSlots > 32 && regroupPasses > 0;
     entities();
+    lap(2);
     place_halo(!regroup);          /* the re-deal starts from the natural halo positions; they are optimised after it */
     if (regroup)
         for (int pass = 0; pass < regroupPasses; pass++) {
@@ -821,9 +827,11 @@ void build_unit(const Mesh &m, const UnitSeed &s, int32_t *diagRel, UnitOut &out
             for (int sl = 0; sl < nSlots; sl++) moved[(size_t)perm[(size_t)sl]] = out.slotElems[(size_t)sl];
             out.slotElems.swap(moved);
             for (int sl = 0; sl < nSlots; sl++) newSlot[(size_t)sl] = perm[(size_t)newSlot[(size_t)sl]];
+            lap(3);
             entities();
             place_halo(true);
         }
+    lap(4);
     for (uint16_t &it : out.items) {
         const int slot = it >> 4;
         if (slot < nSlots) it = (uint16_t)((newSlot[(size_t)slot] << 4) | (it & 15));
@@ -835,6 +843,7 @@ void build_unit(const Mesh &m, const UnitSeed &s, int32_t *diagRel, UnitOut &out
     while (out.slotNodes.size() % 8) out.slotNodes.push_back(0);    /* 16-byte granules */
     while (out.slotElems.size() % 2) out.slotElems.push_back(-1);
     while (out.haloNodes.size() % 4) out.haloNodes.push_back(0);
+    lap(5);
 }
 
 int g_bankModel = 0;
@@ -1042,6 +1051,11 @@ extern "C" int dc_plan_build(dc_plan_t *plan, const int *conn, int nbElem, int n
             tItems[tid].insert(tItems[tid].end(), out.items.begin(), out.items.end());
             useful += out.useful;
         }
+        #pragma omp critical
+        if (verbose && tid == 0)
+            fprintf(stderr, "[dc_plan] thread 0: contributions %.2fs slot classes %.2fs node tables %.2fs re-deal %.2fs "
+                    "halo placement %.2fs output %.2fs\n", work.phase[0], work.phase[1], work.phase[2], work.phase[3],
+                    work.phase[4], work.phase[5]);
     }
     if (error) return -2;
     lap("units");

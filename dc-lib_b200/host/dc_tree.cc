@@ -19,7 +19,7 @@
 #include <cstdlib>
 #include <cstdio>
 #include <vector>
-#include <unordered_map>
+#include <memory>
 #include <algorithm>
 #include <omp.h>
 #include "dc_internal.h"
@@ -179,11 +179,17 @@ struct Rcb {
     }
 };
 
-/* tab[perm[i]] <- tab[i] (rows of dim ints) from inside a task region */
-static void task_scatter_rows(int *tab, const int *perm, int n, int dim)
+/* tab[perm[i]] <- tab[i] (rows of dim ints) from inside a task region; src = scratch for n*dim
+ * ints.  The scratch comes from buffers allocated once per tree (TreeBuilder): fresh gigabyte
+ * allocations at every level of the recursion cost more in page faults than the copy itself. */
+static void task_scatter_rows(int *tab, const int *perm, int n, int dim, int *src)
 {
-    std::vector<int> src(tab, tab + (int64_t)n * dim);
     const int chunk = 1 << 16, nbChunks = (n + chunk - 1) / chunk;
+    #pragma omp taskloop default(shared) grainsize(1) if (nbChunks > 4)
+    for (int c = 0; c < nbChunks; c++) {
+        const int64_t e0 = (int64_t)c * chunk, e1 = std::min<int64_t>(n, e0 + chunk);
+        memcpy(src + e0 * dim, tab + e0 * dim, sizeof(int) * (size_t)((e1 - e0) * dim));
+    }
     #pragma omp taskloop default(shared) grainsize(1) if (nbChunks > 4)
     for (int c = 0; c < nbChunks; c++) {
         const int e0 = c * chunk, e1 = std::min(n, e0 + chunk);
@@ -199,6 +205,10 @@ struct TreeBuilder {
     int maxElem;
     const double *coord = nullptr;   /* node coordinates (original numbering): geometric mode */
     int dimNode = 3;
+    /* scratch indexed by element POSITION (subtrees work on disjoint position ranges) */
+    int *scrRows = nullptr;          /* [nbElem][dimElem] copy of the rows being scattered */
+    int *scrOrder = nullptr;         /* [nbElem] destination of every element of a range */
+    unsigned char *scrCls = nullptr; /* [nbElem] class of every element of a range */
 
     /* node partition of a (sub)mesh: METIS on the nodal graph (reference behaviour) or
      * coordinate bisection when coordinates were supplied */
@@ -250,14 +260,14 @@ void TreeBuilder::tree_creation(tree_t *&tree, int *sepToNode, const int *nodePa
     /* class 0: every node in a part <= pivot, 1: every node beyond it, 2: straddles.
      * The stable 3-way order (reference: DC_create_permutation with 3 parts) is computed
      * chunk-wise so that large ranges near the root are processed by all threads. */
-    std::vector<int> order((size_t)n);
+    int *order = scrOrder + firstElem;                      /* every entry is written below */
     const int *rows = isSep ? sepToNode + (int64_t)sepOffset * dimElem
                             : conn + (int64_t)firstElem * dimElem;
     const int chunk = 1 << 16;
     const int nbChunks = (n + chunk - 1) / chunk;
     std::vector<int> hist((size_t)nbChunks * 3, 0);
     {
-        std::vector<unsigned char> cls((size_t)n);
+        unsigned char *cls = scrCls + firstElem;
         #pragma omp taskloop default(shared) grainsize(1) if (nbChunks > 4)
         for (int c = 0; c < nbChunks; c++) {
             const int e0 = c * chunk, e1 = std::min(n, e0 + chunk);
@@ -292,10 +302,10 @@ void TreeBuilder::tree_creation(tree_t *&tree, int *sepToNode, const int *nodePa
     }
     const int nbLeft = nbLeftOut, nbSep = nbSepOut;
 
-    task_scatter_rows(conn + (int64_t)firstElem * dimElem, order.data(), n, dimElem);
-    task_scatter_rows(posToOrig + firstElem, order.data(), n, 1);
-    if (isSep) task_scatter_rows(sepToNode + (int64_t)sepOffset * dimElem, order.data(), n, dimElem);
-    std::vector<int>().swap(order);
+    int *scratch = scrRows + (int64_t)firstElem * dimElem;
+    task_scatter_rows(conn + (int64_t)firstElem * dimElem, order, n, dimElem, scratch);
+    task_scatter_rows(posToOrig + firstElem, order, n, 1, scratch);
+    if (isSep) task_scatter_rows(sepToNode + (int64_t)sepOffset * dimElem, order, n, dimElem, scratch);
 
     tree = new_tree_node(firstElem, lastElem, nbSep, firstNode, lastNode, isSep, false);
     /* the three subtrees work on disjoint element ranges: build them concurrently (the
@@ -372,6 +382,18 @@ static void create_tree_impl(int *elemToNode, int nbElem, int dimElem, int nbNod
     std::vector<int> posToOrig((size_t)(nbElem > 0 ? nbElem : 1));
     for (int i = 0; i < nbElem; i++) posToOrig[i] = i;
     TreeBuilder b{elemToNode, posToOrig.data(), dimElem, maxElem, coord, dimNode};
+    std::unique_ptr<int[]> scrRows(new int[(size_t)(nbConn > 0 ? nbConn : 1)]), scrOrder(new int[(size_t)(nbElem > 0 ? nbElem : 1)]);
+    std::unique_ptr<unsigned char[]> scrCls(new unsigned char[(size_t)(nbElem > 0 ? nbElem : 1)]);
+    b.scrRows = scrRows.get();
+    b.scrOrder = scrOrder.get();
+    b.scrCls = scrCls.get();
+    /* first touch with one contiguous piece per thread: the chunk-wise tasks of the recursion would
+     * fault the same huge pages from several threads at once, which serialises in the kernel */
+    #pragma omp parallel for schedule(static) num_threads(nt) if (nbConn > (1 << 20))
+    for (int64_t k = 0; k < nbConn; k += 1024) {
+        scrRows[(size_t)k] = 0;
+        if (k < nbElem) { scrOrder[(size_t)k] = 0; scrCls[(size_t)k] = 0; }
+    }
 
     const bool verbose = getenv("DC_PLAN_VERBOSE") != nullptr;
     double t0 = omp_get_wtime();
