@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <vector>
+#include <memory>
 #include <algorithm>
 #include <omp.h>
 #include "../csrc/dc_plan.h"
@@ -21,7 +22,8 @@ struct Mesh {
     const int *row, *col;
     int colBase;
     std::vector<int64_t> n2ePtr;
-    std::vector<int> n2eVal;   /* incident elements of each node, ascending */
+    int *n2eVal = nullptr;     /* incident elements of each node, ascending */
+    std::unique_ptr<int[]> n2eHold;
 };
 
 /* int -> int map with open addressing for the per-unit lookups (element -> slot, column -> edge,
@@ -59,7 +61,11 @@ void build_node_to_elem(Mesh &m)
         m.n2ePtr[(size_t)m.conn[k]]++;                 /* node n (1-based) -> slot n */
     }
     for (int n = 0; n < m.nbNodes; n++) m.n2ePtr[(size_t)n + 1] += m.n2ePtr[n];
-    m.n2eVal.resize((size_t)nc);
+    /* 4 ints per element: not zero-filled by one thread; every thread first touches one contiguous piece */
+    m.n2eHold.reset(new int[(size_t)(nc > 0 ? nc : 1)]);
+    m.n2eVal = m.n2eHold.get();
+    #pragma omp parallel for schedule(static) if (nc > (1 << 18))
+    for (int64_t k = 0; k < nc; k += 1024) m.n2eVal[k] = 0;
     std::vector<int64_t> fill(m.n2ePtr.begin(), m.n2ePtr.end() - 1);
     #pragma omp parallel for schedule(static) if (nc > (1 << 18))
     for (int e = 0; e < m.nbElem; e++)
@@ -71,7 +77,7 @@ void build_node_to_elem(Mesh &m)
         }
     #pragma omp parallel for schedule(dynamic, 4096) if (nc > (1 << 18))
     for (int n = 0; n < m.nbNodes; n++)
-        std::sort(m.n2eVal.begin() + m.n2ePtr[n], m.n2eVal.begin() + m.n2ePtr[(size_t)n + 1]);
+        std::sort(m.n2eVal + m.n2ePtr[n], m.n2eVal + m.n2ePtr[(size_t)n + 1]);
 }
 
 struct UnitSeed {
@@ -173,22 +179,35 @@ struct Selector {
     void split_leaf(int nodeFirst, int nodeCount)
     {
         const int tid = omp_get_thread_num();
+        /* k even pieces of rows [nodeFirst, +nodeCount), or nothing if one of them exceeds the budget */
+        auto even = [&](int k, std::vector<UnitSeed> &pieces) {
+            pieces.clear();
+            int start = nodeFirst;
+            for (int p = 0; p < k; p++) {
+                const int cnt = nodeCount / k + (p < nodeCount % k ? 1 : 0);
+                UnitSeed s{start, cnt, 0, 0, {}};
+                s.halo.assign(m.n2eVal + m.n2ePtr[start], m.n2eVal + m.n2ePtr[(size_t)start + cnt]);
+                std::sort(s.halo.begin(), s.halo.end());
+                s.halo.erase(std::unique(s.halo.begin(), s.halo.end()), s.halo.end());
+                if ((int)s.halo.size() > maxSlots) { pieces.clear(); return false; }
+                pieces.push_back(std::move(s));
+                start += cnt;
+            }
+            return true;
+        };
+        std::vector<UnitSeed> pieces;
+        /* the common case first: both callers have found that the leaf does not fit one unit, so if two even pieces fit,
+         * the greedy cut needs two pieces as well (its first piece is at least as long as the even
+         * one and its second is a subset of the second even piece) -- no need to run it */
+        if (evenSplit && nodeCount >= 2 && (nodeCount + 1) / 2 <= 32 && even(2, pieces)) {
+            for (UnitSeed &s : pieces) seedsT[tid].push_back(std::move(s));
+            return;
+        }
         const size_t seeds0 = seedsT[tid].size(), big0 = bigT[tid].size();
         split_rows(nodeFirst, nodeCount);
         const int k = (int)(seedsT[tid].size() - seeds0);
         if (!evenSplit || bigT[tid].size() != big0 || k < 2 || (nodeCount + k - 1) / k > 32) return;
-        std::vector<UnitSeed> pieces;
-        int start = nodeFirst;
-        for (int p = 0; p < k; p++) {
-            const int cnt = nodeCount / k + (p < nodeCount % k ? 1 : 0);
-            UnitSeed s{start, cnt, 0, 0, {}};
-            s.halo.assign(m.n2eVal.begin() + m.n2ePtr[start], m.n2eVal.begin() + m.n2ePtr[(size_t)start + cnt]);
-            std::sort(s.halo.begin(), s.halo.end());
-            s.halo.erase(std::unique(s.halo.begin(), s.halo.end()), s.halo.end());
-            if ((int)s.halo.size() > maxSlots) return;         /* an even piece does not fit: keep the greedy cut */
-            pieces.push_back(std::move(s));
-            start += cnt;
-        }
+        if (!even(k, pieces)) return;                  /* an even piece does not fit: keep the greedy cut */
         seedsT[tid].resize(seeds0);
         for (UnitSeed &s : pieces) seedsT[tid].push_back(std::move(s));
     }
@@ -214,7 +233,7 @@ struct Selector {
         for (size_t l = first; l < last; l++) {
             const int nf = leaves[l].first, nc = leaves[l].second;
             if (nc <= 0) continue;
-            leafSet.assign(m.n2eVal.begin() + m.n2ePtr[nf], m.n2eVal.begin() + m.n2ePtr[(size_t)nf + nc]);
+            leafSet.assign(m.n2eVal + m.n2ePtr[nf], m.n2eVal + m.n2ePtr[(size_t)nf + nc]);
             std::sort(leafSet.begin(), leafSet.end());
             leafSet.erase(std::unique(leafSet.begin(), leafSet.end()), leafSet.end());
             if ((int)leafSet.size() > maxSlots) {          /* a leaf too big on its own: cut by rows */
@@ -862,7 +881,7 @@ extern "C" int dc_contrib_build(dc_contrib_list_t *out, const int *conn, int nbE
                                 const int *row, const int *col, int colBase, const int *rows,
                                 int64_t nbRows, int symmetric)
 {
-    Mesh m{conn, nbElem, nbNodes, row, col, colBase, {}, {}};
+    Mesh m{conn, nbElem, nbNodes, row, col, colBase, {}, nullptr, {}};
     build_node_to_elem(m);
     std::vector<int64_t> edge, ptr, edgeT;
     std::vector<uint32_t> item;
@@ -923,7 +942,7 @@ extern "C" int dc_plan_build(dc_plan_t *plan, const int *conn, int nbElem, int n
     };
     if (maxSlots < 16 || maxSlots > DC_SLOT_LIMIT) return -1;
     if (nbElem >= (1 << 28)) { /* fallback items hold the element in 28 bits */ }
-    Mesh m{conn, nbElem, nbNodes, row, col, colBase, {}, {}};
+    Mesh m{conn, nbElem, nbNodes, row, col, colBase, {}, nullptr, {}};
     build_node_to_elem(m);
 
     lap("node->elem");
