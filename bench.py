@@ -243,7 +243,7 @@ def main():
     # one slab (cube) per GPU; rank 0 builds tree / CSR / schedule, the others get them over NCCL
     dc.DC_set_max_elem_per_part(capacity)
     ctx, info = multigpu.setup_device_slabs(n, rank, world, device, builder=builder, vec=vec, slots=args.slots, dist=dist,
-                                            bank_model=1 if dim == 1 else 0)
+                                            bank_model=int(os.environ.get("DC_BENCH_BANK_MODEL", "1" if dim == 1 else "0")))
     ctx.set_option("unit_threads", args.threads)
     ctx.set_option("persistent", args.persistent)
     E, N, nnz, st = info["E"], info["N"], info["nnz"], info["stats"]
