@@ -14,8 +14,8 @@ EXTRA="--leaf-nodes 0"
 run DC_AB=capacity200                          # the reference's leaf capacity (the kernel numbers of round 1)
 EXTRA="--slots 800 --threads 512"
 run DC_AB=whole_leaf_units                     # one 62-node leaf per unit, one 512-thread CTA per SM
-EXTRA="--slots 1536 --threads 512"
-run DC_AB=two_leaf_units
+EXTRA="--slots 1280 --threads 512"
+run DC_AB=two_leaf_units                       # the largest elasticity unit that fits 227 KB
 W=l160 EXTRA=""
 run DC_AB=default                              # Laplacian: bank model 1, re-deal
 run DC_BENCH_BANK_MODEL=0                      # gradient bank model (round 1)
