@@ -129,3 +129,28 @@ def test_schedule_reproduces_reference_bits(tmp_path, n, vec, slots, hub, geomet
     got = run_schedule(mesh, plan, dim)
     want = oracle_serial(mesh, dim)
     assert got.tobytes() == want.tobytes()
+
+
+@pytest.mark.skipif(not common.have_ref(0), reason="oracle/_ref not built (no /root/reference here)")
+@pytest.mark.parametrize("dim", [1, 3])
+def test_reference_on_the_bench_tree_equals_the_schedule(tmp_path, dim):
+    """The loop closed for bench.py's geometry: a coordinate-bisection tree with CTA-sized leaves,
+    built by the product, is handed to the UNMODIFIED reference as a tree file (what the bench's CPU
+    arm does); the reference's own DC_tree_traversal over it, the oracle's serial loop and the device
+    schedule interpreted on the CPU give the same bits."""
+    import bench
+    n = 14
+    dc.DC_set_max_elem_per_part(bench.leaf_capacity(n, 62))
+    try:
+        mesh = prepare_mesh(MineLib(0, geometric=True), n, tmp_path)        # stores the tree file
+    finally:
+        dc.DC_set_max_elem_per_part(200)
+    ref = common.RefLib(0)
+    ref.read(mesh["tree_path"], mesh["E"], mesh["N"])
+    got_ref = ref.traversal(mesh, dim)
+    assert not np.isnan(got_ref).any()
+    want = oracle_serial(mesh, dim)
+    assert got_ref.tobytes() == want.tobytes()
+    plan = dc.HostPlan(mesh["conn"], mesh["N"], mesh["row"], mesh["col"], 0, tree_records(mesh), 512,
+                       bank_model=1 if dim == 1 else 0)
+    assert run_schedule(mesh, plan, dim).tobytes() == got_ref.tobytes()
