@@ -131,6 +131,7 @@ struct Selector {
     std::vector<std::vector<int>> bigT;
     std::vector<IntMap> seenT;
     bool evenSplit = true;
+    int maxRows = 0;                 /* > 0: no unit has more rows (DC_PLAN_MAX_ROWS; experiment switch) */
 
     /* rows [nodeFirst, nodeFirst+nodeCount) without a usable subtree: cut greedily -- a piece takes
      * rows while the distinct elements they touch fit the slot budget */
@@ -176,25 +177,28 @@ struct Selector {
      * last one; a piece of more than 32 rows needs a second diagonal task that is mostly padding
      * (24 iterations for a few lanes).  When the same number of pieces can be had with at most 32
      * rows each, cut evenly instead: every piece then has exactly one diagonal task. */
+    /* k even pieces of rows [nodeFirst, +nodeCount), or nothing if one of them exceeds the budget */
+    bool even_pieces(int nodeFirst, int nodeCount, int k, std::vector<UnitSeed> &pieces) const
+    {
+        pieces.clear();
+        int start = nodeFirst;
+        for (int p = 0; p < k; p++) {
+            const int cnt = nodeCount / k + (p < nodeCount % k ? 1 : 0);
+            UnitSeed s{start, cnt, 0, 0, {}};
+            s.halo.assign(m.n2eVal + m.n2ePtr[start], m.n2eVal + m.n2ePtr[(size_t)start + cnt]);
+            std::sort(s.halo.begin(), s.halo.end());
+            s.halo.erase(std::unique(s.halo.begin(), s.halo.end()), s.halo.end());
+            if ((int)s.halo.size() > maxSlots) { pieces.clear(); return false; }
+            pieces.push_back(std::move(s));
+            start += cnt;
+        }
+        return true;
+    }
+
     void split_leaf(int nodeFirst, int nodeCount)
     {
         const int tid = omp_get_thread_num();
-        /* k even pieces of rows [nodeFirst, +nodeCount), or nothing if one of them exceeds the budget */
-        auto even = [&](int k, std::vector<UnitSeed> &pieces) {
-            pieces.clear();
-            int start = nodeFirst;
-            for (int p = 0; p < k; p++) {
-                const int cnt = nodeCount / k + (p < nodeCount % k ? 1 : 0);
-                UnitSeed s{start, cnt, 0, 0, {}};
-                s.halo.assign(m.n2eVal + m.n2ePtr[start], m.n2eVal + m.n2ePtr[(size_t)start + cnt]);
-                std::sort(s.halo.begin(), s.halo.end());
-                s.halo.erase(std::unique(s.halo.begin(), s.halo.end()), s.halo.end());
-                if ((int)s.halo.size() > maxSlots) { pieces.clear(); return false; }
-                pieces.push_back(std::move(s));
-                start += cnt;
-            }
-            return true;
-        };
+        auto even = [&](int k, std::vector<UnitSeed> &pieces) { return even_pieces(nodeFirst, nodeCount, k, pieces); };
         std::vector<UnitSeed> pieces;
         /* the common case first: both callers have found that the leaf does not fit one unit, so if two even pieces fit,
          * the greedy cut needs two pieces as well (its first piece is at least as long as the even
@@ -241,7 +245,15 @@ struct Selector {
                 split_leaf(nf, nc);
                 continue;
             }
-            if (curCount > 0 && curFirst + curCount == nf) {
+            if (maxRows > 0 && nc > maxRows) {             /* row cap (DC_PLAN_MAX_ROWS): even pieces of a leaf that fits */
+                std::vector<UnitSeed> pieces;
+                if (even_pieces(nf, nc, (nc + maxRows - 1) / maxRows, pieces)) {
+                    flush();
+                    for (UnitSeed &s : pieces) seedsT[tid].push_back(std::move(s));
+                    continue;
+                }
+            }
+            if (curCount > 0 && curFirst + curCount == nf && (maxRows <= 0 || curCount + nc <= maxRows)) {
                 merged.resize(cur.size() + leafSet.size());
                 merged.resize((size_t)(std::set_union(cur.begin(), cur.end(), leafSet.begin(), leafSet.end(), merged.begin()) -
                                        merged.begin()));
@@ -947,11 +959,12 @@ extern "C" int dc_plan_build(dc_plan_t *plan, const int *conn, int nbElem, int n
 
     lap("node->elem");
     const int nt = nbThreads > 0 ? nbThreads : omp_get_max_threads();
-    Selector sel{m, maxSlots, {}, {}, {}, {}, true};
+    Selector sel{m, maxSlots, {}, {}, {}, {}, true, 0};
     sel.seedsT.resize((size_t)nt);
     sel.bigT.resize((size_t)nt);
     sel.seenT.resize((size_t)nt);
     if (const char *g = getenv("DC_PLAN_GREEDY_SPLIT")) sel.evenSplit = !(*g && *g != '0');
+    if (const char *g = getenv("DC_PLAN_MAX_ROWS")) sel.maxRows = atoi(g) > 0 ? atoi(g) : 0;
     if (treeRec && nbTreeRec > 0) {
         int64_t cursor = 0;
         index_tree(treeRec, nbTreeRec, cursor, sel.tree, true);

@@ -10,6 +10,7 @@ W=e160 EXTRA=""
 run DC_AB=default                              # capacity ~182, even split, re-deal
 run DC_PLAN_REGROUP=0                          # without the rank re-deal
 run DC_PLAN_GREEDY_SPLIT=1                     # 62-node leaves, greedy row cut
+run DC_PLAN_MAX_ROWS=32                        # no unit above 32 rows: smaller per-unit maxima, ~92 KB of shared memory per CTA
 EXTRA="--leaf-nodes 0"
 run DC_AB=capacity200                          # the reference's leaf capacity (the kernel numbers of round 1)
 EXTRA="--slots 800 --threads 512"
