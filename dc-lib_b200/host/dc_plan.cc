@@ -209,9 +209,16 @@ struct Selector {
         }
         const size_t seeds0 = seedsT[tid].size(), big0 = bigT[tid].size();
         split_rows(nodeFirst, nodeCount);
-        const int k = (int)(seedsT[tid].size() - seeds0);
-        if (!evenSplit || bigT[tid].size() != big0 || k < 2 || (nodeCount + k - 1) / k > 32) return;
-        if (!even(k, pieces)) return;                  /* an even piece does not fit: keep the greedy cut */
+        int k = (int)(seedsT[tid].size() - seeds0);
+        if (bigT[tid].size() != big0) return;          /* a single row exceeds the budget: fallback lists */
+        if (maxRows > 0 && (nodeCount + k - 1) / k > maxRows) {
+            /* row cap: more, even pieces (they get smaller, so they fit sooner or later) */
+            for (k = (nodeCount + maxRows - 1) / maxRows; k <= nodeCount && !even(k, pieces); k++) {}
+            if (pieces.empty()) return;
+        } else {
+            if (!evenSplit || k < 2 || (nodeCount + k - 1) / k > 32) return;
+            if (!even(k, pieces)) return;              /* an even piece does not fit: keep the greedy cut */
+        }
         seedsT[tid].resize(seeds0);
         for (UnitSeed &s : pieces) seedsT[tid].push_back(std::move(s));
     }
