@@ -200,3 +200,25 @@ def test_partition_mesh(nbPart, geometric):
             node_parts[n].add(int(p))
     interior = np.array([len(s) == 1 for s in node_parts])
     assert interior.sum() > 0.5 * N or nbPart >= 8
+
+
+@pytest.mark.parametrize("geometric", [True, False])
+def test_tree_and_schedule_do_not_depend_on_the_thread_count(tmp_path, geometric):
+    """Tree builder (task-parallel recursion over shared scratch) and schedule builder (units built by
+    whichever thread takes them): one thread and all threads give the same tree file bytes and, per unit,
+    the same schedule (tools/plan_hash.canonical_md5)."""
+    import sys
+    sys.path.insert(0, os.path.join(common.ROOT, "tools"))
+    from plan_hash import canonical_md5
+    out = []
+    for threads in (1, 0):
+        dc.DC_set_num_threads(threads)
+        try:
+            mesh = prepare_mesh(MineLib(0, geometric=geometric), 14, tmp_path, tag=f"thr{threads}")
+        finally:
+            dc.DC_set_num_threads(0)
+        plan = dc.HostPlan(mesh["conn"], mesh["N"], mesh["row"], mesh["col"], 0, common.tree_records(mesh), 160,
+                           nbThreads=1 if threads == 1 else 0)
+        out.append((mesh["tree"], mesh["conn"].tobytes(), canonical_md5(plan, mesh["N"])))
+    assert out[0][0] == out[1][0] and out[0][1] == out[1][1]
+    assert out[0][2] == out[1][2]
