@@ -449,18 +449,18 @@ extern "C" int dc_cuda_spmv(dc_cuda_ctx *c, int dim, const double *d_values, con
     return 0;
 }
 
-/* debug: enable per-unit phase stamps; the next assembly fills h_out[nbUnits][8] on request */
+/* debug: enable per-unit phase stamps; the next assembly fills h_out[nbUnits][24] on request */
 extern "C" int dc_cuda_debug_phases(dc_cuda_ctx *c, long long *h_out)
 {
     if (!c) return fail(-1, "dc_cuda_debug_phases: null context");
     CK(cudaSetDevice(c->device));
     if (!c->d_phaseClock) {
-        CK(cudaMalloc((void **)&c->d_phaseClock, sizeof(long long) * 8 * (size_t)(c->nbUnits > 0 ? c->nbUnits : 1)));
+        CK(cudaMalloc((void **)&c->d_phaseClock, sizeof(long long) * 24 * (size_t)(c->nbUnits > 0 ? c->nbUnits : 1)));
         return 0;
     }
     CK(cudaDeviceSynchronize());
     if (h_out)
-        CK(cudaMemcpy(h_out, c->d_phaseClock, sizeof(long long) * 8 * (size_t)c->nbUnits, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(h_out, c->d_phaseClock, sizeof(long long) * 24 * (size_t)c->nbUnits, cudaMemcpyDeviceToHost));
     cudaFree(c->d_phaseClock);
     c->d_phaseClock = nullptr;
     return 0;

@@ -58,7 +58,7 @@ enum {
 namespace dcdev {
 
 template <class Op, int THREADS, int MINB, bool SYM>
-inline int launch_units(dc_launch_args *a, double *d_values, cudaStream_t s)
+inline int launch_units(dc_launch_args *a, double *d_values, const dc_params_t &P, cudaStream_t s)
 {
     UnitLayout L = UnitSmem<Op>::layout(a->maxSlots, a->maxHalo, a->maxNodes, a->maxTasks, a->maxItems, a->maxTgt,
                                         THREADS);
@@ -97,7 +97,7 @@ inline int launch_units(dc_launch_args *a, double *d_values, cudaStream_t s)
     kern<<<(unsigned)grid, THREADS, (size_t)L.total, s>>>(a->d_units, (int)a->nbUnits, a->d_tasks, a->d_items,
                                                            a->d_slotNodes, a->d_haloNodes, a->d_diagRel,
                                                            reinterpret_cast<const int2 *>(a->d_tgt), a->d_coord,
-                                                           d_values, L, a->d_phaseClock);
+                                                           d_values, L, P, a->d_phaseClock);
     return DC_LAUNCH_OK;
 }
 
@@ -109,41 +109,41 @@ inline int launch_operator(dc_launch_args *a, const double *h_params, int nbPara
     constexpr int DD = Op::D * Op::D;
     a->launches = 0;
     if (nbParams < Op::NPARAM || nbParams > DC_MAX_PARAMS) return DC_LAUNCH_PARAMS;
-    if (nbParams > 0 &&
-        cudaMemcpyToSymbolAsync(c_params, h_params, sizeof(double) * (size_t)nbParams, 0, cudaMemcpyHostToDevice, s) !=
-            cudaSuccess)
-        return DC_LAUNCH_CUDA;
+    /* the coefficients are a kernel argument of every launch below (no device-global state: two
+     * assemblies on different streams of one device do not interfere) */
+    dc_params_t P;
+    for (int i = 0; i < DC_MAX_PARAMS; i++) P.v[i] = i < nbParams ? h_params[i] : 0.0;
     if (a->mode == DC_MODE_DETERMINISTIC) {
         if (!a->d_units && a->nbBigEdges == 0) return DC_LAUNCH_NO_PLAN;
         if (a->nbUnits > 0) {
             if (a->symmetric && !Op::SYMMETRIC) return DC_LAUNCH_NOT_SYMMETRIC;
             int rc;
             if (a->symmetric)
-                rc = (a->threads == 128)   ? launch_units<Op, 128, 4, true>(a, d_values, s)
-                     : (a->threads == 512) ? launch_units<Op, 512, 1, true>(a, d_values, s)
-                     : (a->threads == 192) ? launch_units<Op, 192, 3, true>(a, d_values, s)
-                                           : launch_units<Op, 256, 2, true>(a, d_values, s);
+                rc = (a->threads == 128)   ? launch_units<Op, 128, 4, true>(a, d_values, P, s)
+                     : (a->threads == 512) ? launch_units<Op, 512, 1, true>(a, d_values, P, s)
+                     : (a->threads == 192) ? launch_units<Op, 192, 3, true>(a, d_values, P, s)
+                                           : launch_units<Op, 256, 2, true>(a, d_values, P, s);
             else
-                rc = (a->threads == 128) ? launch_units<Op, 128, 4, false>(a, d_values, s)
-                                         : launch_units<Op, 256, 2, false>(a, d_values, s);
+                rc = (a->threads == 128) ? launch_units<Op, 128, 4, false>(a, d_values, P, s)
+                                         : launch_units<Op, 256, 2, false>(a, d_values, P, s);
             if (rc) return rc;
             a->launches++;
         }
         if (a->nbBigEdges > 0) {
             gather_lists<Op><<<(unsigned)((a->nbBigEdges + 127) / 128), 128, 0, s>>>(
-                a->d_bigEdge, a->d_bigPtr, a->d_bigItem, a->d_bigEdgeT, a->nbBigEdges, a->d_conn, a->d_coord, d_values);
+                a->d_bigEdge, a->d_bigPtr, a->d_bigItem, a->d_bigEdgeT, a->nbBigEdges, a->d_conn, a->d_coord, d_values, P);
             a->launches++;
         }
     } else if (a->mode == DC_MODE_ATOMIC) {
         reset_values<<<a->smCount * 8, 256, 0, s>>>(d_values, a->nnz * DD);
         scatter_atomic<Op><<<(unsigned)((a->nbElem + 127) / 128), 128, 0, s>>>(a->d_conn, a->d_coord, a->d_row, a->d_col,
-                                                                                 a->colBase, a->nbElem, d_values);
+                                                                                 a->colBase, a->nbElem, d_values, P);
         a->launches += 2;
     } else if (a->mode == DC_MODE_LIST) {
         if (!a->d_listPtr) return DC_LAUNCH_NO_PLAN;
         gather_lists<Op><<<(unsigned)((a->nbListEdges + 127) / 128), 128, 0, s>>>(
             a->d_listEdge, a->d_listPtr, a->d_listItem, (const int64_t *)nullptr, a->nbListEdges, a->d_conn, a->d_coord,
-            d_values);
+            d_values, P);
         a->launches++;
     } else {
         return DC_LAUNCH_BAD_MODE;

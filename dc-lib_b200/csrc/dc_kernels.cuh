@@ -88,9 +88,27 @@ __device__ __forceinline__ void st_stream_f64(double *addr, double v)
     asm volatile("st.global.cs.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
 }
 
-/* operator coefficients, set with cudaMemcpyToSymbolAsync before a launch */
+/* operator coefficients travel with every launch as a kernel argument (by value): two
+ * assemblies with different coefficients on different streams cannot see each other's */
 #define DC_MAX_PARAMS 8
-__constant__ double c_params[DC_MAX_PARAMS];
+struct dc_params_t { double v[DC_MAX_PARAMS]; };
+
+/* the operator's coefficients in registers for the whole kernel: without the empty asm the
+ * shuffle (whose result ptxas cannot rematerialise) the constant bank is re-read inside the
+ * accumulation loops, one uniform load per trip */
+template <class Op>
+__device__ __forceinline__ void load_params(const dc_params_t &P, double (&prm)[DC_MAX_PARAMS])
+{
+#pragma unroll
+    for (int i = 0; i < DC_MAX_PARAMS; i++) {
+        prm[i] = 0.0;
+        if (i < Op::NPARAM) {
+            const long long b = __double_as_longlong(P.v[i]);
+            const unsigned lo = __shfl_sync(0xffffffffu, (unsigned)b, 0), hi = __shfl_sync(0xffffffffu, (unsigned)(b >> 32), 0);
+            prm[i] = __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+        }
+    }
+}
 
 /* experiment builds only (make variant DEFS=-DDC_KO): knock-out bits from the environment variable
  * DC_KO switch phases of the unit kernel off (wrong results) to measure what each one costs:
@@ -105,7 +123,7 @@ __constant__ int c_ko;
 
 template <class Op>
 __device__ __forceinline__ void load_element(const int *__restrict__ conn, const double *__restrict__ coord,
-                                             int64_t e, double *rec)
+                                             int64_t e, const double *prm, double *rec)
 {
     const int4 c = __ldg(reinterpret_cast<const int4 *>(conn) + e);
     const int n[4] = {c.x - 1, c.y - 1, c.z - 1, c.w - 1};
@@ -114,7 +132,7 @@ __device__ __forceinline__ void load_element(const int *__restrict__ conn, const
     for (int a = 0; a < 4; a++)
 #pragma unroll
         for (int k = 0; k < 3; k++) x[a][k] = __ldg(coord + (int64_t)n[a] * 3 + k);
-    Op::setup(x, c_params, rec);
+    Op::setup(x, prm, rec);
 }
 
 /* ---- deterministic assembly over work units ------------------------------ */
@@ -183,42 +201,99 @@ __device__ __forceinline__ void flush_stage(double *__restrict__ values, const d
     }
 }
 
+/* depth of the software pipeline of the accumulation loops: operands are fetched this many
+ * contributions ahead of their use, items twice as far.  Measured at 160^3 (profiles/README.md,
+ * round 2): 1/1 and 2/1 are equal, deeper rings lose (more registers live across the loop, the
+ * pipe is throughput-bound, not latency-bound) */
+#ifndef DC_PIPE_DIAG
+#define DC_PIPE_DIAG 2
+#endif
+#ifndef DC_PIPE_UPPER
+#define DC_PIPE_UPPER 1
+#endif
+
+/* The contributions of one lane, in the order of its item column it[0], it[32], ... (ascending
+ * element index = the reference's order).  A ring of P operand sets: a contribution is applied,
+ * then its registers are refilled with the operands of the contribution P places further on (its
+ * item was loaded another P places earlier), so P - 1 applications hide a shared-memory round
+ * trip.  iters is the same for the whole warp.  The loop body has no test: T full trips of P
+ * contributions, then the last P .. 2P-1 contributions with the remaining fetches behind P - 1
+ * uniform tests (per task, not per contribution); item loads past the end are clamped (one
+ * wavefront each, at most P per task). */
+template <class Op, int P, bool DIAG>
+__device__ __forceinline__ void accumulate_lane(const uint16_t *it, const int iters, const double *recs,
+                                                const double *prm, double (&acc)[Op::D * Op::D])
+{
+    constexpr int RS = (Op::NS % 2 == 0) ? Op::NS + 1 : Op::NS;
+    constexpr int NO = DIAG ? Op::NOPS_DIAG : Op::NOPS;
+    auto fetch = [&](double (&o)[NO], uint32_t item) {
+        if constexpr (DIAG) Op::fetch_diag(recs + (item >> 4) * RS, item & 3u, o);
+        else Op::fetch(recs + (item >> 4) * RS, item & 15u, o);
+    };
+    auto apply = [&](const double (&o)[NO]) {
+        if constexpr (DIAG) Op::apply_diag(o, prm, acc);
+        else Op::apply(o, prm, acc);
+    };
+    if (iters < P) {                       /* short lists (boundary rows): plain loop */
+        for (int i = 0; i < iters; i++) {
+            double o[NO];
+            fetch(o, it[i * 32]);
+            apply(o);
+        }
+        return;
+    }
+    double ops[P][NO];
+    uint32_t itm[P];
+    const int last = iters - 1;
+#pragma unroll
+    for (int j = 0; j < P; j++) itm[j] = it[j * 32];
+#pragma unroll
+    for (int j = 0; j < P; j++) {
+        fetch(ops[j], itm[j]);
+        itm[j] = it[min(j + P, last) * 32];
+    }
+    const int trips = (iters - P) / P;
+    int c = 0;
+    for (int t = 0; t < trips; t++, c += P) {
+#pragma unroll
+        for (int j = 0; j < P; j++) {
+            apply(ops[j]);
+            fetch(ops[j], itm[j]);
+            itm[j] = it[min(c + j + 2 * P, last) * 32];
+        }
+    }
+    const int rest = iters - c;            /* P <= rest < 2P: rest - P operand sets still to fetch */
+#pragma unroll
+    for (int j = 0; j < P; j++) {
+        apply(ops[j]);
+        if (j + P < rest) fetch(ops[j], itm[j]);
+    }
+#pragma unroll
+    for (int j = 0; j + 1 < P; j++)
+        if (j + P < rest) apply(ops[j]);
+}
+
 /* One task (P2): a lane owns one CSR edge and adds its contributions in ascending element order
  * (the order of the item rows); the block -- and, in the symmetric schedule, its transpose --
  * leaves through the warp's staging area as full-line streaming stores. */
 template <class Op, bool SYM>
 __device__ __forceinline__ void do_task(const dc_unit_t &u, const dc_task_t task, const uint16_t *itemS,
                                         const int2 *tgtS, const double *recs, double *myStage,
-                                        const int *__restrict__ diagRel, double *__restrict__ values, int lane)
+                                        const int *__restrict__ diagRel, double *__restrict__ values,
+                                        const double *prm, int lane)
 {
     constexpr int DD = UnitSmem<Op>::DD;
-    constexpr int RS = UnitSmem<Op>::RS;
     const uint16_t *it = itemS + task.itemRel + lane;
     double acc[DD];
 #pragma unroll
     for (int c = 0; c < DD; c++) acc[c] = 0.0;
     if (SYM && task.kind == DC_TASK_OWNDIAG) {
-        /* diagonal edges only: one gradient per contribution, symmetric block.  The loop is
-         * software-pipelined: item two iterations ahead, operands one ahead (indices are
-         * clamped; padding items point at the all-zero record) */
+        /* diagonal edges only: one gradient per contribution, symmetric block */
         if (DC_KO_ON(4)) return;
         const int iters = DC_KO_ON(16) ? 0 : task.iters;
         /* lanes without an edge (the last task of a class is partial) stay out of the loop, so a
          * half-warp without edges costs no shared-memory wavefronts */
-        if (iters > 0 && ((task.mask >> lane) & 1u)) {
-            double nxt[Op::NOPS_DIAG], cur[Op::NOPS_DIAG];
-            uint32_t item = it[0];
-            Op::fetch_diag(recs + (item >> 4) * RS, item & 3u, nxt);
-            item = it[(iters > 1 ? 1 : 0) * 32];
-            for (int i = 0; i + 1 < iters; i++) {
-#pragma unroll
-                for (int q = 0; q < Op::NOPS_DIAG; q++) cur[q] = nxt[q];
-                Op::fetch_diag(recs + (item >> 4) * RS, item & 3u, nxt);
-                item = it[(i + 2 < iters ? i + 2 : iters - 1) * 32];
-                Op::apply_diag(cur, c_params, acc);
-            }
-            Op::apply_diag(nxt, c_params, acc);        /* the last contribution: nothing left to fetch */
-        }
+        if (iters > 0 && ((task.mask >> lane) & 1u)) accumulate_lane<Op, DC_PIPE_DIAG, true>(it, iters, recs, prm, acc);
         Op::mirror(acc);
         const bool valid = (task.mask >> lane) & 1u;
         int t0 = -1;
@@ -239,20 +314,7 @@ __device__ __forceinline__ void do_task(const dc_unit_t &u, const dc_task_t task
     {
         const int iters = DC_KO_ON(16) ? 0 : task.iters;
         const bool holdsEdge = task.kind != DC_TASK_UPPER || ((task.mask >> lane) & 1u);
-        if (iters > 0 && holdsEdge) {
-            double nxt[Op::NOPS], cur[Op::NOPS];
-            uint32_t item = it[0];
-            Op::fetch(recs + (item >> 4) * RS, item & 15u, nxt);
-            item = it[(iters > 1 ? 1 : 0) * 32];
-            for (int i = 0; i + 1 < iters; i++) {
-#pragma unroll
-                for (int q = 0; q < Op::NOPS; q++) cur[q] = nxt[q];
-                Op::fetch(recs + (item >> 4) * RS, item & 15u, nxt);
-                item = it[(i + 2 < iters ? i + 2 : iters - 1) * 32];
-                Op::apply(cur, c_params, acc);
-            }
-            Op::apply(nxt, c_params, acc);             /* the last contribution: nothing left to fetch */
-        }
+        if (iters > 0 && holdsEdge) accumulate_lane<Op, DC_PIPE_UPPER, false>(it, iters, recs, prm, acc);
     }
     if (task.kind == DC_TASK_DIAG) {
         if ((task.mask >> lane) & 1u) {
@@ -318,7 +380,7 @@ template <class Op, int NW, bool SYM>
 __device__ __forceinline__ void run_tasks(const dc_unit_t &u, const dc_task_t *taskS, const uint16_t *itemS,
                                           const int2 *tgtS, const double *recs, int *nextTask, double *myStage,
                                           const int *__restrict__ diagRel, double *__restrict__ values,
-                                          int warp, int lane)
+                                          const double *prm, int warp, int lane)
 {
     for (int t = warp; t < u.taskCount;) {
         const dc_task_t task = taskS[t];
@@ -327,7 +389,7 @@ __device__ __forceinline__ void run_tasks(const dc_unit_t &u, const dc_task_t *t
             if (lane == 0) nxt = atomicAdd(nextTask, 1);
             t = __shfl_sync(0xffffffffu, nxt, 0);
         }
-        do_task<Op, SYM>(u, task, itemS, tgtS, recs, myStage, diagRel, values, lane);
+        do_task<Op, SYM>(u, task, itemS, tgtS, recs, myStage, diagRel, values, prm, lane);
     }
 }
 
@@ -361,11 +423,14 @@ __global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *_
                                                               const int2 *__restrict__ tgtPairs,
                                                               const double *__restrict__ coord,
                                                               double *__restrict__ values, const UnitLayout L,
+                                                              const dc_params_t P,
                                                               long long *__restrict__ phaseClock)
 {
-    /* phaseClock (normally null): 8 clock64() stamps per unit, written by thread 0
-     * (tools/phase_times.py) */
-#define DC_STAMP(unit, i) do { if (phaseClock && tid == 0) phaseClock[(int64_t)(unit) * 8 + (i)] = clock64(); } while (0)
+    double prm[DC_MAX_PARAMS];
+    load_params<Op>(P, prm);
+    /* phaseClock (normally null): 24 clock64() stamps per unit: 8 written by thread 0, then the
+     * end of the tasks of every warp (tools/phase_times.py) */
+#define DC_STAMP(unit, i) do { if (phaseClock && tid == 0) phaseClock[(int64_t)(unit) * 24 + (i)] = clock64(); } while (0)
     constexpr int DD = UnitSmem<Op>::DD;
     constexpr int RS = UnitSmem<Op>::RS;
     constexpr int NW = THREADS / 32;
@@ -419,7 +484,7 @@ __global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *_
         mbar_init(&bar[2], 1);
         mbar_init(&bar[3], 1);
         *nextTask = NW;
-        *nextHalo = THREADS;
+        *nextHalo = THREADS > 32 ? THREADS - 32 : THREADS;
         descS[0] = units[unit];
         if (unit + stride < nbUnits) descS[1] = units[unit + stride];
     }
@@ -497,8 +562,8 @@ __global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *_
                 for (int a = 0; a < 4; a++)
 #pragma unroll
                     for (int q = 0; q < 3; q++) xb[a][q] = coordS[nb[a] * 3 + q];
-                Op::setup(xa, c_params, ra);
-                Op::setup(xb, c_params, rb);
+                Op::setup(xa, prm, ra);
+                Op::setup(xb, prm, rb);
 #pragma unroll
                 for (int i = 0; i < Op::NS; i++) recs[s0 * RS + i] = ra[i];
                 if (two) {
@@ -506,7 +571,7 @@ __global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *_
                     for (int i = 0; i < Op::NS; i++) recs[s1 * RS + i] = rb[i];
                 }
             } else {
-                Op::setup(xa, c_params, ra);
+                Op::setup(xa, prm, ra);
 #pragma unroll
                 for (int i = 0; i < Op::NS; i++) recs[s0 * RS + i] = ra[i];
             }
@@ -532,19 +597,27 @@ __global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *_
             cp_async_8(dst + 1, src + 1);
             cp_async_8(dst + 2, src + 2);
         };
-        const bool early = hasNext && mbar_test(&bar[3], (uint32_t)(k + 1) & 1u);
-        if (early && tid < descS[(k + 1) & 3].hnodeCount) copy_halo_node(tid);
+        /* warp 0 takes no part in the halo copies: it starts with the longest task (the diagonal
+         * chain) and is the last warp at sync B in 90 % of the units (tools/phase_times.py), so
+         * every copy it issued or waited for sat on the critical path; the other warps copy
+         * nodes tid - 32, tid - 32 + HT, ... */
+        constexpr int HT = THREADS > 32 ? THREADS - 32 : THREADS;      /* threads that copy halo nodes */
+        const int htid = THREADS > 32 ? tid - 32 : tid;
+        const bool copier = htid >= 0;
+        const bool early = copier && hasNext && mbar_test(&bar[3], (uint32_t)(k + 1) & 1u);
+        if (early && htid < descS[(k + 1) & 3].hnodeCount) copy_halo_node(htid);
         DC_STAMP(unit, 3);
 
-        run_tasks<Op, NW, SYM>(u, taskS, itemS, tgtS, recs, nextTask, myStage, diagRel, values, warp, lane);
+        run_tasks<Op, NW, SYM>(u, taskS, itemS, tgtS, recs, nextTask, myStage, diagRel, values, prm, warp, lane);
         DC_STAMP(unit, 4);
-        if (hasNext) {
+        if (phaseClock && lane == 0 && warp < 16) phaseClock[(int64_t)unit * 24 + 8 + warp] = clock64();   /* end of this warp's tasks */
+        if (hasNext && copier) {
             if (!early) mbar_wait(&bar[3], (uint32_t)(k + 1) & 1u);
             const int hCnt = descS[(k + 1) & 3].hnodeCount;
-            if (!early && tid < hCnt) copy_halo_node(tid);
-            /* the rare unit with more halo nodes than threads: chunks of 32, taken by the warps
-             * that run out of tasks first */
-            if (hCnt > THREADS) {
+            if (!early && htid < hCnt) copy_halo_node(htid);
+            /* the rare unit with more halo nodes than copying threads: chunks of 32, taken by the
+             * warps that run out of tasks first */
+            if (hCnt > HT) {
                 for (;;) {
                     int c = 0;
                     if (lane == 0) c = atomicAdd(nextHalo, 32);
@@ -561,7 +634,7 @@ __global__ void __launch_bounds__(THREADS, MINB) gather_units(const dc_unit_t *_
         if (!hasNext) break;
         if (tid == 0) {
             *nextTask = NW;
-            *nextHalo = THREADS;
+            *nextHalo = HT;
             if (!L.schedStride) issue_sched(descS[(k + 1) & 3], k + 1);
         }
         unit = next;
@@ -578,19 +651,21 @@ __global__ void __launch_bounds__(128) gather_lists(const int64_t *__restrict__ 
                                                     const int64_t *__restrict__ edgeT, int64_t nbEdges,
                                                     const int *__restrict__ conn,
                                                     const double *__restrict__ coord,
-                                                    double *__restrict__ values)
+                                                    double *__restrict__ values, const dc_params_t P)
 {
     constexpr int DD = Op::D * Op::D;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nbEdges) return;
+    double prm[DC_MAX_PARAMS];
+    load_params<Op>(P, prm);
     double acc[DD];
 #pragma unroll
     for (int c = 0; c < DD; c++) acc[c] = 0.0;
     for (int64_t q = ptr[i]; q < ptr[i + 1]; q++) {
         const uint32_t it = __ldg(item + q);
         double rec[Op::NS];
-        load_element<Op>(conn, coord, (int64_t)(it >> 4), rec);
-        Op::accumulate(rec, c_params, it & 15u, acc);
+        load_element<Op>(conn, coord, (int64_t)(it >> 4), prm, rec);
+        Op::accumulate(rec, prm, it & 15u, acc);
     }
     double *dst = values + edge[i] * DD;
 #pragma unroll
@@ -609,15 +684,18 @@ __global__ void __launch_bounds__(128) scatter_atomic(const int *__restrict__ co
                                                       const double *__restrict__ coord,
                                                       const int *__restrict__ row,
                                                       const int *__restrict__ col, int colBase,
-                                                      int64_t nbElem, double *__restrict__ values)
+                                                      int64_t nbElem, double *__restrict__ values,
+                                                      const dc_params_t P)
 {
     constexpr int DD = Op::D * Op::D;
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= nbElem) return;
+    double prm[DC_MAX_PARAMS];
+    load_params<Op>(P, prm);
     const int4 c = __ldg(reinterpret_cast<const int4 *>(conn) + e);
     const int n[4] = {c.x - 1, c.y - 1, c.z - 1, c.w - 1};
     double rec[Op::NS];
-    load_element<Op>(conn, coord, e, rec);
+    load_element<Op>(conn, coord, e, prm, rec);
 #pragma unroll
     for (int a = 0; a < 4; a++) {
         const int r0 = __ldg(row + n[a]), r1 = __ldg(row + n[a] + 1);
@@ -630,7 +708,7 @@ __global__ void __launch_bounds__(128) scatter_atomic(const int *__restrict__ co
             double blk[DD];
 #pragma unroll
             for (int q = 0; q < DD; q++) blk[q] = 0.0;
-            Op::accumulate(rec, c_params, (uint32_t)(4 * a + b), blk);   /* = K_e[a][b] */
+            Op::accumulate(rec, prm, (uint32_t)(4 * a + b), blk);   /* = K_e[a][b] */
             double *dst = values + (int64_t)k * DD;
 #pragma unroll
             for (int q = 0; q < DD; q++) red_add_f64(dst + q, blk[q]);

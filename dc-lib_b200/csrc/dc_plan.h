@@ -110,7 +110,9 @@ extern "C" {
  * connectivity; row/col: CSR pattern (col numbering base colBase, any order
  * within a row); leaves: nbLeaves x 8 ints {firstElem,lastElem,lastSep,firstNode,
  * lastNode,isSep,isLeaf,parent-free flag} in PRE-ORDER of the tree -- see
- * dc_plan_build_from_tree for the pointer-tree front end.  Returns 0 on success. */
+ * dc_plan_build_from_tree for the pointer-tree front end.  Returns 0 on success; -5 when rows
+ * fall back to the per-edge lists (or dc_contrib_build is called) on a mesh of 2^28 or more
+ * elements: list items hold the element index in 28 bits. */
 int  dc_plan_build(dc_plan_t *plan, const int *conn, int nbElem, int nbNodes, const int *row,
                    const int *col, int colBase, const int *treeRec, int64_t nbTreeRec,
                    int maxSlots, int nbThreads, int symmetric);

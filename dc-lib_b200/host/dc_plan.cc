@@ -900,6 +900,8 @@ extern "C" int dc_contrib_build(dc_contrib_list_t *out, const int *conn, int nbE
                                 const int *row, const int *col, int colBase, const int *rows,
                                 int64_t nbRows, int symmetric)
 {
+    /* list items are elem << 4 | a << 2 | b in 32 bits: the element must fit 28 bits */
+    if (nbElem >= (1 << 28)) return -5;
     Mesh m{conn, nbElem, nbNodes, row, col, colBase, {}, nullptr, {}};
     build_node_to_elem(m);
     std::vector<int64_t> edge, ptr, edgeT;
@@ -960,7 +962,6 @@ extern "C" int dc_plan_build(dc_plan_t *plan, const int *conn, int nbElem, int n
         if (verbose) { double t1 = omp_get_wtime(); fprintf(stderr, "[dc_plan] %-12s %.2fs\n", what, t1 - t0); t0 = t1; }
     };
     if (maxSlots < 16 || maxSlots > DC_SLOT_LIMIT) return -1;
-    if (nbElem >= (1 << 28)) { /* fallback items hold the element in 28 bits */ }
     Mesh m{conn, nbElem, nbNodes, row, col, colBase, {}, nullptr, {}};
     build_node_to_elem(m);
 
@@ -1170,6 +1171,7 @@ extern "C" int dc_plan_build(dc_plan_t *plan, const int *conn, int nbElem, int n
     plan->nbSlotsTotal = slotsTotal;
     plan->nbItemsUseful = useful;
     if (!bigRows.empty()) {
+        /* hub rows go to the per-edge lists, whose items hold the element in 28 bits: -5 beyond that */
         int rc = dc_contrib_build(&plan->big, conn, nbElem, nbNodes, row, col, colBase,
                                   bigRows.data(), (int64_t)bigRows.size(), symmetric);
         if (rc) return rc;

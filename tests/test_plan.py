@@ -176,3 +176,16 @@ def test_plan_without_tree_uses_row_blocks(tmp_path):
     mesh = prepare_mesh(MineLib(0), 8, tmp_path)
     plan = dc.HostPlan(mesh["conn"], mesh["N"], mesh["row"], mesh["col"], 0, None, 300, symmetric=False)
     assert plan.c.nbUnits > 1 and plan.c.nbItemsUseful == 16 * mesh["E"]
+
+
+def test_list_items_refuse_meshes_beyond_28_bit_element_indices():
+    """Fallback / DC_MODE_LIST items are elem << 4 | a << 2 | b in 32 bits: dc_contrib_build must refuse 2^28 or
+    more elements instead of truncating the element index (checked before any array is touched)."""
+    import ctypes
+    cl = dc.ContribList()
+    conn = np.ones((1, 4), dtype=np.int32)
+    row = np.zeros(2, dtype=np.int32)
+    col = np.zeros(1, dtype=np.int32)
+    rc = dc.lib().dc_contrib_build(ctypes.byref(cl), conn.ctypes.data, 1 << 28, 1, row.ctypes.data, col.ctypes.data, 0,
+                                   None, 0, 1)
+    assert rc == -5

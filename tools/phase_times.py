@@ -1,31 +1,41 @@
-"""Per-phase cycle counts of gather_units (clock64 stamps of thread 0, debug hook)."""
-import sys, os, tempfile, ctypes
+"""Per-phase cycle counts of gather_units (clock64 stamps, debug hook dc_cuda_debug_phases): thread 0's
+phases and the end of the tasks of every warp, on the bench geometry.
+usage: python tools/phase_times.py <cube> <slots> <threads> [leaf_nodes=62]"""
+import sys, os, ctypes
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT)
 import numpy as np, torch
 import dc_lib_b200 as dc
-import common
-n = int(sys.argv[1]); slots = int(sys.argv[2]); threads = int(sys.argv[3]); geo = len(sys.argv) > 4 and sys.argv[4] == 'geo'
-with tempfile.TemporaryDirectory() as tmp:
-    mesh = common.prepare_mesh(common.MineLib(0, geometric=geo), n, tmp)
-plan = dc.HostPlan(mesh["conn"], mesh["N"], mesh["row"], mesh["col"], 0, common.tree_records(mesh), slots)
-ctx = dc.Context(0); ctx.set_mesh(mesh["conn"], mesh["coord"], mesh["row"], mesh["col"], 0); ctx.upload_plan(plan)
+import bench
+n = int(sys.argv[1]); slots = int(sys.argv[2]); threads = int(sys.argv[3])
+leaf_nodes = int(sys.argv[4]) if len(sys.argv) > 4 else 62
+dc.DC_set_max_elem_per_part(bench.leaf_capacity(n, leaf_nodes))
+w = bench.build_workload(dc, n, 0, "geometric")
+plan = dc.HostPlan(w["conn"], w["N"], w["row"], w["col"], 0, w["rec"], slots)
+ctx = dc.Context(0); ctx.set_mesh(w["conn"], w["coord"], w["row"], w["col"], 0); ctx.upload_plan(plan)
 ctx.set_option("unit_threads", threads)
-ctx.set_option("persistent", int(sys.argv[5]) if len(sys.argv) > 5 else 1)
-vals = torch.empty(mesh["nnz"] * 9, dtype=torch.float64, device="cuda")
-prm = [common.LAMBDA, common.MU]
+vals = torch.empty(w["nnz"] * 9, dtype=torch.float64, device="cuda")
+prm = [bench.LAMBDA, bench.MU]
 for _ in range(3): ctx.assemble(dc.OP_ELASTICITY, prm, dc.MODE_DETERMINISTIC, vals)
 L = dc.lib(); L.dc_cuda_debug_phases.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
 L.dc_cuda_debug_phases(ctx.h, None)
 ctx.assemble(dc.OP_ELASTICITY, prm, dc.MODE_DETERMINISTIC, vals)
 nu = plan.c.nbUnits
-out = np.zeros((nu, 8), dtype=np.int64)
+out = np.zeros((nu, 24), dtype=np.int64)
 L.dc_cuda_debug_phases(ctx.h, out.ctypes.data)
-persistent = int(sys.argv[5]) if len(sys.argv) > 5 else 1
-out = out[out[:, 1] > 0]          # stamp 0 only exists for the first unit of each CTA
+out = out[out[:, 1] > 0]
 d = np.diff(out[:, 1:7], axis=1)
-names = ["records (P1b) + sync A", "wait schedule", "accumulate+store (warp 0)", "halo gather of next unit", "sync B (other warps)"]
+names = ["records (P1b) + sync A", "issue copies of next unit", "tasks (warp 0)", "halo gather of next unit", "sync B (wait for others)"]
 tot = (out[:, 6] - out[:, 1])
-print(f"units {nu}  elements {mesh['E']}  own elems/unit {mesh['E']/nu:.0f}  mean cycles/unit {tot.mean():.0f}")
+st = plan.stats()
+print(f"units {nu}  elements {w['E']}  elems/unit {w['E']/nu:.0f}  tasks/unit {st['tasks']/nu:.2f}  mean cycles/unit {tot.mean():.0f}")
 for i, nm in enumerate(names):
-    print(f"  {nm:24s} mean {d[:, i].mean():8.0f}  median {np.median(d[:, i]):8.0f}  share {d[:, i].sum()/tot.sum()*100:5.1f}%")
+    print(f"  {nm:28s} mean {d[:, i].mean():8.0f}  median {np.median(d[:, i]):8.0f}  share {d[:, i].sum()/tot.sum()*100:5.1f}%")
+nw = threads // 32
+ends = out[:, 8:8 + nw] - out[:, 3:4]          # end of every warp's tasks, relative to the start of the task phase
+print("end of tasks per warp (cycles after the start of the task phase), mean:")
+print("  " + " ".join(f"w{i}:{ends[:, i].mean():.0f}" for i in range(nw)))
+srt = np.sort(ends, axis=1)
+print(f"  first warp done {srt[:, 0].mean():.0f}  median warp {srt[:, nw // 2].mean():.0f}  last warp {srt[:, -1].mean():.0f}  "
+      f"last is warp 0 in {np.mean(np.argmax(ends, axis=1) == 0) * 100:.0f}% of units; mean idle per warp before sync B "
+      f"{(srt[:, -1:] - ends).mean():.0f}")
