@@ -8,6 +8,7 @@
  * callbacks cannot execute on the GPU -- the accelerated path is
  * DC_assembly_device() (dc_device.cc), which never comes through here.
  */
+#include <cstdio>
 #include <cstring>
 #include <omp.h>
 #include "dc_internal.h"
@@ -93,6 +94,16 @@ void DC_tree_traversal (void (*userSeqFct)(void *, DCargs_t *), void (*userVecFc
                         void (*userCommFct)(void *, DCcommArgs_t *), void *userArgs,
                         void *userCommArgs)
 {
+    /* userCommFct is only called by the reference's MULTITHREADED_COMM variant (tree_traversal.cc:65-73);
+     * like its BULK_SYNCHRONOUS variant this traversal never calls it -- said once, not silently */
+    if (userCommFct) {
+        static bool told = false;
+        if (!told) {
+            told = true;
+            fprintf(stderr, "DC_tree_traversal: userCommFct is not called (bulk-synchronous library): exchange the interface "
+                            "after the traversal.\n");
+        }
+    }
     LeafVisitor v{userSeqFct, userVecFct, userCommFct, userArgs, userCommArgs,
                   dc::options().vecSize > 0 && userVecFct != nullptr};
     run(v);

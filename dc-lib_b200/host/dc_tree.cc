@@ -459,8 +459,22 @@ void DC_finalize_tree (int *nodeToNodeRow, int *elemToNode, int *intfIndex, int 
                        int *intfDstOffsets, int *nbDCcomm, int nbElem, int dimElem,
                        int nbBlocks, int nbIntf, int rank)
 {
-    (void)elemToNode; (void)intfIndex; (void)intfNodes; (void)intfDstOffsets; (void)nbDCcomm;
-    (void)nbElem; (void)dimElem; (void)nbBlocks; (void)nbIntf; (void)rank;
+    /* The interface arguments only matter to the reference's MULTITHREADED_COMM variant
+     * (tree_creation.cc:48-169: per-leaf slices of the MPI interface); this library behaves like the
+     * BULK_SYNCHRONOUS variant, which ignores them too (tree_creation.cc:176-202) -- the interface
+     * exchange of the device path is dc_cuda_exchange_* (include/dc_cuda.h).  A caller re-linked from a
+     * MULTITHREADED_COMM build is told so once instead of silently getting no per-leaf communication. */
+    (void)elemToNode; (void)intfIndex; (void)intfNodes; (void)intfDstOffsets;
+    (void)nbElem; (void)dimElem; (void)nbBlocks; (void)rank;
+    if (nbDCcomm) *nbDCcomm = 0;
+    if (nbIntf > 0 && intfIndex) {
+        static bool told = false;
+        if (!told) {
+            told = true;
+            fprintf(stderr, "DC_finalize_tree: %d interfaces given; this library is bulk-synchronous (no per-leaf interface "
+                            "lists, nbDCcomm = 0): exchange after the assembly, or use dc_cuda_exchange_* on the device path.\n", nbIntf);
+        }
+    }
     if (!treeHead) dc::fatal("Error: DC_finalize_tree called without a D&C tree.");
     finalize_rec(treeHead, nodeToNodeRow);
 }
