@@ -31,6 +31,10 @@ WORKLOADS = {
     "c2": (40, 3, 4, "metis"),               # BASELINE config 2: 40^3, elasticity, D&C + colouring
     "m100": (100, 3, 0, "metis"),            # 6M tets, elasticity (METIS tree, as the reference builds it)
     "m64": (64, 3, 0, "metis"),
+    # BASELINE config 4: ONE graded / relabelled / shuffled cube, METIS-split over the GPUs (strong scaling);
+    # DC_BENCH_C4_N sets the cube (default 200^3 = 48 M tets: the METIS cut of rank 0 and the extraction of the
+    # parts are host work that has to fit the GPU-minutes of a run)
+    "c4": (int(os.environ.get("DC_BENCH_C4_N", "200")), 3, 0, "geometric"),
 }
 
 
@@ -203,7 +207,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    config = {"workload": f"{args.workload}: jittered Kuhn cube {n}^3 ({6 * n ** 3} tets) per GPU, "
+    c4 = args.workload == "c4"
+    config = {"workload": f"{args.workload}: jittered Kuhn cube {n}^3 ({6 * n ** 3} tets) {'in all, graded + relabelled + shuffled, cut into one part per GPU by DC_partition_mesh (' + os.environ.get('DC_BENCH_C4_PARTITION', 'metis') + ')' if c4 else 'per GPU'}, "
                           f"operatorDim {dim} ({'isotropic elasticity' if dim == 3 else 'P1 Laplacian'}), "
                           f"{'D&C + colouring VEC_SIZE ' + str(vec) if vec else 'pure D&C'} tree "
                           f"({'METIS node partitions' if builder == 'metis' else 'coordinate-bisection node partitions'}), "
@@ -242,8 +247,12 @@ def main():
 
     # one slab (cube) per GPU; rank 0 builds tree / CSR / schedule, the others get them over NCCL
     dc.DC_set_max_elem_per_part(capacity)
-    ctx, info = multigpu.setup_device_slabs(n, rank, world, device, builder=builder, vec=vec, slots=args.slots, dist=dist,
-                                            bank_model=int(os.environ.get("DC_BENCH_BANK_MODEL", "1" if dim == 1 else "0")))
+    if c4:
+        ctx, info = multigpu.setup_device_parts(n, rank, world, device, slots=args.slots, dist=dist,
+                                                partition=os.environ.get("DC_BENCH_C4_PARTITION", "metis"))
+    else:
+        ctx, info = multigpu.setup_device_slabs(n, rank, world, device, builder=builder, vec=vec, slots=args.slots, dist=dist,
+                                                bank_model=int(os.environ.get("DC_BENCH_BANK_MODEL", "1" if dim == 1 else "0")))
     ctx.set_option("unit_threads", args.threads)
     ctx.set_option("persistent", args.persistent)
     E, N, nnz, st = info["E"], info["N"], info["nnz"], info["stats"]
@@ -251,7 +260,8 @@ def main():
     per = dim * dim
     vals = torch.empty(nnz * per, dtype=torch.float64, device=device)
     stream = torch.cuda.current_stream().cuda_stream
-    exch = multigpu.DeviceInterfaceExchange(info["intf"], per, device, dist) if world > 1 else None
+    exch = multigpu.device_exchange(info["intf"], per, device, dist, rank, world) if world > 1 else None
+    overlap = os.environ.get("DC_BENCH_OVERLAP", "1") != "0"
 
     def barrier():
         if world > 1:
@@ -259,9 +269,13 @@ def main():
         torch.cuda.synchronize()
 
     def step():
-        ctx.assemble(op, prm, dc.MODE_DETERMINISTIC, vals, stream)
-        if exch:
-            exch.run(vals, stream)           # NCCL send/recv of interface partial sums + unpack-add
+        if exch and overlap:
+            # interface units, pack over NVLink || interior units, unpack-add (dc_cuda_assemble_exchange)
+            ctx.assemble_exchange(exch, op, prm, vals, stream)
+        else:
+            ctx.assemble(op, prm, dc.MODE_DETERMINISTIC, vals, stream)
+            if exch:
+                exch.run(vals, stream)       # pack into the neighbours' buffers, wait, unpack-add
 
     # ---- device-resident timing -------------------------------------------------------
     for _ in range(args.warmup):
@@ -332,10 +346,16 @@ def main():
     else:
         host_matches_device = None
 
+    per_rank = None
     if world > 1:
         t = torch.tensor([ms, e2e_ms, kernel_ms], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, e2e_ms, kernel_ms = float(t[0]), float(t[1]), float(t[2])
+        mine = torch.tensor([E, info.get("interface_edges", 0), exch.bytes_per_step if exch else 0, info.get("nb_front", 0)],
+                            dtype=torch.int64, device=device)
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = [[int(v) for v in a.tolist()] for a in allr]
         dist.barrier()
     if rank != 0:
         if world > 1:
@@ -354,14 +374,15 @@ def main():
         traffic, traffic_src = tj["dram_bytes_per_element"] * E, tj["source"]
     achieved = b_alg / (kernel_ms * 1e-3) / 1e9
     line = {
-        "metric": "assembled elements/s (fp64, CSR scatter-add)", "value": world * E / (ms * 1e-3), "unit": "elements/s",
+        "metric": "assembled elements/s (fp64, CSR scatter-add)",
+        "value": (info["E_global"] if c4 else world * E) / (ms * 1e-3), "unit": "elements/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+        "scaling": "strong" if c4 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "kernel": "gather_units", "kernel_ms": kernel_ms,
                      "algorithmic_bytes_per_launch": b_alg, "bytes_per_element": b_alg / E},
-        "e2e": {"value": world * E / (e2e_ms * 1e-3), "unit": "elements/s", "ms_per_step": e2e_ms,
+        "e2e": {"value": (info["E_global"] if c4 else world * E) / (e2e_ms * 1e-3), "unit": "elements/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": 24 * N, "d2h_bytes_per_step": 8 * per * nnz, "steps": e2e_steps,
                 "host_buffer": host_buffer, "checksum": checksum, "host_matches_device_sample": host_matches_device},
         "gpu_launches": launches, "clocks": sampler.summary(),
@@ -370,8 +391,18 @@ def main():
                   "item_padding_efficiency": st["items_useful"] / max(st["items"], 1), "host_cores": os.cpu_count()},
     }
     if world > 1:
-        line["config"]["parallelism"] = (f"{world} slabs (one cube per GPU, stacked along x), interface-edge partial sums "
-                                         "exchanged with NCCL send/recv and added by the unpack-add kernel")
+        line["config"]["parallelism"] = (f"{world} slabs (one cube per GPU, stacked along x), interface-edge partial sums pushed "
+                                         "into the neighbours' buffers over NVLink peer memory (dc_cuda_exchange), "
+                                         + ("overlapped with the interior units" if overlap else "after the assembly"))
+        line["front_units"] = info.get("nb_front", 0)
+        if c4:
+            line["config"]["parallelism"] = (f"{world} parts of one mesh (DC_partition_mesh), every rank its own D&C tree and schedule; "
+                                             "partial sums of the CSR edges two or more ranks hold pushed over NVLink peer memory "
+                                             "(dc_cuda_exchange), " + ("overlapped with the interior units" if overlap else "after the assembly"))
+            line["per_rank"] = {"elements": [r[0] for r in per_rank], "interface_edges": [r[1] for r in per_rank],
+                                "interface_bytes_per_step": [r[2] for r in per_rank], "front_units": [r[3] for r in per_rank]}
+            line["setup"]["partition_s"] = info.get("partition_s")
+            line["setup"]["mesh_s"] = info.get("mesh_s")
         line["interface_bytes_per_step_per_gpu"] = exch.bytes_per_step
     if not args.no_cpu_baseline and world == 1:      # the CPU arm is reported at N = 1 only
         base = cpu_reference(dim, 3, 1, leaf_nodes=args.leaf_nodes)

@@ -121,6 +121,28 @@ def _declare(L):
     L.dc_cuda_spmv.argtypes = [vp, c_int, vp, vp, vp, vp]
     L.dc_cuda_pack_edges.argtypes = [vp, vp, c_int64, c_int, vp, vp]
     L.dc_cuda_unpack_add_edges.argtypes = [vp, vp, c_int64, c_int, vp, vp]
+    L.dc_cuda_exchange_create.argtypes = [POINTER(c_void_p), c_int, c_int, c_int, vp, vp, vp]
+    L.dc_cuda_exchange_create_device.argtypes = [POINTER(c_void_p), c_int, c_int, c_int, vp, vp, vp]
+    L.dc_cuda_exchange_neighbours.argtypes = [vp]
+    L.dc_cuda_exchange_export.argtypes = [vp, c_int, vp]
+    L.dc_cuda_exchange_import.argtypes = [vp, c_int, vp]
+    L.dc_cuda_exchange_pack.argtypes = [vp, vp, vp]
+    L.dc_cuda_exchange_unpack.argtypes = [vp, vp, vp]
+    L.dc_cuda_exchange_run.argtypes = [vp, vp, vp]
+    L.dc_cuda_exchange_bytes.argtypes = [vp]
+    L.dc_cuda_exchange_bytes.restype = c_int64
+    L.dc_cuda_exchange_set_blocks.argtypes = [vp, c_int]
+    L.dc_cuda_exchange_destroy.argtypes = [vp]
+    L.dc_cuda_exchange_destroy.restype = None
+    L.dc_cuda_exchange_last_error.restype = c_char_p
+    L.dc_cuda_set_front_units.argtypes = [vp, c_int64]
+    L.dc_cuda_assemble_units.argtypes = [vp, c_int, vp, c_int, vp, vp, c_int64, c_int64, c_int, c_int]
+    L.dc_cuda_assemble_exchange.argtypes = [vp, vp, c_int, vp, c_int, vp, vp]
+    L.dc_cuda_assemble_exchange_with.argtypes = [vp, vp, vp, vp, c_int, vp, vp]
+    L.dc_interface_edges.argtypes = [vp, vp, c_int, vp, c_int, vp, vp]
+    L.dc_interface_edges.restype = c_int64
+    L.dc_plan_order_units.argtypes = [POINTER(Plan), vp]
+    L.dc_plan_order_units.restype = c_int64
     L.dc_cuda_csr_begin.argtypes = [vp, c_int, c_int, vp, POINTER(c_int64), POINTER(c_void_p), vp]
     L.dc_cuda_csr_columns.argtypes = [vp, vp, c_int, vp]
     L.dc_cuda_csr_node_to_elem.argtypes = [vp, vp, vp, vp]
@@ -310,6 +332,12 @@ class HostPlan:
                     maxTasks=int(c.maxTasks), maxItems=int(c.maxItems), maxTgt=int(c.maxTgt),
                     symmetric=int(c.symmetric), bigEdges=int(c.big.nbEdges))
 
+    def order_units(self, node_flag):
+        """Units that own a flagged row (uint8 per node: the interface nodes) move to the front of the
+        schedule (dc_plan_order_units); returns their number, for Context.set_front_units."""
+        flag = np.ascontiguousarray(node_flag, dtype=np.uint8)
+        return int(lib().dc_plan_order_units(byref(self.c), _p(flag)))
+
     def diag_rel(self, nbNodes):
         return np.ctypeslib.as_array(self.c.diagRel, shape=(max(nbNodes, 1),))[:nbNodes]
 
@@ -398,6 +426,22 @@ class Context:
         self._ck(lib().dc_cuda_assemble_with(self.h, launcher, _p(prm) if prm.size else None, prm.size, mode,
                                              _p(values), stream), "dc_cuda_assemble_with")
 
+    def set_front_units(self, n):
+        self._ck(lib().dc_cuda_set_front_units(self.h, int(n)), "dc_cuda_set_front_units")
+
+    def assemble_units(self, op, params, values, first, count, reserve=0, skip_big=False, stream=None):
+        prm = np.ascontiguousarray(params if params is not None else [], dtype=np.float64)
+        self._ck(lib().dc_cuda_assemble_units(self.h, op, _p(prm) if prm.size else None, prm.size, _p(values), stream,
+                                              int(first), int(count), int(reserve), 1 if skip_big else 0),
+                 "dc_cuda_assemble_units")
+
+    def assemble_exchange(self, exchange, op, params, values, stream=None):
+        """One step of a multi-GPU rank: front units, pack || other units, unpack (dc_cuda_assemble_exchange)."""
+        prm = np.ascontiguousarray(params if params is not None else [], dtype=np.float64)
+        self._ck(lib().dc_cuda_assemble_exchange(self.h, exchange.h if exchange is not None else None, op,
+                                                 _p(prm) if prm.size else None, prm.size, _p(values), stream),
+                 "dc_cuda_assemble_exchange")
+
     def assemble_to_host(self, op, params, mode, out, stream=None):
         """The call a reference user makes: values land in the HOST array `out`."""
         dim = OP_DIM[op]
@@ -429,6 +473,96 @@ class Context:
             self.close()
         except Exception:
             pass
+
+
+class DeviceExchange:
+    """Binding of dc_cuda_exchange_* (include/dc_cuda.h): interface exchange over peer memory.
+    intf: {neighbour rank: local CSR edges shared with it (numpy int64 or torch CUDA int64), in the
+    order both sides agree on}.  Handles travel through `dist` (torch.distributed, one rank per
+    process) or are swapped directly with connect_local() when the ranks live in one process."""
+
+    HANDLE_BYTES = 128
+
+    def __init__(self, intf, per_edge, device_index):
+        import torch
+        self.nbs = sorted(intf)
+        self.per = per_edge
+        counts = [int(intf[nb].shape[0]) if hasattr(intf[nb], "shape") else len(intf[nb]) for nb in self.nbs]
+        ptr = np.zeros(len(self.nbs) + 1, dtype=np.int64)
+        ptr[1:] = np.cumsum(counts)
+        ranks = np.ascontiguousarray(self.nbs, dtype=np.int32)
+        self.h = c_void_p()
+        on_device = any(isinstance(intf[nb], torch.Tensor) and intf[nb].is_cuda for nb in self.nbs)
+        if on_device:
+            self._edges = (torch.cat([intf[nb].to(torch.int64).reshape(-1) for nb in self.nbs]) if self.nbs
+                           else torch.zeros(0, dtype=torch.int64, device=f"cuda:{device_index}"))
+            rc = lib().dc_cuda_exchange_create_device(byref(self.h), device_index, per_edge, len(self.nbs), _p(ranks), _p(ptr),
+                                                      _p(self._edges))
+        else:
+            edges = (np.ascontiguousarray(np.concatenate([np.asarray(intf[nb], dtype=np.int64) for nb in self.nbs]))
+                     if self.nbs else np.zeros(0, dtype=np.int64))
+            rc = lib().dc_cuda_exchange_create(byref(self.h), device_index, per_edge, len(self.nbs), _p(ranks), _p(ptr), _p(edges))
+        if rc:
+            raise RuntimeError("dc_cuda_exchange_create: " + lib().dc_cuda_exchange_last_error().decode())
+        self.bytes_per_step = int(lib().dc_cuda_exchange_bytes(self.h))
+        self.launches_per_step = 2 * len(self.nbs)
+
+    def _ck(self, rc, what):
+        if rc:
+            raise RuntimeError(f"{what}: {lib().dc_cuda_exchange_last_error().decode()} (code {rc})")
+
+    def export(self, nb):
+        buf = ctypes.create_string_buffer(self.HANDLE_BYTES)
+        self._ck(lib().dc_cuda_exchange_export(self.h, self.nbs.index(nb), buf), "dc_cuda_exchange_export")
+        return buf.raw
+
+    def import_(self, nb, handle):
+        self._ck(lib().dc_cuda_exchange_import(self.h, self.nbs.index(nb), handle), "dc_cuda_exchange_import")
+
+    def connect(self, dist, rank, world):
+        """Swap the handles with the neighbours through torch.distributed (any backend)."""
+        mine = {(rank, nb): self.export(nb) for nb in self.nbs}
+        everyone = [None] * world
+        dist.all_gather_object(everyone, mine)
+        for nb in self.nbs:
+            self.import_(nb, everyone[nb][(nb, rank)])
+
+    @staticmethod
+    def connect_local(exchanges):
+        """exchanges: {rank: DeviceExchange} living in this process."""
+        for r, x in exchanges.items():
+            for nb in x.nbs:
+                x.import_(nb, exchanges[nb].export(r))
+
+    def pack(self, values, stream=None):
+        self._ck(lib().dc_cuda_exchange_pack(self.h, _p(values), stream), "dc_cuda_exchange_pack")
+
+    def unpack(self, values, stream=None):
+        self._ck(lib().dc_cuda_exchange_unpack(self.h, _p(values), stream), "dc_cuda_exchange_unpack")
+
+    def run(self, values, stream=None):
+        self._ck(lib().dc_cuda_exchange_run(self.h, _p(values), stream), "dc_cuda_exchange_run")
+
+    def close(self):
+        if self.h:
+            lib().dc_cuda_exchange_destroy(self.h)
+            self.h = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def interface_edges(row, col, nodes, colBase=0):
+    """CSR edges among the listed interface nodes (1-based, the reference's intfNodes slice of one
+    neighbour), ordered by (position of the row node, position of the column node): (edges, keys)."""
+    row, col, nodes = _i32(row), _i32(col), _i32(nodes)
+    n = lib().dc_interface_edges(_p(row), _p(col), colBase, _p(nodes), nodes.shape[0], None, None)
+    edges, keys = np.empty(n, dtype=np.int64), np.empty(n, dtype=np.int64)
+    lib().dc_interface_edges(_p(row), _p(col), colBase, _p(nodes), nodes.shape[0], _p(edges), _p(keys))
+    return edges, keys
 
 
 def permute_double_2d(d_in, d_out, d_perm, dimItem, stream=None):
@@ -524,4 +658,4 @@ def build_csr_fast(conn, nbNodes, colBase=0):
     return row, col
 
 
-from .meshgen import kuhn_cube, jitter_coords, build_csr, hub_collapse  # noqa: E402,F401
+from .meshgen import kuhn_cube, jitter_coords, build_csr, hub_collapse, scramble_mesh  # noqa: E402,F401

@@ -61,6 +61,11 @@ struct dc_cuda_ctx {
     int64_t valuesLen = 0;
     int64_t launches = 0;
     long long *d_phaseClock = nullptr;   /* debug: per-unit phase stamps (dc_cuda_debug_phases) */
+    /* multi-GPU step (dc_cuda_assemble_exchange): units that own interface rows come first in d_units */
+    int64_t nbFrontUnits = 0;
+    int exchangeReserve = 4;             /* CTA slots the interior launch leaves to the pack / unpack kernels */
+    cudaStream_t sideStream = nullptr;
+    cudaEvent_t evFront = nullptr, evJoin = nullptr;
 };
 
 extern "C" const char *dc_cuda_last_error(void) { return g_err.c_str(); }
@@ -115,6 +120,7 @@ static void free_plan(dc_cuda_ctx *c)
     c->d_units = nullptr; c->d_tasks = nullptr; c->d_items = nullptr; c->d_halo = c->d_diagRel = nullptr;
     c->d_bigEdge = c->d_bigPtr = nullptr; c->d_bigItem = nullptr;
     c->nbUnits = c->nbBigEdges = 0;
+    c->nbFrontUnits = 0;
 }
 static void free_lists(dc_cuda_ctx *c)
 {
@@ -129,6 +135,9 @@ extern "C" void dc_cuda_destroy(dc_cuda_ctx *c)
     cudaSetDevice(c->device);
     free_mesh(c); free_plan(c); free_lists(c);
     cudaFree(c->d_values);
+    if (c->sideStream) cudaStreamDestroy(c->sideStream);
+    if (c->evFront) cudaEventDestroy(c->evFront);
+    if (c->evJoin) cudaEventDestroy(c->evJoin);
     delete c;
 }
 
@@ -278,6 +287,7 @@ static void fill_args(const dc_cuda_ctx *c, int mode, dc_launch_args *a)
     a->d_bigEdge = c->d_bigEdge; a->d_bigPtr = c->d_bigPtr; a->d_bigEdgeT = c->d_bigEdgeT; a->d_bigItem = c->d_bigItem;
     a->d_listEdge = c->d_listEdge; a->d_listPtr = c->d_listPtr; a->d_listItem = c->d_listItem;
     a->d_phaseClock = c->d_phaseClock;
+    a->unitFirst = 0; a->unitCount = c->nbUnits; a->reserveCtas = 0; a->skipBigRows = 0;
 }
 
 static int explain(int rc)
@@ -321,6 +331,86 @@ extern "C" int dc_cuda_assemble(dc_cuda_ctx *c, int op, const double *h_params, 
             return dc_cuda_assemble_with(c, dc_builtin_elasticity, h_params, nbParams, mode, d_values, stream);
         default:
             return fail(-9, "dc_cuda_assemble: unknown operator");
+    }
+}
+
+/* a range of the units (the pieces dc_cuda_assemble_exchange is made of) */
+extern "C" int dc_cuda_assemble_units(dc_cuda_ctx *c, int op, const double *h_params, int nbParams, double *d_values,
+                                      void *stream, int64_t unitFirst, int64_t unitCount, int reserveCtas, int skipBigRows)
+{
+    if (!c || !c->d_coord) return fail(-1, "dc_cuda_assemble_units: no mesh");
+    if (!d_values || unitFirst < 0 || unitCount < 0 || unitFirst + unitCount > c->nbUnits)
+        return fail(-1, "dc_cuda_assemble_units: bad argument");
+    if (op != DC_OP_P1_TET_LAPLACIAN && op != DC_OP_P1_TET_ELASTICITY) return fail(-9, "dc_cuda_assemble_units: unknown operator");
+    CK(cudaSetDevice(c->device));
+    dc_launch_args a;
+    fill_args(c, DC_MODE_DETERMINISTIC, &a);
+    a.unitFirst = unitFirst; a.unitCount = unitCount; a.reserveCtas = reserveCtas; a.skipBigRows = skipBigRows;
+    const int rc = (op == DC_OP_P1_TET_LAPLACIAN ? dc_builtin_laplacian : dc_builtin_elasticity)(&a, h_params, nbParams, d_values, stream);
+    c->launches += a.launches;
+    return explain(rc);
+}
+
+extern "C" int dc_cuda_set_front_units(dc_cuda_ctx *c, int64_t nbFrontUnits)
+{
+    if (!c || nbFrontUnits < 0 || nbFrontUnits > c->nbUnits) return fail(-1, "dc_cuda_set_front_units: bad argument");
+    c->nbFrontUnits = nbFrontUnits;
+    return 0;
+}
+
+/* front units (+ fallback rows) -> pack on the side stream || other units with a few CTA slots
+ * left free -> unpack on the side stream -> join */
+extern "C" int dc_cuda_assemble_exchange_with(dc_cuda_ctx *c, dc_cuda_exchange *x, dc_operator_launcher launcher,
+                                              const double *h_params, int nbParams, double *d_values, void *stream)
+{
+    if (!c || !c->d_coord) return fail(-1, "dc_cuda_assemble_exchange: no mesh");
+    if (!d_values || !launcher) return fail(-1, "dc_cuda_assemble_exchange: null argument");
+    CK(cudaSetDevice(c->device));
+    if (!x || dc_cuda_exchange_neighbours(x) == 0)
+        return dc_cuda_assemble_with(c, launcher, h_params, nbParams, DC_MODE_DETERMINISTIC, d_values, stream);
+    if (!c->sideStream) {
+        int lo = 0, hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CK(cudaStreamCreateWithPriority(&c->sideStream, cudaStreamNonBlocking, hi));
+        CK(cudaEventCreateWithFlags(&c->evFront, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c->evJoin, cudaEventDisableTiming));
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t front = c->nbFrontUnits > 0 ? c->nbFrontUnits : c->nbUnits;
+    dc_launch_args a;
+    fill_args(c, DC_MODE_DETERMINISTIC, &a);
+    a.unitFirst = 0; a.unitCount = front;
+    int rc = launcher(&a, h_params, nbParams, d_values, stream);
+    c->launches += a.launches;
+    if (rc) return explain(rc);
+    CK(cudaEventRecord(c->evFront, s));
+    CK(cudaStreamWaitEvent(c->sideStream, c->evFront, 0));
+    if (dc_cuda_exchange_pack(x, d_values, c->sideStream)) return fail(-15, dc_cuda_exchange_last_error());
+    if (front < c->nbUnits) {
+        fill_args(c, DC_MODE_DETERMINISTIC, &a);
+        a.unitFirst = front; a.unitCount = c->nbUnits - front;
+        a.reserveCtas = c->exchangeReserve; a.skipBigRows = 1;
+        rc = launcher(&a, h_params, nbParams, d_values, stream);
+        c->launches += a.launches;
+        if (rc) return explain(rc);
+    }
+    if (dc_cuda_exchange_unpack(x, d_values, c->sideStream)) return fail(-15, dc_cuda_exchange_last_error());
+    c->launches += 2 * dc_cuda_exchange_neighbours(x);
+    CK(cudaEventRecord(c->evJoin, c->sideStream));
+    CK(cudaStreamWaitEvent(s, c->evJoin, 0));
+    return 0;
+}
+
+extern "C" int dc_cuda_assemble_exchange(dc_cuda_ctx *c, dc_cuda_exchange *x, int op, const double *h_params, int nbParams,
+                                         double *d_values, void *stream)
+{
+    switch (op) {
+        case DC_OP_P1_TET_LAPLACIAN:
+            return dc_cuda_assemble_exchange_with(c, x, dc_builtin_laplacian, h_params, nbParams, d_values, stream);
+        case DC_OP_P1_TET_ELASTICITY:
+            return dc_cuda_assemble_exchange_with(c, x, dc_builtin_elasticity, h_params, nbParams, d_values, stream);
+        default:
+            return fail(-9, "dc_cuda_assemble_exchange: unknown operator");
     }
 }
 
@@ -587,6 +677,11 @@ extern "C" int dc_cuda_set_option(dc_cuda_ctx *c, const char *name, int value)
         if (value != 128 && value != 192 && value != 256 && value != 512)
             return fail(-12, "dc_cuda_set_option: unit_threads must be 128, 192, 256 or 512");
         c->threads = value;
+        return 0;
+    }
+    if (!strcmp(name, "exchange_reserve")) {
+        if (value < 0 || value > 64) return fail(-12, "dc_cuda_set_option: exchange_reserve must be 0..64");
+        c->exchangeReserve = value;
         return 0;
     }
     if (!strcmp(name, "persistent")) {

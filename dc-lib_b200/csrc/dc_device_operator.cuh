@@ -46,6 +46,11 @@ struct dc_launch_args {
     const int64_t *d_listEdge, *d_listPtr;
     const uint32_t *d_listItem;
     long long *d_phaseClock;
+    /* which part of the schedule this launch covers (multi-GPU overlap, dc_cuda_assemble_exchange):
+     * units [unitFirst, unitFirst + unitCount), the persistent grid leaves reserveCtas CTA slots free,
+     * the rows of the fallback lists are assembled unless skipBigRows */
+    int64_t unitFirst, unitCount;
+    int reserveCtas, skipBigRows;
     int launches;          /* out: kernels launched */
 };
 
@@ -79,12 +84,13 @@ inline int launch_units(dc_launch_args *a, double *d_values, const dc_params_t &
     }
     /* persistent grid: SMs x resident CTAs (the kernel strides over the units), or one CTA per
      * unit when a->persistent == 0 */
-    int64_t grid = a->nbUnits;
+    int64_t grid = a->unitCount;
     if (a->persistent) {
         int perSm = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kern, THREADS, (size_t)L.total) != cudaSuccess || perSm < 1)
             return DC_LAUNCH_CUDA;
-        const int64_t resident = (int64_t)perSm * a->smCount;
+        int64_t resident = (int64_t)perSm * a->smCount - a->reserveCtas;
+        if (resident < 1) resident = 1;
         if (resident < grid) grid = resident;
     }
 #ifdef DC_KO
@@ -94,7 +100,7 @@ inline int launch_units(dc_launch_args *a, double *d_values, const dc_params_t &
         cudaMemcpyToSymbolAsync(c_ko, &bits, sizeof(int), 0, cudaMemcpyHostToDevice, s);
     }
 #endif
-    kern<<<(unsigned)grid, THREADS, (size_t)L.total, s>>>(a->d_units, (int)a->nbUnits, a->d_tasks, a->d_items,
+    kern<<<(unsigned)grid, THREADS, (size_t)L.total, s>>>(a->d_units + a->unitFirst, (int)a->unitCount, a->d_tasks, a->d_items,
                                                            a->d_slotNodes, a->d_haloNodes, a->d_diagRel,
                                                            reinterpret_cast<const int2 *>(a->d_tgt), a->d_coord,
                                                            d_values, L, P, a->d_phaseClock);
@@ -115,7 +121,7 @@ inline int launch_operator(dc_launch_args *a, const double *h_params, int nbPara
     for (int i = 0; i < DC_MAX_PARAMS; i++) P.v[i] = i < nbParams ? h_params[i] : 0.0;
     if (a->mode == DC_MODE_DETERMINISTIC) {
         if (!a->d_units && a->nbBigEdges == 0) return DC_LAUNCH_NO_PLAN;
-        if (a->nbUnits > 0) {
+        if (a->unitCount > 0) {
             if (a->symmetric && !Op::SYMMETRIC) return DC_LAUNCH_NOT_SYMMETRIC;
             int rc;
             if (a->symmetric)
@@ -129,7 +135,7 @@ inline int launch_operator(dc_launch_args *a, const double *h_params, int nbPara
             if (rc) return rc;
             a->launches++;
         }
-        if (a->nbBigEdges > 0) {
+        if (a->nbBigEdges > 0 && !a->skipBigRows) {
             gather_lists<Op><<<(unsigned)((a->nbBigEdges + 127) / 128), 128, 0, s>>>(
                 a->d_bigEdge, a->d_bigPtr, a->d_bigItem, a->d_bigEdgeT, a->nbBigEdges, a->d_conn, a->d_coord, d_values, P);
             a->launches++;

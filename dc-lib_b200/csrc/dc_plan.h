@@ -124,6 +124,11 @@ int  dc_contrib_build(dc_contrib_list_t *out, const int *conn, int nbElem, int n
  * 1 = the 10 entries of a symmetric 4x4 element matrix in 11-word records (P1 Laplacian).  Any schedule is
  * valid for any operator; the model only decides how many bank conflicts the record reads have. */
 void dc_plan_set_bank_model(int model);
+/* Multi-GPU overlap: move the units that own a flagged row (nodeFlag[node] != 0: the interface
+ * nodes of this rank) to the front of plan->units, keeping the order inside both groups; returns
+ * their number.  Units are independent of one another, so any order is a valid schedule; with the
+ * interface rows first their partial sums can travel while the other units are assembled. */
+int64_t dc_plan_order_units(dc_plan_t *plan, const unsigned char *nodeFlag);
 void dc_plan_free(dc_plan_t *plan);
 void dc_contrib_free(dc_contrib_list_t *c);
 #ifdef __cplusplus

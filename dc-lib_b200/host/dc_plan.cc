@@ -1179,6 +1179,21 @@ extern "C" int dc_plan_build(dc_plan_t *plan, const int *conn, int nbElem, int n
     return 0;
 }
 
+extern "C" int64_t dc_plan_order_units(dc_plan_t *plan, const unsigned char *nodeFlag)
+{
+    if (!plan || !nodeFlag || plan->nbUnits <= 0) return 0;
+    std::vector<dc_unit_t> front, rest;
+    for (int64_t u = 0; u < plan->nbUnits; u++) {
+        const dc_unit_t &d = plan->units[u];
+        bool hit = false;
+        for (int n = d.nodeFirst; n < d.nodeFirst + d.nodeCount && !hit; n++) hit = nodeFlag[n] != 0;
+        (hit ? front : rest).push_back(d);
+    }
+    std::copy(front.begin(), front.end(), plan->units);
+    std::copy(rest.begin(), rest.end(), plan->units + front.size());
+    return (int64_t)front.size();
+}
+
 extern "C" void dc_plan_set_bank_model(int model) { g_bankModel = model == 1 ? 1 : 0; }
 
 extern "C" void dc_contrib_free(dc_contrib_list_t *c)

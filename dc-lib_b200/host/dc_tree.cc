@@ -301,6 +301,14 @@ void TreeBuilder::tree_creation(tree_t *&tree, int *sepToNode, const int *nodePa
         nbSepOut = total[2];
     }
     const int nbLeft = nbLeftOut, nbSep = nbSepOut;
+    if (nbSep == n) {
+        /* every element straddles the cut (a clump around a few nodes, seen with coordinate bisection of
+         * separators of irregular parts): cutting again would recurse on the same set for ever -- the
+         * reference has no guard either (tree_creation.cc:415-478) -- so the set stays one leaf; the
+         * schedule builder cuts over-sized leaves by rows */
+        tree = new_tree_node(firstElem, lastElem, 0, firstNode, lastNode, isSep, true);
+        return;
+    }
 
     int *scratch = scrRows + (int64_t)firstElem * dimElem;
     task_scatter_rows(conn + (int64_t)firstElem * dimElem, order, n, dimElem, scratch);

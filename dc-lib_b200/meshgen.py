@@ -94,3 +94,20 @@ def hub_collapse(conn, coord, n, block=3, stride=9):
     remap[used] = np.arange(used.shape[0])
     c = remap[c]
     return np.ascontiguousarray(c + 1, dtype=np.int32), np.ascontiguousarray(coord[used]), int(used.shape[0])
+
+
+def scramble_mesh(conn, coord, seed=2024):
+    """BASELINE config C4's irregular mesh: graded coordinates (smooth monotone warp x -> x^1.5 of the
+    unit cube), a seeded random relabelling of the nodes and a shuffle of the elements, applied BEFORE
+    DC_create_tree / DC_partition_mesh (the library has to find the locality again)."""
+    rng = np.random.default_rng(seed)
+    N, E = coord.shape[0], conn.shape[0]
+    lo = coord.min(axis=0)
+    span = coord.max(axis=0) - lo
+    coord = np.ascontiguousarray(((coord - lo) / span) ** 1.5 * span)
+    relabel = rng.permutation(N).astype(np.int32)          # old node -> new node
+    new_coord = np.empty_like(coord)
+    new_coord[relabel] = coord
+    new_conn = relabel[conn - 1] + 1
+    new_conn = np.ascontiguousarray(new_conn[rng.permutation(E)], dtype=np.int32)
+    return new_conn, np.ascontiguousarray(new_coord)

@@ -91,18 +91,25 @@ def _pair_keys(conn_g, n_glob, keep):
     return np.unique(a[ok] * np.int64(n_glob) + b[ok])
 
 
-def build_part(conn_g, coord_g, elem_part, rank, world, builder="metis", vec=0):
+def build_part(conn_g, coord_g, elem_part, rank, world, builder="metis", vec=0, csr_device=None):
     """Appendix-A driver for part `rank` of a GENERAL element partition (DC_partition_mesh) of one
     global mesh (BASELINE config 4: an irregular mesh split over the GPUs): local renumbering, own
     D&C tree, CSR pattern of the local elements, and per neighbouring rank the local CSR edges
     that the neighbour holds too -- listed by ascending (global row, global column), so both sides
     agree on the order.  Every rank holds the global connectivity here (host memory only); the
-    device only ever sees the local part.  Returns the same dictionary as build_slab."""
+    device only ever sees the local part.  All passes are O(global elements) array operations
+    (no per-rank sort of the whole mesh).  Returns the same dictionary as build_slab."""
+    import time
     n_glob = coord_g.shape[0]
     mine = np.flatnonzero(elem_part == rank)
     conn_mine_g = conn_g[mine]
-    nodes = np.unique(conn_mine_g.astype(np.int64) - 1)                  # global ids of the local nodes, ascending
-    conn = np.ascontiguousarray(np.searchsorted(nodes, conn_mine_g.astype(np.int64) - 1) + 1, dtype=np.int32)
+    mine_nodes = np.zeros(n_glob, dtype=bool)
+    mine_nodes[conn_mine_g.reshape(-1) - 1] = True
+    nodes = np.flatnonzero(mine_nodes)                                   # global ids of the local nodes, ascending
+    local_of = np.zeros(n_glob, dtype=np.int32)
+    local_of[nodes] = np.arange(1, nodes.shape[0] + 1, dtype=np.int32)
+    conn = np.ascontiguousarray(local_of[conn_mine_g - 1], dtype=np.int32)
+    del local_of
     coord = np.ascontiguousarray(coord_g[nodes])
     E, N = conn.shape[0], nodes.shape[0]
     DC_set_vec_size(vec)
@@ -113,19 +120,22 @@ def build_part(conn_g, coord_g, elem_part, rank, world, builder="metis", vec=0):
     node_perm = get_node_perm(N)
     DC_permute_double_2d_array(coord, N, 3)
     DC_renumber_int_array(conn.reshape(-1), 4 * E)
-    row, col = build_csr_fast(conn, N)
+    t_csr = time.time()
+    if csr_device is not None:
+        import torch
+        from . import build_csr_device
+        d_row, d_col = build_csr_device(torch.from_numpy(conn).to(csr_device), N)
+        row, col = d_row.cpu().numpy(), d_col.cpu().numpy()
+        del d_row, d_col
+    else:
+        row, col = build_csr_fast(conn, N)
+    t_csr = time.time() - t_csr
     DC_finalize_tree(row, conn, E, 4)
     rec = flatten_tree()
     gid_of_new = np.empty(N, dtype=np.int64)
     gid_of_new[node_perm] = nodes
-    # local CSR entries keyed by global (row, col)
-    rows = np.repeat(np.arange(N, dtype=np.int64), np.diff(row))
-    key_local = gid_of_new[rows] * np.int64(n_glob) + gid_of_new[col]
-    order = np.argsort(key_local, kind="stable")
-    key_sorted = key_local[order]
-    mine_nodes = np.zeros(n_glob, dtype=bool)
-    mine_nodes[nodes] = True
     intf = {}
+    rows = None
     for q in range(world):
         if q == rank:
             continue
@@ -133,19 +143,81 @@ def build_part(conn_g, coord_g, elem_part, rank, world, builder="metis", vec=0):
         if theirs.shape[0] == 0:
             continue
         shared = np.zeros(n_glob, dtype=bool)
-        shared[np.unique(theirs.astype(np.int64) - 1)] = True
+        shared[theirs.reshape(-1) - 1] = True
         shared &= mine_nodes
         if not shared.any():
             continue
-        common = np.intersect1d(_pair_keys(conn_mine_g, n_glob, shared), _pair_keys(theirs, n_glob, shared),
-                                assume_unique=True)
-        if common.shape[0] == 0:
+        # local CSR entries whose two nodes are shared with q, keyed by global (row, col) ...
+        if rows is None:
+            rows = np.repeat(np.arange(N, dtype=np.int64), np.diff(row))
+        cand = np.flatnonzero(shared[gid_of_new[rows]] & shared[gid_of_new[col]])
+        key_cand = gid_of_new[rows[cand]] * np.int64(n_glob) + gid_of_new[col[cand]]
+        order = np.argsort(key_cand, kind="stable")
+        # ... of which q holds those that one of ITS elements produces
+        theirs_keys = _pair_keys(theirs, n_glob, shared)
+        pos = np.searchsorted(key_cand[order], theirs_keys)
+        pos[pos >= order.shape[0]] = 0
+        hit = key_cand[order][pos] == theirs_keys if order.shape[0] else np.zeros(0, dtype=bool)
+        if not hit.any():
             continue
-        pos = np.searchsorted(key_sorted, common)
-        assert np.array_equal(key_sorted[pos], common)
-        intf[q] = np.ascontiguousarray(order[pos], dtype=np.int64)
+        intf[q] = np.ascontiguousarray(cand[order[pos[hit]]], dtype=np.int64)       # ascending global key
     return dict(conn=conn, coord=coord, row=row, col=col, E=E, N=N, nnz=int(row[-1]), rec=rec, intf=intf,
-                gid_of_new=gid_of_new, node_perm=node_perm, rank=rank, world=world, elems=mine)
+                gid_of_new=gid_of_new, node_perm=node_perm, rank=rank, world=world, elems=mine, csr_s=t_csr)
+
+
+def setup_device_parts(n, rank, world, device, slots=512, dist=None, seed=2024, partition="metis", bank_model=0):
+    """BASELINE config 4 on the device: ONE graded / relabelled / shuffled Kuhn cube n^3 (scramble_mesh), cut into
+    `world` parts by DC_partition_mesh on rank 0 (METIS recursive bisection of the nodal graph, the call
+    DC_create_tree makes, partitioning.cc:167-228; "geometric" = coordinate bisection) and broadcast; every
+    rank extracts its part (build_part), builds its own D&C tree (coordinate bisection), CSR pattern (on the
+    GPU) and schedule with the interface units first, and uploads them.  Returns (ctx, info) like
+    setup_device_slabs; info["intf"] holds the per-neighbour edge lists."""
+    import time
+
+    import torch
+
+    from . import Context, HostPlan, kuhn_cube_fast, scramble_mesh
+    t0 = time.time()
+    DC_set_num_threads(0)
+    conn_g, coord_g, n_glob = kuhn_cube_fast(n)
+    conn_g, coord_g = scramble_mesh(conn_g, coord_g, seed=seed)
+    t_mesh = time.time() - t0
+    t1 = time.time()
+    if world > 1:
+        part_t = torch.empty(conn_g.shape[0], dtype=torch.int32, device=device)
+        if rank == 0:
+            part = DC_partition_mesh(conn_g, n_glob, world, coord_g if partition == "geometric" else None)
+            part_t.copy_(torch.from_numpy(part))
+        dist.broadcast(part_t, src=0)
+        part = part_t.cpu().numpy()
+        del part_t
+    else:
+        part = np.zeros(conn_g.shape[0], dtype=np.int32)
+    t_part = time.time() - t1
+    t1 = time.time()
+    p = build_part(conn_g, coord_g, part, rank, world, builder="geometric", csr_device=device)
+    E_glob = conn_g.shape[0]
+    del conn_g, coord_g, part
+    t_tree = time.time() - t1
+    t1 = time.time()
+    plan = HostPlan(p["conn"], p["N"], p["row"], p["col"], 0, p["rec"], slots, bank_model=bank_model)
+    nb_front = 0
+    if p["intf"]:
+        flag = np.zeros(p["N"], dtype=np.uint8)
+        for e in p["intf"].values():
+            flag[np.searchsorted(p["row"], e, side="right") - 1] = 1
+        nb_front = plan.order_units(flag)
+    t_plan = time.time() - t1
+    ctx = Context(torch.device(device).index or 0)
+    ctx.set_mesh(p["conn"], p["coord"], p["row"], p["col"], 0)
+    ctx.upload_plan(plan)
+    ctx.set_front_units(nb_front)
+    st = plan.stats()
+    info = dict(E=p["E"], N=p["N"], nnz=p["nnz"], E_global=E_glob, stats=st, tree_s=t_tree, plan_s=t_plan, csr_s=p["csr_s"],
+                mesh_s=t_mesh, partition_s=t_part, nb_front=nb_front, intf=p["intf"],
+                coord=torch.from_numpy(p["coord"]), setup_s=time.time() - t0,
+                interface_edges=int(sum(e.shape[0] for e in p["intf"].values())))
+    return ctx, info
 
 
 class InterfaceExchange:
@@ -213,6 +285,16 @@ def setup_device_slabs(n, rank, world, device, builder="geometric", vec=0, slots
         t1 = time.time()
         plan = HostPlan(slab["conn"], slab["N"], slab["row"], slab["col"], 0, slab["rec"], slots, symmetric=symmetric,
                         bank_model=bank_model)
+        intf_l = plane_edges(node_perm, slab["row"], slab["col"], n, 0) if world > 1 else np.zeros(0, np.int64)
+        intf_r = plane_edges(node_perm, slab["row"], slab["col"], n, n) if world > 1 else np.zeros(0, np.int64)
+        nb_front = 0
+        if world > 1:
+            # units that own a row of either interface plane go first: their partial sums travel while the
+            # other units are assembled (every slab has the same topology, so both planes are flagged)
+            flag = np.zeros(slab["N"], dtype=np.uint8)
+            for e in (intf_l, intf_r):
+                flag[np.searchsorted(slab["row"], e, side="right") - 1] = 1
+            nb_front = plan.order_units(flag)
         t_plan = time.time() - t1
         arr = plan.arrays()
         if arr["bigEdges"]:
@@ -221,14 +303,13 @@ def setup_device_slabs(n, rank, world, device, builder="geometric", vec=0, slots
                     tasks=arr["tasks"], items=arr["items"].view(np.int16), slotNodes=arr["slotNodes"].view(np.int16),
                     haloNodes=arr["haloNodes"],
                     diagRel=plan.diag_rel(slab["N"]), tgt=arr["tgt"],
-                    intf_left=plane_edges(node_perm, slab["row"], slab["col"], n, 0) if world > 1 else np.zeros(0, np.int64),
-                    intf_right=plane_edges(node_perm, slab["row"], slab["col"], n, n) if world > 1 else np.zeros(0, np.int64))
+                    intf_left=intf_l, intf_right=intf_r)
         for k in names:
             tensors[k] = torch.from_numpy(np.ascontiguousarray(host[k])).to(device)
         st = plan.stats()
         meta = dict(shapes={k: (tuple(tensors[k].shape), str(tensors[k].dtype)) for k in names},
                     ints={k: arr[k] for k in ("nbUnits", "maxSlots", "maxHalo", "maxNodes", "maxTasks", "maxItems", "maxTgt", "symmetric")},
-                    E=slab["E"], N=slab["N"], nnz=slab["nnz"], stats=st, tree_s=t_tree, plan_s=t_plan,
+                    E=slab["E"], N=slab["N"], nnz=slab["nnz"], stats=st, tree_s=t_tree, plan_s=t_plan, nb_front=nb_front,
                     csr_s=slab["csr_s"])
         del plan, slab, host, arr
     if world > 1:
@@ -254,6 +335,7 @@ def setup_device_slabs(n, rank, world, device, builder="geometric", vec=0, slots
                   slotNodes=tensors["slotNodes"], haloNodes=tensors["haloNodes"], diagRel=tensors["diagRel"],
                   tgt=tensors["tgt"], **meta["ints"])
     ctx.set_plan_device(plan_t)
+    ctx.set_front_units(meta.get("nb_front", 0))
     intf = {}
     if rank > 0:
         intf[rank - 1] = tensors["intf_left"]
@@ -263,15 +345,12 @@ def setup_device_slabs(n, rank, world, device, builder="geometric", vec=0, slots
     return ctx, info
 
 
-class DeviceInterfaceExchange(InterfaceExchange):
-    """InterfaceExchange over edge lists that already live on the device."""
+def device_exchange(intf, per_edge, device, dist, rank, world):
+    """dc_cuda_exchange over the per-neighbour edge lists (numpy or CUDA tensors): peer-memory
+    transport inside libdc_b200.so; torch.distributed only carries the 128-byte handles once."""
+    import torch
 
-    def __init__(self, intf, per_edge, device, dist):
-        import torch
-        self.torch, self.dist, self.per, self.on_gpu = torch, dist, per_edge, True
-        self.nbs = sorted(intf)
-        self.edges = {nb: intf[nb] for nb in self.nbs}
-        self.send = {nb: torch.empty(intf[nb].numel() * per_edge, dtype=torch.float64, device=device) for nb in self.nbs}
-        self.recv = {nb: torch.empty_like(self.send[nb]) for nb in self.nbs}
-        self.bytes_per_step = sum(2 * 8 * self.send[nb].numel() for nb in self.nbs)
-        self.launches_per_step = 2 * len(self.nbs)
+    from . import DeviceExchange
+    x = DeviceExchange(intf, per_edge, torch.device(device).index or 0)
+    x.connect(dist, rank, world)
+    return x

@@ -25,6 +25,10 @@ extern "C" {
 #endif
 
 typedef struct dc_cuda_ctx dc_cuda_ctx;
+struct dc_launch_args;
+typedef int (*dc_operator_launcher)(struct dc_launch_args *args, const double *h_params, int nbParams,
+                                    double *d_values, void *stream);
+
 struct dc_plan_s;   /* dc_plan_t, see dc-lib_b200/csrc/dc_plan.h */
 
 enum { DC_OP_P1_TET_LAPLACIAN = 0, DC_OP_P1_TET_ELASTICITY = 1 };
@@ -73,9 +77,6 @@ int  dc_cuda_assemble(dc_cuda_ctx *ctx, int op, const double *h_params, int nbPa
 /* Same with a user-defined device operator: `launcher` is the function a user's .cu file
  * defines with DC_DEVICE_OPERATOR(name, Functor) (dc-lib_b200/csrc/dc_device_operator.cuh) --
  * the device-side replacement of the reference's host function pointers. */
-struct dc_launch_args;
-typedef int (*dc_operator_launcher)(struct dc_launch_args *args, const double *h_params, int nbParams,
-                                    double *d_values, void *stream);
 int  dc_cuda_assemble_with(dc_cuda_ctx *ctx, dc_operator_launcher launcher, const double *h_params,
                            int nbParams, int mode, double *d_values, void *stream);
 /* Convenience: values owned by the context. */
@@ -97,15 +98,72 @@ int  dc_cuda_renumber(int *d_tab, const int *d_perm, int64_t size, int isFortran
 int  dc_cuda_reset_edges(double *d_values, int64_t firstEdge, int64_t lastEdge, int perEdge,
                          void *stream);
 
-/* Interface exchange between GPUs (the reference leaves halo exchange to the user's
- * MPI/GASPI code through userCommFct, src/tree_traversal.cc:65-73; the data layout follows
- * its intfIndex/intfNodes/intfDst triple, include/DC.h:51-53, at edge granularity):
+/* Interface exchange between the GPUs of one node.  The reference leaves the halo exchange to the
+ * user's MPI/GASPI code (userCommFct, src/tree_traversal.cc:65-73) and prepares, per neighbour domain,
+ * the interface nodes and their place in the neighbour's receive buffer (intfIndex / intfNodes /
+ * intfDstOffsets, include/DC.h:51-53,141-143; src/tree_creation.cc:48-169).  Here the same lists exist at
+ * CSR-edge granularity and the transport is peer memory over NVLink (csrc/dc_cuda_exchange.cu): per
+ * neighbour, the local CSR edges both ranks hold, in an order both sides agree on (dc_interface_edges
+ * below derives them from the reference's node lists).
+ *   create   edges of neighbour i = edges[edgePtr[i] .. edgePtr[i+1]), neighbourRank ascending;
+ *            _device: the concatenated list already lives on the device (not copied, not freed)
+ *   export   128-byte handle of MY receive buffer for neighbour i -- hand it to that rank by any
+ *            means (MPI, torch.distributed, a file) ...
+ *   import   ... which imports it as the buffer it pushes into (CUDA IPC between processes, the
+ *            plain pointer + peer access inside one process)
+ *   pack     gather the partial sums of the shared edges into the neighbours' buffers and raise
+ *            their flags; unpack: wait for the own flags and add the buffers (neighbours in the
+ *            order of creation: a fixed summation order); run = pack + unpack.
+ * All calls are asynchronous on `stream`; every rank calls pack/unpack once per step. */
+#define DC_EXCHANGE_HANDLE_BYTES 128
+typedef struct dc_cuda_exchange dc_cuda_exchange;
+int  dc_cuda_exchange_create(dc_cuda_exchange **x, int device, int perEdge, int nbNeighbours,
+                             const int *neighbourRank, const int64_t *edgePtr, const int64_t *h_edges);
+int  dc_cuda_exchange_create_device(dc_cuda_exchange **x, int device, int perEdge, int nbNeighbours,
+                                    const int *neighbourRank, const int64_t *edgePtr, const int64_t *d_edges);
+int  dc_cuda_exchange_neighbours(const dc_cuda_exchange *x);
+int  dc_cuda_exchange_export(dc_cuda_exchange *x, int nbIndex, void *handle);
+int  dc_cuda_exchange_import(dc_cuda_exchange *x, int nbIndex, const void *handle);
+int  dc_cuda_exchange_pack(dc_cuda_exchange *x, const double *d_values, void *stream);
+int  dc_cuda_exchange_unpack(dc_cuda_exchange *x, double *d_values, void *stream);
+int  dc_cuda_exchange_run(dc_cuda_exchange *x, double *d_values, void *stream);
+int64_t dc_cuda_exchange_bytes(const dc_cuda_exchange *x);       /* sent + received per step */
+int  dc_cuda_exchange_set_blocks(dc_cuda_exchange *x, int maxBlocks);   /* CTAs per pack / unpack kernel (default 64) */
+void dc_cuda_exchange_destroy(dc_cuda_exchange *x);
+const char *dc_cuda_exchange_last_error(void);
+
+/* One assembly step of a rank of a multi-GPU run: the units that own interface rows first
+ * (dc_cuda_set_front_units), pack on a side stream as soon as they are done, the other units with a few
+ * CTA slots left free so that the pack / unpack kernels find room beside the persistent grid
+ * ("exchange_reserve" option, default 4), unpack, join: the exchange hides behind the interior units
+ * (the reference's MULTITHREADED_COMM idea, src/tree_creation.cc:48-169, at unit granularity). */
+int  dc_cuda_set_front_units(dc_cuda_ctx *ctx, int64_t nbFrontUnits);
+/* the pieces of that step, for callers that order them themselves: units [unitFirst, +unitCount) of the
+ * schedule, reserveCtas CTA slots of the persistent grid left free, fallback rows skipped on request */
+int  dc_cuda_assemble_units(dc_cuda_ctx *ctx, int op, const double *h_params, int nbParams, double *d_values,
+                            void *stream, int64_t unitFirst, int64_t unitCount, int reserveCtas, int skipBigRows);
+int  dc_cuda_assemble_exchange(dc_cuda_ctx *ctx, dc_cuda_exchange *x, int op, const double *h_params,
+                               int nbParams, double *d_values, void *stream);
+int  dc_cuda_assemble_exchange_with(dc_cuda_ctx *ctx, dc_cuda_exchange *x, dc_operator_launcher launcher,
+                                    const double *h_params, int nbParams, double *d_values, void *stream);
+
+/* Lower-level pieces (kept for callers that bring their own transport, e.g. NCCL or MPI buffers):
  * pack gathers the partial sums of the listed CSR edges into a contiguous send buffer,
  * unpack_add adds a received buffer (local, or a peer GPU's buffer mapped over NVLink). */
 int  dc_cuda_pack_edges(const double *d_values, const int64_t *d_edge, int64_t nbEdges, int perEdge,
                         double *d_buf, void *stream);
 int  dc_cuda_unpack_add_edges(double *d_values, const int64_t *d_edge, int64_t nbEdges, int perEdge,
                               const double *d_buf, void *stream);
+
+/* The CSR edges two domains share, from the reference's interface layout: `nodes` = the interface
+ * nodes shared with ONE neighbour (1-based local ids, in the order both sides list them -- the
+ * reference's intfNodes slice intfIndex[i] .. intfIndex[i+1]).  Writes, ordered by (position of the
+ * row node, position of the column node) in that list, the local edge of every pair of listed nodes
+ * that is an entry of the local pattern, and its key position(row) * nbListed + position(col); returns
+ * the count (edges / keys may be NULL to size the arrays).  Both sides must exchange only the keys
+ * they BOTH hold: on conforming interfaces the lists are equal; otherwise intersect the key lists. */
+int64_t dc_interface_edges(const int *h_row, const int *h_col, int colBase, const int *nodes, int nbListed,
+                           int64_t *edges, int64_t *keys);
 
 /* Consumer of the assembled matrix (what the reference's user, Mini-FEM, does next;
  * README.md:32): y = A x for the D x D-block CSR values the assembly left on the device, with the
@@ -130,7 +188,8 @@ void dc_cuda_csr_end(dc_cuda_csr *handle);
 
 /* Tuning knobs: "unit_threads" = CTA size of the unit kernel (128, 192, 256 or 512; default 256);
  * "persistent" = 1 (default): SMs x resident CTAs stride over the units and prefetch the next
- * unit's inputs, 0: one CTA per unit. */
+ * unit's inputs, 0: one CTA per unit; "exchange_reserve" = CTA slots dc_cuda_assemble_exchange leaves
+ * free beside the interior units for the pack / unpack kernels (default 4). */
 int  dc_cuda_set_option(dc_cuda_ctx *ctx, const char *name, int value);
 
 /* Number of kernels this context has launched (for honest launch accounting). */

@@ -205,21 +205,7 @@ class MineLib:
         dc.DC_read_tree(path, E, N)
 
 
-def scramble_mesh(conn, coord, seed=2024):
-    """BASELINE config C4's irregular mesh at test size: graded coordinates (smooth monotone warp
-    x -> x^1.5 of the unit cube), a seeded random relabelling of the nodes and a shuffle of the
-    elements, applied BEFORE DC_create_tree (the library has to find the locality again)."""
-    rng = np.random.default_rng(seed)
-    N, E = coord.shape[0], conn.shape[0]
-    span = coord.max(axis=0) - coord.min(axis=0)
-    unit = (coord - coord.min(axis=0)) / span
-    coord = np.ascontiguousarray(unit ** 1.5 * span)
-    relabel = rng.permutation(N).astype(np.int32)          # old node -> new node
-    new_coord = np.empty_like(coord)
-    new_coord[relabel] = coord
-    new_conn = relabel[conn - 1] + 1
-    new_conn = np.ascontiguousarray(new_conn[rng.permutation(E)], dtype=np.int32)
-    return new_conn, np.ascontiguousarray(new_coord)
+scramble_mesh = dc.scramble_mesh          # BASELINE config C4's irregular mesh (dc-lib_b200/meshgen.py)
 
 
 def prepare_mesh(lib, n, tmp_path, hub=False, tag="t", scramble=False):

@@ -222,3 +222,27 @@ def test_tree_and_schedule_do_not_depend_on_the_thread_count(tmp_path, geometric
         out.append((mesh["tree"], mesh["conn"].tobytes(), canonical_md5(plan, mesh["N"])))
     assert out[0][0] == out[1][0] and out[0][1] == out[1][1]
     assert out[0][2] == out[1][2]
+
+
+def test_geometric_tree_of_an_irregular_part_terminates():
+    """Regression: one METIS part of the graded / relabelled / shuffled cube (BASELINE config 4) has separators
+    in which every element straddles a coordinate cut; the recursion used to cut the same set again for ever
+    (stack overflow at 80^3).  Such a set now stays one leaf, and the tree still covers every element once."""
+    from dc_lib_b200 import multigpu
+    conn, coord, N = dc.kuhn_cube_fast(80)
+    conn, coord = dc.scramble_mesh(conn, coord)
+    part = dc.DC_partition_mesh(conn, N, 4)
+    dc.DC_set_max_elem_per_part(182)
+    try:
+        p = multigpu.build_part(conn, coord, part, 1, 4, builder="geometric")
+    finally:
+        dc.DC_set_max_elem_per_part(200)
+    rec = p["rec"]
+    leaves = rec[rec[:, 6] == 1]
+    sizes = leaves[:, 1] - leaves[:, 0] + 1
+    assert sizes.sum() == p["E"] and sizes.min() >= 0
+    covered = np.zeros(p["E"], dtype=np.int32)
+    for first, last in leaves[:, :2]:
+        covered[first:last + 1] += 1
+    assert (covered == 1).all()
+    dc.DC_free_tree()
