@@ -255,6 +255,8 @@ def main():
                                                 bank_model=int(os.environ.get("DC_BENCH_BANK_MODEL", "1" if dim == 1 else "0")))
     ctx.set_option("unit_threads", args.threads)
     ctx.set_option("persistent", args.persistent)
+    if "DC_BENCH_RESERVE" in os.environ:
+        ctx.set_option("exchange_reserve", int(os.environ["DC_BENCH_RESERVE"]))
     E, N, nnz, st = info["E"], info["N"], info["nnz"], info["stats"]
     op, prm = (dc.OP_ELASTICITY, [LAMBDA, MU]) if dim == 3 else (dc.OP_LAPLACIAN, None)
     per = dim * dim
@@ -268,8 +270,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    split_only = os.environ.get("DC_BENCH_OVERLAP", "1") == "split"      # experiment: the two launches without the exchange
+
     def step():
-        if exch and overlap:
+        if exch and split_only:
+            nf, nu = info.get("nb_front", 0), st["units"]
+            ctx.assemble_units(op, prm, vals, 0, nf, stream=stream)
+            ctx.assemble_units(op, prm, vals, nf, nu - nf, reserve=int(os.environ.get("DC_BENCH_RESERVE", "4")), skip_big=True, stream=stream)
+        elif exch and overlap:
             # interface units, pack over NVLink || interior units, unpack-add (dc_cuda_assemble_exchange)
             ctx.assemble_exchange(exch, op, prm, vals, stream)
         else:

@@ -369,9 +369,13 @@ extern "C" int dc_cuda_assemble_exchange_with(dc_cuda_ctx *c, dc_cuda_exchange *
     if (!x || dc_cuda_exchange_neighbours(x) == 0)
         return dc_cuda_assemble_with(c, launcher, h_params, nbParams, DC_MODE_DETERMINISTIC, d_values, stream);
     if (!c->sideStream) {
+        /* LOWEST priority: when the front units finish, the interior launch and the pack kernel become
+         * ready together; the interior CTAs must be placed first (two per SM, all registers) and the
+         * pack / unpack blocks take the slots left free -- a pack block placed first would keep a whole
+         * interior CTA off its SM, and with the static unit stride that CTA finishes late by as much */
         int lo = 0, hi = 0;
         CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        CK(cudaStreamCreateWithPriority(&c->sideStream, cudaStreamNonBlocking, hi));
+        CK(cudaStreamCreateWithPriority(&c->sideStream, cudaStreamNonBlocking, lo));
         CK(cudaEventCreateWithFlags(&c->evFront, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&c->evJoin, cudaEventDisableTiming));
     }
@@ -384,9 +388,7 @@ extern "C" int dc_cuda_assemble_exchange_with(dc_cuda_ctx *c, dc_cuda_exchange *
     c->launches += a.launches;
     if (rc) return explain(rc);
     CK(cudaEventRecord(c->evFront, s));
-    CK(cudaStreamWaitEvent(c->sideStream, c->evFront, 0));
-    if (dc_cuda_exchange_pack(x, d_values, c->sideStream)) return fail(-15, dc_cuda_exchange_last_error());
-    if (front < c->nbUnits) {
+    if (front < c->nbUnits) {            /* enqueued BEFORE the pack: see above */
         fill_args(c, DC_MODE_DETERMINISTIC, &a);
         a.unitFirst = front; a.unitCount = c->nbUnits - front;
         a.reserveCtas = c->exchangeReserve; a.skipBigRows = 1;
@@ -394,6 +396,8 @@ extern "C" int dc_cuda_assemble_exchange_with(dc_cuda_ctx *c, dc_cuda_exchange *
         c->launches += a.launches;
         if (rc) return explain(rc);
     }
+    CK(cudaStreamWaitEvent(c->sideStream, c->evFront, 0));
+    if (dc_cuda_exchange_pack(x, d_values, c->sideStream)) return fail(-15, dc_cuda_exchange_last_error());
     if (dc_cuda_exchange_unpack(x, d_values, c->sideStream)) return fail(-15, dc_cuda_exchange_last_error());
     c->launches += 2 * dc_cuda_exchange_neighbours(x);
     CK(cudaEventRecord(c->evJoin, c->sideStream));

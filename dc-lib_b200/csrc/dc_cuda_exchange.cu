@@ -83,9 +83,19 @@ __global__ void __launch_bounds__(256) push_edges(const double *__restrict__ val
                                                   unsigned long long *flag, unsigned long long stamp, unsigned int *done)
 {
     const int64_t total = nbEdges * perEdge, stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += stride) {
-        const int64_t k = w / perEdge;
-        buf[w] = values[__ldg(edge + k) * perEdge + (w - k * perEdge)];
+    for (int64_t w0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w0 < total; w0 += 4 * stride) {
+        double v[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int64_t w = w0 + q * stride;
+            if (w < total) {
+                const int64_t k = w / perEdge;
+                v[q] = values[__ldg(edge + k) * perEdge + (w - k * perEdge)];
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            if (w0 + q * stride < total) buf[w0 + q * stride] = v[q];
     }
     __threadfence_system();
     __syncthreads();
@@ -107,10 +117,25 @@ __global__ void __launch_bounds__(256) wait_add_edges(double *__restrict__ value
         while (ld_acquire_sys(flag) < stamp) __nanosleep(64);
     __syncthreads();
     const int64_t total = nbEdges * perEdge, stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += stride) {
-        const int64_t k = w / perEdge;
-        double *dst = values + __ldg(edge + k) * perEdge + (w - k * perEdge);
-        *dst = __dadd_rn(*dst, __ldcv(buf + w));          /* written by another GPU: not through the read-only path */
+    /* four independent words per thread and trip: the kernel often runs on the few CTA slots the
+     * persistent assembly grid leaves free, where only memory-level parallelism hides the latency */
+    for (int64_t w0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w0 < total; w0 += 4 * stride) {
+        double *dst[4];
+        double add[4], old[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int64_t w = w0 + q * stride;
+            dst[q] = nullptr;
+            if (w < total) {
+                const int64_t k = w / perEdge;
+                dst[q] = values + __ldg(edge + k) * perEdge + (w - k * perEdge);
+                add[q] = __ldcv(buf + w);                /* written by another GPU: not through the read-only path */
+                old[q] = *dst[q];
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            if (dst[q]) *dst[q] = __dadd_rn(old[q], add[q]);
     }
 }
 
