@@ -15,6 +15,12 @@ dc_cuda_ctx *g_ctx = nullptr;
 int g_mode = DC_DEVICE_DETERMINISTIC;
 int g_maxSlots = 512;     /* measured best with 256-thread CTAs, two per SM (profiles/README.md) */
 int g_symmetric = 1;     /* both built-in operators have bitwise symmetric element matrices */
+/* interface of this domain (DC_device_set_interface), consumed by DC_device_set_mesh */
+std::vector<int> g_intfRank, g_intfIndex, g_intfNodes;
+dc_cuda_exchange *g_exchange = nullptr;
+int g_exchangeDim = 0;                       /* operatorDim the exchange buffers were sized for */
+std::vector<int64_t> g_intfEdgePtr, g_intfEdges;
+int g_device = 0;
 
 [[noreturn]] void die(const char *what)
 {
@@ -62,8 +68,33 @@ extern "C" int dc_get_elem_perm (int *out, int nbElem)
 
 void DC_device_init (int device)
 {
+    if (g_exchange) { dc_cuda_exchange_destroy(g_exchange); g_exchange = nullptr; }
     if (g_ctx) { dc_cuda_destroy(g_ctx); g_ctx = nullptr; }
     if (dc_cuda_create(&g_ctx, device)) die("DC_device_init failed");
+    g_device = device;
+}
+
+void DC_device_set_interface (int nbIntf, const int *neighbourRank, const int *intfIndex, const int *intfNodes)
+{
+    g_intfRank.assign(neighbourRank, neighbourRank + nbIntf);
+    g_intfIndex.assign(intfIndex, intfIndex + nbIntf + 1);
+    g_intfNodes.assign(intfNodes, intfNodes + (nbIntf > 0 ? intfIndex[nbIntf] : 0));
+}
+
+void DC_device_exchange_handle (int intf, void *handle128)
+{
+    if (!g_exchange || dc_cuda_exchange_export(g_exchange, intf, handle128)) {
+        fprintf(stderr, "Error: DC_device_exchange_handle: %s\n", g_exchange ? dc_cuda_exchange_last_error() : "no interface set");
+        exit(EXIT_FAILURE);
+    }
+}
+
+void DC_device_exchange_connect (int intf, const void *handle128)
+{
+    if (!g_exchange || dc_cuda_exchange_import(g_exchange, intf, handle128)) {
+        fprintf(stderr, "Error: DC_device_exchange_connect: %s\n", g_exchange ? dc_cuda_exchange_last_error() : "no interface set");
+        exit(EXIT_FAILURE);
+    }
 }
 
 void DC_device_set_mode (int mode) { g_mode = mode; }
@@ -85,8 +116,32 @@ void DC_device_set_mesh (const double *coord, const int *elemToNode, const int *
         fprintf(stderr, "Error: DC_device_set_mesh: cannot build the device schedule (code %d).\n", rc);
         exit(EXIT_FAILURE);
     }
+    /* several domains: interface edges from the node lists, interface units first, exchange buffers */
+    int64_t nbFront = 0;
+    if (g_exchange) { dc_cuda_exchange_destroy(g_exchange); g_exchange = nullptr; }
+    const int nbIntf = (int)g_intfRank.size();
+    std::vector<int64_t> edgePtr((size_t)nbIntf + 1, 0), edges;
+    if (nbIntf > 0) {
+        std::vector<unsigned char> flag((size_t)nbNodes, 0);
+        for (int i = 0; i < nbIntf; i++) {
+            const int *nodes = g_intfNodes.data() + g_intfIndex[i];
+            const int cnt = g_intfIndex[i + 1] - g_intfIndex[i];
+            const int64_t ne = dc_interface_edges(nodeToNodeRow, nodeToNodeColumn, colBase, nodes, cnt, nullptr, nullptr);
+            edges.resize((size_t)(edgePtr[i] + ne));
+            dc_interface_edges(nodeToNodeRow, nodeToNodeColumn, colBase, nodes, cnt, edges.data() + edgePtr[i], nullptr);
+            edgePtr[(size_t)i + 1] = edgePtr[i] + ne;
+            for (int p = 0; p < cnt; p++) flag[(size_t)nodes[p] - 1] = 1;
+        }
+        nbFront = dc_plan_order_units(&plan, flag.data());
+    }
     if (dc_cuda_upload_plan(g_ctx, &plan)) die("DC_device_set_mesh: schedule upload failed");
     dc_plan_free(&plan);
+    if (nbIntf > 0) {
+        if (dc_cuda_set_front_units(g_ctx, nbFront)) die("DC_device_set_mesh: front units");
+        /* per-edge words follow the operator; both built-ins are created lazily at the first assembly */
+    }
+    g_intfEdgePtr = edgePtr;
+    g_intfEdges = edges;
 }
 
 void DC_device_update_coords (const double *coord)
@@ -94,16 +149,55 @@ void DC_device_update_coords (const double *coord)
     if (!g_ctx || dc_cuda_update_coords(g_ctx, coord, nullptr)) die("DC_device_update_coords failed");
 }
 
-double *DC_assembly_device_resident (int op, const double *opParams, int nbParams, int operatorDim)
+/* the exchange is created when the first assembly tells how many doubles an edge carries */
+static void ensure_exchange(int operatorDim)
+{
+    if (g_intfRank.empty() || (g_exchange && g_exchangeDim == operatorDim)) return;
+    if (g_exchange) dc_cuda_exchange_destroy(g_exchange);
+    g_exchange = nullptr;
+    if (dc_cuda_exchange_create(&g_exchange, g_device, operatorDim * operatorDim, (int)g_intfRank.size(), g_intfRank.data(),
+                                g_intfEdgePtr.data(), g_intfEdges.data())) {
+        fprintf(stderr, "Error: DC_device: cannot create the interface exchange (%s)\n", dc_cuda_exchange_last_error());
+        exit(EXIT_FAILURE);
+    }
+    g_exchangeDim = operatorDim;
+}
+
+/* DC_device_set_interface users create the exchange explicitly (the handles must be swapped before
+ * the first assembly): operatorDim of the operator that will be assembled */
+void DC_device_prepare_exchange (int operatorDim) { ensure_exchange(operatorDim); }
+
+static double *assemble_resident(int op, DC_device_operator launcher, const double *opParams, int nbParams, int operatorDim)
 {
     if (!g_ctx) dc::fatal("Error: DC_assembly_device called before DC_device_set_mesh.");
-    const int wantDim = (op == DC_OP_ELASTICITY) ? 3 : 1;
-    if (operatorDim != wantDim) dc::fatal("Error: operatorDim does not match the device operator.");
     double *d_values = nullptr;
     if (dc_cuda_values(g_ctx, operatorDim, &d_values)) die("DC_assembly_device: cannot allocate values");
     const int mode = (g_mode == DC_DEVICE_ATOMIC) ? DC_MODE_ATOMIC : DC_MODE_DETERMINISTIC;
-    if (dc_cuda_assemble(g_ctx, op, opParams, nbParams, mode, d_values, nullptr)) die("DC_assembly_device failed");
+    int rc;
+    if (!g_intfRank.empty()) {
+        if (mode != DC_MODE_DETERMINISTIC) dc::fatal("Error: DC_assembly_device: several domains need the deterministic mode.");
+        ensure_exchange(operatorDim);
+        rc = launcher ? dc_cuda_assemble_exchange_with(g_ctx, g_exchange, (dc_operator_launcher)launcher, opParams, nbParams, d_values, nullptr)
+                      : dc_cuda_assemble_exchange(g_ctx, g_exchange, op, opParams, nbParams, d_values, nullptr);
+    } else {
+        rc = launcher ? dc_cuda_assemble_with(g_ctx, (dc_operator_launcher)launcher, opParams, nbParams, mode, d_values, nullptr)
+                      : dc_cuda_assemble(g_ctx, op, opParams, nbParams, mode, d_values, nullptr);
+    }
+    if (rc) die("DC_assembly_device failed");
     return d_values;
+}
+
+double *DC_assembly_device_resident (int op, const double *opParams, int nbParams, int operatorDim)
+{
+    const int wantDim = (op == DC_OP_ELASTICITY) ? 3 : 1;
+    if (operatorDim != wantDim) dc::fatal("Error: operatorDim does not match the device operator.");
+    return assemble_resident(op, nullptr, opParams, nbParams, operatorDim);
+}
+
+double *DC_assembly_device_resident_with (DC_device_operator launcher, const double *opParams, int nbParams, int operatorDim)
+{
+    if (!launcher) dc::fatal("Error: DC_assembly_device_with: null operator.");
+    return assemble_resident(-1, launcher, opParams, nbParams, operatorDim);
 }
 
 void DC_assembly_device (int op, const double *opParams, int nbParams, double *nodeToNodeValue,
@@ -114,10 +208,21 @@ void DC_assembly_device (int op, const double *opParams, int nbParams, double *n
         die("DC_assembly_device: device->host copy failed");
 }
 
+void DC_assembly_device_with (DC_device_operator launcher, const double *opParams, int nbParams, double *nodeToNodeValue,
+                              int operatorDim)
+{
+    DC_assembly_device_resident_with(launcher, opParams, nbParams, operatorDim);
+    if (dc_cuda_download_values(g_ctx, operatorDim, nodeToNodeValue, nullptr) || dc_cuda_sync(nullptr))
+        die("DC_assembly_device_with: device->host copy failed");
+}
+
 void DC_device_finalize ()
 {
+    if (g_exchange) dc_cuda_exchange_destroy(g_exchange);
+    g_exchange = nullptr;
     if (g_ctx) dc_cuda_destroy(g_ctx);
     g_ctx = nullptr;
+    g_intfRank.clear(); g_intfIndex.clear(); g_intfNodes.clear();
 }
 
 extern "C" {
@@ -135,4 +240,11 @@ void dc_assembly_device_ (int *op, const double *opParams, int *nbParams, double
     DC_assembly_device(*op, opParams, *nbParams, nodeToNodeValue, *operatorDim);
 }
 void dc_device_finalize_ () { DC_device_finalize(); }
+void dc_device_set_interface_ (int *nbIntf, const int *neighbourRank, const int *intfIndex, const int *intfNodes)
+{
+    DC_device_set_interface(*nbIntf, neighbourRank, intfIndex, intfNodes);
+}
+void dc_device_prepare_exchange_ (int *operatorDim) { DC_device_prepare_exchange(*operatorDim); }
+void dc_device_exchange_handle_ (int *intf, void *handle128) { DC_device_exchange_handle(*intf, handle128); }
+void dc_device_exchange_connect_ (int *intf, const void *handle128) { DC_device_exchange_connect(*intf, handle128); }
 }

@@ -42,7 +42,33 @@ void DC_assembly_device (int op, const double *opParams, int nbParams, double *n
                          int operatorDim);
 /* Same without the copy; the values stay in device memory (pointer returned). */
 double *DC_assembly_device_resident (int op, const double *opParams, int nbParams, int operatorDim);
+/* Same with a user-defined device operator: `launcher` is the function a user's .cu file defines with
+ * DC_DEVICE_OPERATOR(name, Functor) (dc-lib_b200/csrc/dc_device_operator.cuh) -- what replaces the
+ * host function pointers userSeqFct / userVecFct of the reference (src/tree_traversal.cc:106-117). */
+struct dc_launch_args;
+typedef int (*DC_device_operator) (struct dc_launch_args *args, const double *opParams, int nbParams,
+                                   double *deviceValues, void *stream);
+void DC_assembly_device_with (DC_device_operator launcher, const double *opParams, int nbParams,
+                              double *nodeToNodeValue, int operatorDim);
+double *DC_assembly_device_resident_with (DC_device_operator launcher, const double *opParams, int nbParams,
+                                          int operatorDim);
 void DC_device_finalize ();
+
+/* ---- several domains, one GPU each (one process per domain, as with the reference's MPI/GASPI users) ----
+ * The interface of this domain in the reference's layout (DC_finalize_tree, include/DC.h:141-143): for
+ * neighbour i the nodes intfNodes[intfIndex[i] .. intfIndex[i+1]) -- 1-based local ids AFTER
+ * DC_renumber_int_array, listed in the same order by both domains -- shared with rank neighbourRank[i]
+ * (ascending).  Call before DC_device_set_mesh, which then puts the work units that own interface rows
+ * first and creates the peer-memory exchange (dc_cuda_exchange_*, include/dc_cuda.h).  Every domain hands
+ * the 128-byte handle of its receive buffer for neighbour i to that neighbour (MPI_Sendrecv, a file, ...),
+ * which connects it; from then on DC_assembly_device sums the interface entries across the domains, the
+ * exchange overlapped with the interior units (the reference's MULTITHREADED_COMM, at unit granularity). */
+void DC_device_set_interface (int nbIntf, const int *neighbourRank, const int *intfIndex, const int *intfNodes);
+/* after DC_device_set_mesh: size the exchange buffers for the operator that will be assembled
+ * (operatorDim^2 doubles per interface edge); then swap the handles */
+void DC_device_prepare_exchange (int operatorDim);
+void DC_device_exchange_handle (int intf, void *handle128);
+void DC_device_exchange_connect (int intf, const void *handle128);
 
 extern "C" {
     void dc_device_init_ (int *device);
@@ -53,6 +79,10 @@ extern "C" {
     void dc_assembly_device_ (int *op, const double *opParams, int *nbParams,
                               double *nodeToNodeValue, int *operatorDim);
     void dc_device_finalize_ ();
+    void dc_device_set_interface_ (int *nbIntf, const int *neighbourRank, const int *intfIndex, const int *intfNodes);
+    void dc_device_prepare_exchange_ (int *operatorDim);
+    void dc_device_exchange_handle_ (int *intf, void *handle128);
+    void dc_device_exchange_connect_ (int *intf, const void *handle128);
     /* flatten the current tree in pre-order: 8 ints per tree node
      * {firstElem,lastElem,lastSep,firstNode,lastNode,isSep,isLeaf,hasSep};
      * returns the node count (call with out = NULL to size the buffer) */
