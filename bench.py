@@ -190,9 +190,10 @@ def main():
                          "default capacity of 200 elements; -1 = 62 for elasticity on coordinate-bisection trees, else 0")
     ap.add_argument("--persistent", type=int, default=int(os.environ.get("DC_BENCH_PERSISTENT", "1")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--verify", action="store_true",
-                    help="full-size property checks on the device (repeatability, atomic mode within 1e-12, "
-                         "rigid translations in the kernel of the operator); printed as a second JSON line")
+    ap.add_argument("--verify", action="store_true", help="(default at one GPU; kept for compatibility)")
+    ap.add_argument("--no-verify", action="store_true",
+                    help="skip the full-size property checks (repeatability, atomic mode within 1e-12, rigid translations "
+                         "in the kernel of the operator) that the line carries as `verify` at one GPU")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     n, dim, vec, builder = WORKLOADS[args.workload]
@@ -416,9 +417,10 @@ def main():
         base = cpu_reference(dim, 3, 1, leaf_nodes=args.leaf_nodes)
         base.pop("ms_per_step")
         line["cpu_baseline"] = base
-    print(json.dumps(line), flush=True)
-    if args.verify and world == 1:
-        # size-independent properties at the full workload size (the oracle cannot run here)
+    if world == 1 and not args.no_verify:
+        # size-independent properties at the full workload size (the oracle cannot run here): a repeat run is
+        # bitwise equal, the order-free atomic mode agrees within 1e-12, and rigid translations are in the
+        # kernel of the operator (row block sums vanish)
         ctx.assemble(op, prm, dc.MODE_DETERMINISTIC, vals, stream)
         torch.cuda.synchronize()
         again = torch.empty_like(vals)
@@ -437,20 +439,18 @@ def main():
         atomic_rel = max(float((again[a:b] - vals[a:b]).abs().max()) for a, b in chunks(vals.numel())) / scale
         del again
         torch.cuda.empty_cache()
-        row_t = ctx._keep[2]
+        row_t = ctx._keep[2] if getattr(ctx, "_keep", None) else torch.from_numpy(info["row"]).to(device)
         acc = torch.zeros((N, per), dtype=torch.float64, device=device)
         echunk = chunk // 16
-        edge_row = torch.searchsorted(row_t[1:].contiguous(), torch.arange(0, nnz, echunk, device=device, dtype=row_t.dtype),
-                                      right=True)                      # row of the first edge of every chunk
-        for ci, (a, b) in enumerate((f, min(nnz, f + echunk)) for f in range(0, nnz, echunk)):
+        for a, b in ((f, min(nnz, f + echunk)) for f in range(0, nnz, echunk)):
             ids = torch.searchsorted(row_t[1:].contiguous(), torch.arange(a, b, device=device, dtype=row_t.dtype), right=True)
             acc.index_add_(0, ids, vals.view(nnz, per)[a:b])
         rowsum_rel = float(acc.abs().max()) / scale               # constants / translations: K * 1 = 0
-        del edge_row
-        print(json.dumps({"verify": {"elements": E, "deterministic_repeat_bitwise": repeatable,
-                                     "atomic_vs_deterministic_max_rel": atomic_rel,
-                                     "row_block_sums_max_rel": rowsum_rel, "tolerance": 1e-12,
-                                     "ok": repeatable and atomic_rel <= 1e-12 and rowsum_rel <= 1e-9}}), flush=True)
+        del acc
+        line["verify"] = {"elements": E, "deterministic_repeat_bitwise": repeatable,
+                          "atomic_vs_deterministic_max_rel": atomic_rel, "row_block_sums_max_rel": rowsum_rel,
+                          "tolerance": 1e-12, "ok": bool(repeatable and atomic_rel <= 1e-12 and rowsum_rel <= 1e-9)}
+    print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

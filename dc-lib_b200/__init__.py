@@ -90,6 +90,7 @@ def _declare(L):
     L.dc_cuda_update_coords.argtypes = [vp, vp, vp]
     L.dc_cuda_upload_plan.argtypes = [vp, POINTER(Plan)]
     L.dc_cuda_set_plan_device.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int]
+    L.dc_cuda_set_plan_big_device.argtypes = [vp, vp, vp, vp, vp, c_int64]
     L.dc_cuda_download_range.argtypes = [vp, c_int64, c_int64, vp, vp]
     L.dc_cuda_upload_lists.argtypes = [vp, vp, vp, vp, c_int64, c_int64]
     L.dc_cuda_assemble.argtypes = [vp, c_int, vp, c_int, c_int, vp, vp]
@@ -330,7 +331,10 @@ class HostPlan:
                     haloNodes=view(c.haloNodes, c.nbHaloNodes, np.int32), tgt=view(c.tgt, c.nbTgt, np.int32, 2),
                     nbUnits=int(c.nbUnits), maxSlots=int(c.maxSlots), maxHalo=int(c.maxHalo), maxNodes=int(c.maxNodes),
                     maxTasks=int(c.maxTasks), maxItems=int(c.maxItems), maxTgt=int(c.maxTgt),
-                    symmetric=int(c.symmetric), bigEdges=int(c.big.nbEdges))
+                    symmetric=int(c.symmetric), bigEdges=int(c.big.nbEdges),
+                    bigEdge=view(c.big.edge, c.big.nbEdges, np.int64), bigPtr=view(c.big.ptr, c.big.nbEdges + 1 if c.big.nbEdges else 0, np.int64),
+                    bigItem=view(c.big.item, c.big.nbItems, np.uint32),
+                    bigEdgeT=view(c.big.edgeT, c.big.nbEdges if c.symmetric else 0, np.int64))
 
     def order_units(self, node_flag):
         """Units that own a flagged row (uint8 per node: the interface nodes) move to the front of the
@@ -394,6 +398,10 @@ class Context:
                                                _p(t["slotNodes"]), _p(t["haloNodes"]), _p(t["diagRel"]), _p(t["tgt"]),
                                                t["nbUnits"], t["maxSlots"], t["maxHalo"], t["maxNodes"], t["maxTasks"],
                                                t["maxItems"], t["maxTgt"], t["symmetric"]), "dc_cuda_set_plan_device")
+        if t.get("bigEdges"):
+            self._ck(lib().dc_cuda_set_plan_big_device(self.h, _p(t["bigEdge"]), _p(t["bigPtr"]), _p(t["bigItem"]),
+                                                       _p(t["bigEdgeT"]) if t["symmetric"] else None, t["bigEdges"]),
+                     "dc_cuda_set_plan_big_device")
 
     def download_range(self, d_values, first, count, h_buf, stream=None):
         self._ck(lib().dc_cuda_download_range(_p(d_values), first, count, _p(h_buf), stream), "dc_cuda_download_range")

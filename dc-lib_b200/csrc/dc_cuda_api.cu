@@ -110,6 +110,7 @@ static void free_plan(dc_cuda_ctx *c)
     if (!c->ownsPlan) {
         c->d_units = nullptr; c->d_tasks = nullptr; c->d_items = nullptr; c->d_halo = c->d_diagRel = c->d_tgt = nullptr;
         c->d_slotNodes = nullptr;
+        c->d_bigEdge = c->d_bigPtr = c->d_bigEdgeT = nullptr; c->d_bigItem = nullptr;
         c->ownsPlan = true;
     }
     cudaFree(c->d_slotNodes); c->d_slotNodes = nullptr;
@@ -255,6 +256,23 @@ extern "C" int dc_cuda_set_plan_device(dc_cuda_ctx *c, const void *d_units, cons
     c->nbBigEdges = 0;
     c->maxSlots = maxSlots; c->maxHalo = maxHalo; c->maxNodes = maxNodes; c->maxTasks = maxTasks;
     c->maxItems = maxItems; c->maxTgt = maxTgt; c->symmetric = symmetric;
+    return 0;
+}
+
+/* fallback lists (rows too large for a unit) for a schedule adopted with dc_cuda_set_plan_device */
+extern "C" int dc_cuda_set_plan_big_device(dc_cuda_ctx *c, const int64_t *d_bigEdge, const int64_t *d_bigPtr,
+                                           const uint32_t *d_bigItem, const int64_t *d_bigEdgeT, int64_t nbBigEdges)
+{
+    if (!c || c->ownsPlan) return fail(-1, "dc_cuda_set_plan_big_device: call dc_cuda_set_plan_device first");
+    if (nbBigEdges < 0 || (nbBigEdges > 0 && (!d_bigEdge || !d_bigPtr || !d_bigItem)))
+        return fail(-1, "dc_cuda_set_plan_big_device: bad argument");
+    if (c->symmetric && nbBigEdges > 0 && !d_bigEdgeT)
+        return fail(-1, "dc_cuda_set_plan_big_device: the symmetric schedule needs the transposed edges");
+    c->d_bigEdge = const_cast<int64_t *>(d_bigEdge);
+    c->d_bigPtr = const_cast<int64_t *>(d_bigPtr);
+    c->d_bigItem = const_cast<uint32_t *>(d_bigItem);
+    c->d_bigEdgeT = const_cast<int64_t *>(d_bigEdgeT);
+    c->nbBigEdges = nbBigEdges;
     return 0;
 }
 

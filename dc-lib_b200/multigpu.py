@@ -214,7 +214,7 @@ def setup_device_parts(n, rank, world, device, slots=512, dist=None, seed=2024, 
     ctx.set_front_units(nb_front)
     st = plan.stats()
     info = dict(E=p["E"], N=p["N"], nnz=p["nnz"], E_global=E_glob, stats=st, tree_s=t_tree, plan_s=t_plan, csr_s=p["csr_s"],
-                mesh_s=t_mesh, partition_s=t_part, nb_front=nb_front, intf=p["intf"],
+                mesh_s=t_mesh, partition_s=t_part, nb_front=nb_front, intf=p["intf"], row=p["row"],
                 coord=torch.from_numpy(p["coord"]), setup_s=time.time() - t0,
                 interface_edges=int(sum(e.shape[0] for e in p["intf"].values())))
     return ctx, info
@@ -274,7 +274,7 @@ def setup_device_slabs(n, rank, world, device, builder="geometric", vec=0, slots
     from . import Context, HostPlan, permute_double_2d
 
     names = ["conn", "row", "col", "node_perm", "units", "tasks", "items", "slotNodes", "haloNodes", "diagRel", "tgt",
-             "intf_left", "intf_right"]
+             "bigEdge", "bigPtr", "bigItem", "bigEdgeT", "intf_left", "intf_right"]
     t0 = time.time()
     tensors, meta = {}, None
     if rank == 0:
@@ -297,18 +297,17 @@ def setup_device_slabs(n, rank, world, device, builder="geometric", vec=0, slots
             nb_front = plan.order_units(flag)
         t_plan = time.time() - t1
         arr = plan.arrays()
-        if arr["bigEdges"]:
-            raise RuntimeError("setup_device_slabs: rows exceeding the unit budget are not supported on this path")
         host = dict(conn=slab["conn"], row=slab["row"], col=slab["col"], node_perm=node_perm, units=arr["units"],
                     tasks=arr["tasks"], items=arr["items"].view(np.int16), slotNodes=arr["slotNodes"].view(np.int16),
                     haloNodes=arr["haloNodes"],
                     diagRel=plan.diag_rel(slab["N"]), tgt=arr["tgt"],
+                    bigEdge=arr["bigEdge"], bigPtr=arr["bigPtr"], bigItem=arr["bigItem"].view(np.int32), bigEdgeT=arr["bigEdgeT"],
                     intf_left=intf_l, intf_right=intf_r)
         for k in names:
             tensors[k] = torch.from_numpy(np.ascontiguousarray(host[k])).to(device)
         st = plan.stats()
         meta = dict(shapes={k: (tuple(tensors[k].shape), str(tensors[k].dtype)) for k in names},
-                    ints={k: arr[k] for k in ("nbUnits", "maxSlots", "maxHalo", "maxNodes", "maxTasks", "maxItems", "maxTgt", "symmetric")},
+                    ints={k: arr[k] for k in ("nbUnits", "maxSlots", "maxHalo", "maxNodes", "maxTasks", "maxItems", "maxTgt", "symmetric", "bigEdges")},
                     E=slab["E"], N=slab["N"], nnz=slab["nnz"], stats=st, tree_s=t_tree, plan_s=t_plan, nb_front=nb_front,
                     csr_s=slab["csr_s"])
         del plan, slab, host, arr
@@ -333,7 +332,8 @@ def setup_device_slabs(n, rank, world, device, builder="geometric", vec=0, slots
     ctx.set_mesh_device(tensors["conn"], d_coord, tensors["row"], tensors["col"], meta["nnz"], 0)
     plan_t = dict(units=tensors["units"], tasks=tensors["tasks"], items=tensors["items"],
                   slotNodes=tensors["slotNodes"], haloNodes=tensors["haloNodes"], diagRel=tensors["diagRel"],
-                  tgt=tensors["tgt"], **meta["ints"])
+                  tgt=tensors["tgt"], bigEdge=tensors["bigEdge"], bigPtr=tensors["bigPtr"], bigItem=tensors["bigItem"],
+                  bigEdgeT=tensors["bigEdgeT"], **meta["ints"])
     ctx.set_plan_device(plan_t)
     ctx.set_front_units(meta.get("nb_front", 0))
     intf = {}

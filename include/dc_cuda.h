@@ -60,12 +60,16 @@ int  dc_cuda_update_coords(dc_cuda_ctx *ctx, const double *h_coord, void *stream
 /* Schedule built by dc_plan_build() (host); copied to the device. */
 int  dc_cuda_upload_plan(dc_cuda_ctx *ctx, const struct dc_plan_s *plan);
 /* Same, adopting schedule arrays that already live in device memory (e.g. received from
- * another rank over NCCL); not copied, not freed.  No big-row fallback list on this path. */
+ * another rank over NCCL); not copied, not freed. */
 int  dc_cuda_set_plan_device(dc_cuda_ctx *ctx, const void *d_units, const void *d_tasks,
                              const void *d_items, const void *d_slotNodes, const int *d_haloNodes,
                              const int *d_diagRel, const int *d_tgt, int64_t nbUnits, int maxSlots,
                              int maxHalo, int maxNodes, int maxTasks, int maxItems, int maxTgt,
                              int symmetric);
+/* ... and its fallback lists for the rows that fit no unit (dc_plan_t.big: edge, ptr, item and, for the
+ * symmetric schedule, edgeT), adopted the same way. */
+int  dc_cuda_set_plan_big_device(dc_cuda_ctx *ctx, const int64_t *d_bigEdge, const int64_t *d_bigPtr,
+                                 const uint32_t *d_bigItem, const int64_t *d_bigEdgeT, int64_t nbBigEdges);
 /* Explicit contribution lists for DC_MODE_LIST (all edges). */
 int  dc_cuda_upload_lists(dc_cuda_ctx *ctx, const int64_t *h_edge, const int64_t *h_ptr,
                           const uint32_t *h_item, int64_t nbEdges, int64_t nbItems);

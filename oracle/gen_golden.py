@@ -22,8 +22,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import common  # noqa: E402
 
 CASES = [(4, 0), (6, 0), (6, 4), (8, 0), (8, 4), (10, 0), (10, 2), (10, 4), (10, 8), (16, 0), (16, 4),
-         (20, 0), (20, 4), (40, 0), (40, 4)]
-HUB_CASES = [(18, 0), (18, 4)]
+         (20, 0), (20, 4), (40, 0), (40, 4), (64, 0)]
+HUB_CASES = [(18, 0), (18, 4), (64, 0)]
 RAW_LIMIT = 8       # raw tree file + values kept up to this cube size
 
 
@@ -40,7 +40,7 @@ def main():
                              tree_md5=common.md5(mesh["tree"]), conn_md5=common.md5(mesh["conn"]),
                              coord_md5=common.md5(mesh["coord"]))
                 for dim in (1, 3):
-                    if n > 20 and dim == 3 and vec == 0:
+                    if n > 20 and dim == 3 and vec == 0 and not hub:
                         continue
                     vals = ref.traversal(mesh, dim)
                     entry[f"values_md5_d{dim}"] = common.md5(vals)

@@ -429,3 +429,59 @@ def test_more_halo_nodes_than_threads(tmp_path):
     ctx.set_option("unit_threads", 128)
     for dim in (3, 1):
         assert _run(ctx, mesh, dim, dc.MODE_DETERMINISTIC).tobytes() == oracle_serial(mesh, dim).tobytes()
+
+
+def test_device_resident_plan_with_hub_rows(tmp_path):
+    """dc_cuda_set_plan_device + dc_cuda_set_plan_big_device: the schedule arrays adopted from device memory (the
+    path multi-GPU runs use after receiving the schedule from another rank), on a hub mesh whose high-valence
+    rows exceed the unit budget and go through the fallback lists: bit-identical to the oracle."""
+    import torch
+    mesh = prepare_mesh(MineLib(0), 18, tmp_path, hub=True)
+    plan = dc.HostPlan(mesh["conn"], mesh["N"], mesh["row"], mesh["col"], 0, tree_records(mesh), 100)
+    arr = plan.arrays()
+    assert arr["bigEdges"] > 0
+    dev = "cuda:0"
+    t = {k: torch.from_numpy(np.ascontiguousarray(arr[k])).to(dev) for k in ("units", "tasks", "tgt", "haloNodes", "bigEdge", "bigPtr", "bigEdgeT")}
+    t["items"] = torch.from_numpy(arr["items"].view(np.int16).copy()).to(dev)
+    t["slotNodes"] = torch.from_numpy(arr["slotNodes"].view(np.int16).copy()).to(dev)
+    t["bigItem"] = torch.from_numpy(arr["bigItem"].view(np.int32).copy()).to(dev)
+    t["diagRel"] = torch.from_numpy(plan.diag_rel(mesh["N"]).copy()).to(dev)
+    for k in ("nbUnits", "maxSlots", "maxHalo", "maxNodes", "maxTasks", "maxItems", "maxTgt", "symmetric", "bigEdges"):
+        t[k] = arr[k]
+    d_coord = torch.zeros((mesh["N"] + 2, 3), dtype=torch.float64, device=dev)
+    d_coord[:mesh["N"]] = torch.from_numpy(mesh["coord"]).to(dev)
+    ctx = dc.Context(0)
+    ctx.set_mesh_device(torch.from_numpy(mesh["conn"]).to(dev), d_coord[:mesh["N"]], torch.from_numpy(mesh["row"]).to(dev),
+                        torch.from_numpy(mesh["col"]).to(dev), mesh["nnz"], 0)
+    ctx.set_plan_device(t)
+    for dim, op, prm in ((1, dc.OP_LAPLACIAN, None), (3, dc.OP_ELASTICITY, [LAMBDA, MU])):
+        vals = torch.full((mesh["nnz"] * dim * dim,), float("nan"), dtype=torch.float64, device=dev)
+        ctx.assemble(op, prm, dc.MODE_DETERMINISTIC, vals)
+        torch.cuda.synchronize()
+        assert vals.cpu().numpy().tobytes() == oracle_serial(mesh, dim).tobytes()
+
+
+@pytest.mark.parametrize("key,dim", [("kuhn64_vec0", 1), ("hub64_vec0", 1), ("hub64_vec0", 3)])
+def test_parity_at_64_cubed_against_reference_golden(tmp_path, key, dim):
+    """1.5 M tets: the values of the reference's own traversal over the reference's own tree (golden md5) ==
+    GPU deterministic mode, bit for bit; hub64 is BASELINE config C5 (high-valence mesh, nodes of valence
+    ~100): the order-free red.global mode agrees within 1e-12."""
+    g = GOLD[key]
+    mesh = prepare_mesh(MineLib(g["vec"]), g["n"], tmp_path, hub=g["hub"])
+    ctx, _ = _ctx(mesh, slots=512)
+    got = _run(ctx, mesh, dim, dc.MODE_DETERMINISTIC)
+    assert md5(got) == g[f"values_md5_d{dim}"]
+    if g["hub"]:
+        fast = _run(ctx, mesh, dim, dc.MODE_ATOMIC)
+        assert _rel_err(fast, got) <= REL_TOL
+
+
+def test_parity_at_100_cubed_metis_tree_against_the_oracle(tmp_path):
+    """6 M tets with the tree the reference would build (METIS node partitions, capacity 200): GPU
+    deterministic elasticity == the oracle's serial ascending-element loop (= the reference's traversal
+    order, tests/test_oracle_vs_reference.py), bit for bit."""
+    mesh = prepare_mesh(MineLib(0), 100, tmp_path)
+    ctx, plan = _ctx(mesh, slots=512)
+    got = _run(ctx, mesh, 3, dc.MODE_DETERMINISTIC)
+    want = oracle_serial(mesh, 3)
+    assert got.tobytes() == want.tobytes()

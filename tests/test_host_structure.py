@@ -31,11 +31,14 @@ def test_tree_file_matches_golden(tmp_path, key):
             assert f.read() == mesh["tree"]
 
 
-@pytest.mark.parametrize("key", ["kuhn40_vec0", "kuhn40_vec4"])
+@pytest.mark.parametrize("key", ["kuhn40_vec0", "kuhn40_vec4", "kuhn64_vec0", "hub64_vec0"])
 def test_tree_file_matches_golden_c1_c2(tmp_path, key):
-    """BASELINE configs C1 / C2: the 40^3 cube, pure D&C and D&C + colouring (VEC_SIZE 4)."""
+    """BASELINE configs C1 / C2: the 40^3 cube, pure D&C and D&C + colouring (VEC_SIZE 4); the 64^3 cube
+    (1.57 M tets, the largest size SURVEY.md 4 asks a structural golden for) and the 64^3 hub mesh of
+    config C5 (valence ~100 hubs): tree file, element order and renumbering equal the reference's bytes."""
     g = GOLD[key]
-    mesh = prepare_mesh(MineLib(g["vec"]), g["n"], tmp_path)
+    mesh = prepare_mesh(MineLib(g["vec"]), g["n"], tmp_path, hub=g["hub"])
+    assert (mesh["E"], mesh["N"], mesh["nnz"]) == (g["E"], g["N"], g["nnz"])
     assert md5(mesh["tree"]) == g["tree_md5"]
     assert md5(mesh["conn"]) == g["conn_md5"]
 
