@@ -100,6 +100,8 @@ def _declare(L):
     L.dc_cuda_permute_double_2d.argtypes = [vp, vp, vp, c_int64, c_int, vp]
     L.dc_cuda_permute_int_2d.argtypes = [vp, vp, vp, c_int64, c_int, vp]
     L.dc_cuda_renumber.argtypes = [vp, vp, c_int64, c_int, vp]
+    L.dc_cuda_gather_double_2d.argtypes = [vp, vp, vp, c_int64, c_int, vp]
+    L.dc_cuda_gather_int_2d.argtypes = [vp, vp, vp, c_int64, c_int, vp]
     L.dc_cuda_reset_edges.argtypes = [vp, c_int64, c_int64, c_int, vp]
     L.dc_cuda_launch_count.argtypes = [vp]
     L.dc_cuda_launch_count.restype = c_int64
@@ -581,6 +583,19 @@ def permute_double_2d(d_in, d_out, d_perm, dimItem, stream=None):
 
 def permute_int_2d(d_in, d_out, d_perm, dimItem, stream=None):
     rc = lib().dc_cuda_permute_int_2d(_p(d_in), _p(d_out), _p(d_perm), d_perm.shape[0], dimItem, stream)
+    if rc:
+        raise RuntimeError(lib().dc_cuda_last_error().decode())
+
+
+def gather_double_2d(d_in, d_out, d_inv, dimItem, stream=None):
+    """d_out[d] = d_in[inv[d]] (inv = inverse permutation: new position -> old position)."""
+    rc = lib().dc_cuda_gather_double_2d(_p(d_in), _p(d_out), _p(d_inv), d_inv.shape[0], dimItem, stream)
+    if rc:
+        raise RuntimeError(lib().dc_cuda_last_error().decode())
+
+
+def gather_int_2d(d_in, d_out, d_inv, dimItem, stream=None):
+    rc = lib().dc_cuda_gather_int_2d(_p(d_in), _p(d_out), _p(d_inv), d_inv.shape[0], dimItem, stream)
     if rc:
         raise RuntimeError(lib().dc_cuda_last_error().decode())
 

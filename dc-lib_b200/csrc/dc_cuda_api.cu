@@ -42,7 +42,7 @@ struct dc_cuda_ctx {
     uint16_t *d_slotNodes = nullptr;
     int *d_tgt = nullptr;
     int64_t *d_bigEdgeT = nullptr;
-    int threads = 256;       /* CTA size of the unit kernel (128, 192 or 256) */
+    int threads = 256;       /* CTA size of the unit kernel (128, 256 or 512) */
     int persistent = 1;      /* persistent grid with next-unit prefetch (0: one CTA per unit) */
     int64_t nbUnits = 0, nbBigEdges = 0;
     bool ownsPlan = true;
@@ -503,10 +503,32 @@ extern "C" int dc_cuda_permute_int_2d(const int *d_in, int *d_out, const int *d_
     return 0;
 }
 
+extern "C" int dc_cuda_gather_double_2d(const double *d_in, double *d_out, const int *d_inv, int64_t nbItem, int dimItem,
+                                        void *stream)
+{
+    if (nbItem <= 0) return 0;
+    gather_rows<double><<<grid_for(nbItem * dimItem, 256), 256, 0, (cudaStream_t)stream>>>(d_in, d_out, d_inv, nbItem, dimItem);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int dc_cuda_gather_int_2d(const int *d_in, int *d_out, const int *d_inv, int64_t nbItem, int dimItem, void *stream)
+{
+    if (nbItem <= 0) return 0;
+    const bool vec = dimItem == 4 && ((reinterpret_cast<uintptr_t>(d_in) | reinterpret_cast<uintptr_t>(d_out)) & 15) == 0;
+    if (vec)
+        gather_rows_int4<<<grid_for((nbItem + 1) / 2, 256), 256, 0, (cudaStream_t)stream>>>(
+            reinterpret_cast<const int4 *>(d_in), reinterpret_cast<int4 *>(d_out), d_inv, nbItem);
+    else
+        gather_rows<int><<<grid_for(nbItem * dimItem, 256), 256, 0, (cudaStream_t)stream>>>(d_in, d_out, d_inv, nbItem, dimItem);
+    CK(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int dc_cuda_renumber(int *d_tab, const int *d_perm, int64_t size, int isFortran, void *stream)
 {
     if (size <= 0) return 0;
-    renumber<<<grid_for(size, 256), 256, 0, (cudaStream_t)stream>>>(d_tab, d_perm, size, isFortran ? 1 : 0);
+    renumber<<<grid_for(size / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(d_tab, d_perm, size, isFortran ? 1 : 0);
     CK(cudaGetLastError());
     return 0;
 }
@@ -696,8 +718,8 @@ extern "C" int dc_cuda_set_option(dc_cuda_ctx *c, const char *name, int value)
 {
     if (!c || !name) return fail(-1, "dc_cuda_set_option: null argument");
     if (!strcmp(name, "unit_threads")) {
-        if (value != 128 && value != 192 && value != 256 && value != 512)
-            return fail(-12, "dc_cuda_set_option: unit_threads must be 128, 192, 256 or 512");
+        if (value != 128 && value != 256 && value != 512)
+            return fail(-12, "dc_cuda_set_option: unit_threads must be 128, 256 or 512");
         c->threads = value;
         return 0;
     }

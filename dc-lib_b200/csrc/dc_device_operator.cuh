@@ -127,7 +127,6 @@ inline int launch_operator(dc_launch_args *a, const double *h_params, int nbPara
             if (a->symmetric)
                 rc = (a->threads == 128)   ? launch_units<Op, 128, 4, true>(a, d_values, P, s)
                      : (a->threads == 512) ? launch_units<Op, 512, 1, true>(a, d_values, P, s)
-                     : (a->threads == 192) ? launch_units<Op, 192, 3, true>(a, d_values, P, s)
                                            : launch_units<Op, 256, 2, true>(a, d_values, P, s);
             else
                 rc = (a->threads == 128) ? launch_units<Op, 128, 4, false>(a, d_values, P, s)

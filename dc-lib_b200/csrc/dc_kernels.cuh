@@ -756,12 +756,65 @@ __global__ void __launch_bounds__(256) permute_rows_int4(const int4 *__restrict_
         out[__ldg(perm + i)] = in[i];
 }
 
+/* out[d][:] = in[inv[d]][:] -- the same permutation told by destination (inv = inverse of perm).
+ * Measured on B200 (profiles/README.md, round 2): a partial write of a 32-byte sector makes the L2
+ * fetch the sector from DRAM first, so the scatter form above moves twice the algorithmic bytes
+ * (rows of 16 or 24 bytes never fill a sector on their own).  Told by destination, consecutive
+ * threads write consecutive words -- whole sectors, whole lines -- and only the READS are scattered,
+ * which costs nothing extra when neighbouring rows are fetched close in time (tree orderings are
+ * local).  The library owns both directions of its permutations, so its own callers use this form. */
+template <typename T>
+__global__ void __launch_bounds__(256) gather_rows(const T *__restrict__ in, T *__restrict__ out,
+                                                   const int *__restrict__ inv, int64_t nbItem, int dimItem)
+{
+    const int64_t total = nbItem * dimItem;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += stride) {
+        const int64_t d = w / dimItem;
+        const int j = (int)(w - d * dimItem);
+        out[w] = __ldg(in + (int64_t)__ldg(inv + d) * dimItem + j);
+    }
+}
+
+/* 16-byte rows (the tetrahedron connectivity): two rows in flight per thread */
+__global__ void __launch_bounds__(256) gather_rows_int4(const int4 *__restrict__ in, int4 *__restrict__ out,
+                                                        const int *__restrict__ inv, int64_t nbItem)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; d < nbItem; d += 2 * stride) {
+        const int64_t d1 = d + stride;
+        const int s0 = __ldg(inv + d), s1 = d1 < nbItem ? __ldg(inv + d1) : 0;
+        const int4 a = __ldg(in + s0);
+        if (d1 < nbItem) {
+            const int4 b = __ldg(in + s1);
+            out[d1] = b;
+        }
+        out[d] = a;
+    }
+}
+
+/* tab[i] = perm[tab[i] - base] + base, four entries per thread (16-byte loads and stores of tab; the
+ * four look-ups of perm are independent) with a scalar head / tail */
 __global__ void __launch_bounds__(256) renumber(int *__restrict__ tab, const int *__restrict__ perm, int64_t size,
                                                 int base)
 {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < size; i += stride)
-        tab[i] = __ldg(perm + (tab[i] - base)) + base;
+    const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t head = ((16 - (reinterpret_cast<uintptr_t>(tab) & 15)) & 15) / 4;        /* ints before the first 16-byte boundary */
+    const int64_t h = head < size ? head : size;
+    const int64_t quads = (size - h) / 4;
+    int4 *body = reinterpret_cast<int4 *>(tab + h);
+    for (int64_t q = t0; q < quads; q += stride) {
+        int4 v = body[q];
+        v.x = __ldg(perm + (v.x - base)) + base;
+        v.y = __ldg(perm + (v.y - base)) + base;
+        v.z = __ldg(perm + (v.z - base)) + base;
+        v.w = __ldg(perm + (v.w - base)) + base;
+        body[q] = v;
+    }
+    if (t0 < h) tab[t0] = __ldg(perm + (tab[t0] - base)) + base;
+    const int64_t tail = h + 4 * quads + t0;
+    if (tail < size) tab[tail] = __ldg(perm + (tab[tail] - base)) + base;
 }
 
 /* ---- interface exchange (multi-GPU) ------------------------------------------ */

@@ -271,7 +271,7 @@ def setup_device_slabs(n, rank, world, device, builder="geometric", vec=0, slots
 
     import torch
 
-    from . import Context, HostPlan, permute_double_2d
+    from . import Context, HostPlan, gather_double_2d
 
     names = ["conn", "row", "col", "node_perm", "units", "tasks", "items", "slotNodes", "haloNodes", "diagRel", "tgt",
              "bigEdge", "bigPtr", "bigItem", "bigEdgeT", "intf_left", "intf_right"]
@@ -325,7 +325,11 @@ def setup_device_slabs(n, rank, world, device, builder="geometric", vec=0, slots
     _, coord_old, _ = kuhn_cube_fast(n, seed=seed, x_offset=rank * n, coords_only=True)
     d_old = torch.from_numpy(coord_old).to(device)
     d_coord = torch.zeros((d_old.shape[0] + 2, 3), dtype=torch.float64, device=device)[:d_old.shape[0]]   # 2 spare nodes
-    permute_double_2d(d_old, d_coord, tensors["node_perm"], 3, torch.cuda.current_stream().cuda_stream)
+    # told by destination (new position -> old position): whole sectors are written
+    inv = torch.empty_like(tensors["node_perm"])
+    inv[tensors["node_perm"].long()] = torch.arange(inv.numel(), dtype=inv.dtype, device=inv.device)
+    gather_double_2d(d_old, d_coord, inv, 3, torch.cuda.current_stream().cuda_stream)
+    del inv
     torch.cuda.synchronize()
     del d_old, coord_old
     ctx = Context(torch.device(device).index or 0)

@@ -97,6 +97,13 @@ int  dc_cuda_permute_double_2d(const double *d_in, double *d_out, const int *d_p
                                int64_t nbItem, int dimItem, void *stream);
 int  dc_cuda_permute_int_2d(const int *d_in, int *d_out, const int *d_perm, int64_t nbItem,
                             int dimItem, void *stream);
+/* The same permutation told by destination: d_out[d] = d_in[inv[d]] with inv the inverse of perm
+ * (new position -> old position).  Whole sectors are written, only the reads are scattered: the fast
+ * form on B200, where a partial sector write costs a DRAM fetch (profiles/README.md). */
+int  dc_cuda_gather_double_2d(const double *d_in, double *d_out, const int *d_inv, int64_t nbItem,
+                              int dimItem, void *stream);
+int  dc_cuda_gather_int_2d(const int *d_in, int *d_out, const int *d_inv, int64_t nbItem, int dimItem,
+                           void *stream);
 int  dc_cuda_renumber(int *d_tab, const int *d_perm, int64_t size, int isFortran, void *stream);
 /* Zero d_values[first*perEdge, (last+1)*perEdge) -- the reset of one edge interval. */
 int  dc_cuda_reset_edges(double *d_values, int64_t firstEdge, int64_t lastEdge, int perEdge,
@@ -190,7 +197,7 @@ int  dc_cuda_csr_columns(dc_cuda_csr *handle, int *d_col, int colBase, void *str
 int  dc_cuda_csr_node_to_elem(dc_cuda_csr *handle, int64_t *d_ptr, int *d_val, void *stream);
 void dc_cuda_csr_end(dc_cuda_csr *handle);
 
-/* Tuning knobs: "unit_threads" = CTA size of the unit kernel (128, 192, 256 or 512; default 256);
+/* Tuning knobs: "unit_threads" = CTA size of the unit kernel (128, 256 or 512; default 256);
  * "persistent" = 1 (default): SMs x resident CTAs stride over the units and prefetch the next
  * unit's inputs, 0: one CTA per unit; "exchange_reserve" = CTA slots dc_cuda_assemble_exchange leaves
  * free beside the interior units for the pack / unpack kernels (default 4). */

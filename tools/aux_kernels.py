@@ -35,7 +35,25 @@ coord = torch.rand(N, 3, dtype=torch.float64, device=dev, generator=g); out = to
 report("permute_rows<double> coord [N][3]", timed(lambda: dc.permute_double_2d(coord, out, nperm, 3)), 2 * coord.numel() * 8 + 4 * N)
 conn = torch.randint(1, N + 1, (E, 4), dtype=torch.int32, device=dev, generator=g); outc = torch.empty_like(conn)
 report("permute_rows_int4 elemToNode [E][4]", timed(lambda: dc.permute_int_2d(conn, outc, eperm, 4)), 2 * conn.numel() * 4 + 4 * E)
-report("renumber elemToNode (4E entries)", timed(lambda: dc.renumber(outc, nperm, True)), 2 * conn.numel() * 4)
+ninv = torch.empty_like(nperm); ninv[nperm.long()] = torch.arange(N, dtype=torch.int32, device=dev)
+einv = torch.empty_like(eperm); einv[eperm.long()] = torch.arange(E, dtype=torch.int32, device=dev)
+report("gather_rows<double> coord [N][3] (by destination)", timed(lambda: dc.gather_double_2d(coord, out, ninv, 3)), 2 * coord.numel() * 8 + 4 * N)
+report("gather_rows_int4 elemToNode [E][4] (by destination)", timed(lambda: dc.gather_int_2d(conn, outc, einv, 4)), 2 * conn.numel() * 4 + 4 * E)
+report("renumber elemToNode (4E entries), random node ids", timed(lambda: dc.renumber(outc, nperm, True)), 2 * conn.numel() * 4)
+# node ids as a tree-ordered mesh has them: the nodes of an element lie within a few thousand ids of each other
+base_id = (torch.arange(E, device=dev) * (N / E)).long()
+local = (base_id[:, None] + torch.randint(-2000, 2000, (E, 4), device=dev, generator=g)).clamp_(0, N - 1).to(torch.int32) + 1
+report("renumber elemToNode (4E entries), local node ids", timed(lambda: dc.renumber(local, nperm, True)), 2 * local.numel() * 4)
+del local, base_id
+# the connectivity of a real tree-ordered mesh (160^3 cube after DC_create_tree_geometric / permute / renumber):
+# neighbouring elements share nodes, so the lanes of a load share sectors
+import bench
+dc.DC_set_max_elem_per_part(bench.leaf_capacity(160, 62))
+w = bench.build_workload(dc, 160, 0, "geometric")
+real = torch.from_numpy(w["conn"]).to(dev)
+rperm = perm_like_tree(w["N"])
+report("renumber elemToNode (4E entries), 160^3 tree-ordered mesh", timed(lambda: dc.renumber(real, rperm, True)), 2 * real.numel() * 4)
+del real, rperm, w
 del conn, outc, coord, out
 for dim in (1, 3):
     vals = torch.empty(nnz * dim * dim, dtype=torch.float64, device=dev)
