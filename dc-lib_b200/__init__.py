@@ -122,6 +122,7 @@ def _declare(L):
     L.dc_get_node_perm.argtypes = [vp, c_int]
     L.dc_get_elem_perm.argtypes = [vp, c_int]
     L.dc_cuda_spmv.argtypes = [vp, c_int, vp, vp, vp, vp]
+    L.dc_cuda_block_jacobi.argtypes = [vp, c_int, vp, vp, POINTER(c_int), vp]
     L.dc_cuda_pack_edges.argtypes = [vp, vp, c_int64, c_int, vp, vp]
     L.dc_cuda_unpack_add_edges.argtypes = [vp, vp, c_int64, c_int, vp, vp]
     L.dc_cuda_exchange_create.argtypes = [POINTER(c_void_p), c_int, c_int, c_int, vp, vp, vp]
@@ -466,6 +467,12 @@ class Context:
     def spmv(self, dim, values, x, y, stream=None):
         """y = A x with the assembled block-CSR values (torch CUDA tensors)."""
         self._ck(lib().dc_cuda_spmv(self.h, dim, _p(values), _p(x), _p(y), stream), "dc_cuda_spmv")
+
+    def block_jacobi(self, dim, values, inv_diag, stream=None):
+        """inv_diag[N][dim*dim] = inverse diagonal blocks of the assembled matrix; returns the number of bad rows."""
+        bad = c_int(0)
+        self._ck(lib().dc_cuda_block_jacobi(self.h, dim, _p(values), _p(inv_diag), byref(bad), stream), "dc_cuda_block_jacobi")
+        return bad.value
 
     def set_option(self, name, value):
         self._ck(lib().dc_cuda_set_option(self.h, name.encode(), int(value)), "dc_cuda_set_option")

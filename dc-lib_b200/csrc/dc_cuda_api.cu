@@ -583,6 +583,35 @@ extern "C" int dc_cuda_spmv(dc_cuda_ctx *c, int dim, const double *d_values, con
     return 0;
 }
 
+/* inverse diagonal blocks of the assembled matrix (block-Jacobi preconditioner); *nbBad (host, may be NULL)
+ * receives the number of rows without a usable diagonal block -- reading it synchronises the stream */
+extern "C" int dc_cuda_block_jacobi(dc_cuda_ctx *c, int dim, const double *d_values, double *d_invDiag, int *nbBad,
+                                    void *stream)
+{
+    if (!c || !c->d_row || !c->d_col) return fail(-1, "dc_cuda_block_jacobi: no CSR pattern on the device");
+    if (!d_values || !d_invDiag) return fail(-1, "dc_cuda_block_jacobi: null argument");
+    if (dim != 1 && dim != 3) return fail(-9, "dc_cuda_block_jacobi: dim must be 1 or 3");
+    CK(cudaSetDevice(c->device));
+    if (c->nbNodes <= 0) { if (nbBad) *nbBad = 0; return 0; }
+    int *d_bad = nullptr;
+    cudaStream_t s = (cudaStream_t)stream;
+    CK(cudaMallocAsync((void **)&d_bad, sizeof(int), s));
+    CK(cudaMemsetAsync(d_bad, 0, sizeof(int), s));
+    const unsigned grid = grid_for((int64_t)c->nbNodes, 256);
+    if (dim == 1)
+        block_jacobi<1><<<grid, 256, 0, s>>>(c->d_row, c->d_col, c->colBase, d_values, d_invDiag, c->nbNodes, d_bad);
+    else
+        block_jacobi<3><<<grid, 256, 0, s>>>(c->d_row, c->d_col, c->colBase, d_values, d_invDiag, c->nbNodes, d_bad);
+    CK(cudaGetLastError());
+    c->launches++;
+    if (nbBad) {
+        CK(cudaMemcpyAsync(nbBad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    }
+    CK(cudaFreeAsync(d_bad, s));
+    return 0;
+}
+
 /* debug: enable per-unit phase stamps; the next assembly fills h_out[nbUnits][24] on request */
 extern "C" int dc_cuda_debug_phases(dc_cuda_ctx *c, long long *h_out)
 {

@@ -869,5 +869,56 @@ __global__ void __launch_bounds__(256) bsr_spmv(const int *__restrict__ row, con
     }
 }
 
+/* Block-Jacobi preconditioner of the assembled matrix (what the reference's user
+ * builds next): inv[r] = inverse of the D x D diagonal block of row r, one thread per row -- the diagonal
+ * edge is found in the row's columns, the 3 x 3 inverse is the adjugate over the determinant in a fixed
+ * operation order (cofactors fma(p, q, -(r * s)), det = fma(a02, c02, fma(a01, c01, a00 * c00))).
+ * A row without a diagonal entry, or a singular block, gets zeros and is counted in *bad. */
+template <int D>
+__global__ void __launch_bounds__(256) block_jacobi(const int *__restrict__ row, const int *__restrict__ col, int colBase,
+                                                    const double *__restrict__ values, double *__restrict__ inv,
+                                                    int64_t nbRows, int *__restrict__ bad)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nbRows; r += stride) {
+        int k = __ldg(row + r);
+        const int k1 = __ldg(row + r + 1);
+        while (k < k1 && __ldg(col + k) - colBase != r) k++;
+        double *o = inv + r * D * D;
+        if (k == k1) {
+#pragma unroll
+            for (int q = 0; q < D * D; q++) o[q] = 0.0;
+            atomicAdd(bad, 1);
+            continue;
+        }
+        const double *a = values + (int64_t)k * D * D;
+        if (D == 1) {
+            const double v = a[0];
+            o[0] = v != 0.0 ? __drcp_rn(v) : 0.0;
+            if (v == 0.0) atomicAdd(bad, 1);
+        } else {
+            double m[9], c[9];
+#pragma unroll
+            for (int q = 0; q < 9; q++) m[q] = __ldcs(a + q);
+            c[0] = cross_comp(m[4], m[8], m[5], m[7]);
+            c[1] = cross_comp(m[5], m[6], m[3], m[8]);
+            c[2] = cross_comp(m[3], m[7], m[4], m[6]);
+            c[3] = cross_comp(m[2], m[7], m[1], m[8]);
+            c[4] = cross_comp(m[0], m[8], m[2], m[6]);
+            c[5] = cross_comp(m[1], m[6], m[0], m[7]);
+            c[6] = cross_comp(m[1], m[5], m[2], m[4]);
+            c[7] = cross_comp(m[2], m[3], m[0], m[5]);
+            c[8] = cross_comp(m[0], m[4], m[1], m[3]);
+            const double det = __fma_rn(m[2], c[2], __fma_rn(m[1], c[1], __dmul_rn(m[0], c[0])));
+            const double id = det != 0.0 ? __drcp_rn(det) : 0.0;
+            if (det == 0.0) atomicAdd(bad, 1);
+            /* inverse = adjugate / det; adjugate = transposed cofactor matrix */
+            o[0] = __dmul_rn(c[0], id); o[1] = __dmul_rn(c[3], id); o[2] = __dmul_rn(c[6], id);
+            o[3] = __dmul_rn(c[1], id); o[4] = __dmul_rn(c[4], id); o[5] = __dmul_rn(c[7], id);
+            o[6] = __dmul_rn(c[2], id); o[7] = __dmul_rn(c[5], id); o[8] = __dmul_rn(c[8], id);
+        }
+    }
+}
+
 }  // namespace dcdev
 #endif

@@ -181,6 +181,11 @@ int64_t dc_interface_edges(const int *h_row, const int *h_col, int colBase, cons
  * context's CSR pattern; x and y hold D doubles per node (dim = 1 or 3).  Fixed summation order
  * (ascending edge, then column component, one fma per entry). */
 int  dc_cuda_spmv(dc_cuda_ctx *ctx, int dim, const double *d_values, const double *d_x, double *d_y, void *stream);
+/* ... and its block-Jacobi preconditioner: d_invDiag[nbNodes][dim*dim] = inverse of the diagonal block of
+ * every row (adjugate over determinant, fixed operation order).  *nbBad (host pointer, may be NULL: then
+ * the call stays asynchronous) = rows without a diagonal entry or with a singular block (they get zeros). */
+int  dc_cuda_block_jacobi(dc_cuda_ctx *ctx, int dim, const double *d_values, double *d_invDiag, int *nbBad,
+                          void *stream);
 
 /* CSR pattern of the renumbered mesh, built on the device.  In the reference this is the user's
  * step between DC_renumber_int_array and DC_finalize_tree (the library only ships the node ->

@@ -485,3 +485,30 @@ def test_parity_at_100_cubed_metis_tree_against_the_oracle(tmp_path):
     got = _run(ctx, mesh, 3, dc.MODE_DETERMINISTIC)
     want = oracle_serial(mesh, 3)
     assert got.tobytes() == want.tobytes()
+
+
+@pytest.mark.parametrize("dim", [1, 3])
+def test_block_jacobi_of_the_assembled_matrix(tmp_path, dim):
+    """dc_cuda_block_jacobi (second half of the consumer step): the inverse of the
+    diagonal block of every row of the matrix the assembly left on the device; block * inverse = identity
+    within 1e-12 (elasticity and Laplacian diagonal blocks are well conditioned), no bad rows."""
+    import torch
+    mesh = prepare_mesh(MineLib(0), 10, tmp_path)
+    plan = dc.HostPlan(mesh["conn"], mesh["N"], mesh["row"], mesh["col"], 0, tree_records(mesh), 400)
+    ctx = dc.Context(0)
+    ctx.set_mesh(mesh["conn"], mesh["coord"], mesh["row"], mesh["col"], 0)
+    ctx.upload_plan(plan)
+    N, nnz = mesh["N"], mesh["nnz"]
+    op, prm = (dc.OP_ELASTICITY, [LAMBDA, MU]) if dim == 3 else (dc.OP_LAPLACIAN, None)
+    vals = torch.empty(nnz * dim * dim, dtype=torch.float64, device="cuda:0")
+    ctx.assemble(op, prm, dc.MODE_DETERMINISTIC, vals)
+    inv = torch.full((N * dim * dim,), float("nan"), dtype=torch.float64, device="cuda:0")
+    assert ctx.block_jacobi(dim, vals, inv) == 0
+    v = vals.cpu().numpy().reshape(nnz, dim, dim)
+    rows = np.repeat(np.arange(N), np.diff(mesh["row"]))
+    diag = v[np.flatnonzero(mesh["col"] == rows)]
+    assert diag.shape[0] == N
+    got = inv.cpu().numpy().reshape(N, dim, dim)
+    err = np.abs(np.einsum("nij,njk->nik", diag, got) - np.eye(dim)).max()
+    assert err <= 1e-12
+    ctx.close()
