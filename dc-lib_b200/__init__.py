@@ -159,6 +159,9 @@ def _declare(L):
     L.dc_get_time_.restype = c_double
     L.dc_create_tree_.argtypes = [vp, ip, ip, ip]
     L.dc_create_tree_geometric_.argtypes = [vp, ip, ip, ip, vp, ip]
+    L.dc_create_tree_device_.argtypes = [vp, ip, ip, ip]
+    L.dc_device_select_.argtypes = [ip]
+    L.dc_create_tree_geometric_device_.argtypes = [vp, ip, ip, ip, vp, ip]
     L.dc_partition_mesh_.argtypes = [vp, ip, ip, ip, ip, vp, ip, vp]
     L.dc_finalize_tree_.argtypes = [vp, vp, vp, vp, vp, vp, ip, ip, ip, ip, ip]
     L.dc_store_tree_.argtypes = [c_char_p, ip, ip, ip, ip]
@@ -220,6 +223,26 @@ def DC_create_tree_geometric(elemToNode, nbElem, dimElem, nbNodes, coord):
     assert elemToNode.dtype == np.int32 and elemToNode.flags.c_contiguous
     assert coord.dtype == np.float64 and coord.flags.c_contiguous
     lib().dc_create_tree_geometric_(_p(elemToNode), _i(nbElem), _i(dimElem), _i(nbNodes), _p(coord), _i(coord.shape[1]))
+
+
+def DC_device_select(device):
+    """CUDA device of DC_create_tree_device / DC_create_tree_geometric_device (include/DC_device.h)."""
+    lib().dc_device_select_(_i(device))
+
+
+def DC_create_tree_device(elemToNode, nbElem, dimElem, nbNodes):
+    """DC_create_tree with the level-wise element passes of the tree proper on the GPU
+    (include/DC_device.h); same bytes as DC_create_tree."""
+    assert elemToNode.dtype == np.int32 and elemToNode.flags.c_contiguous
+    lib().dc_create_tree_device_(_p(elemToNode), _i(nbElem), _i(dimElem), _i(nbNodes))
+
+
+def DC_create_tree_geometric_device(elemToNode, nbElem, dimElem, nbNodes, coord):
+    """DC_create_tree_geometric with the element passes of the tree proper on the GPU."""
+    assert elemToNode.dtype == np.int32 and elemToNode.flags.c_contiguous
+    assert coord.dtype == np.float64 and coord.flags.c_contiguous
+    lib().dc_create_tree_geometric_device_(_p(elemToNode), _i(nbElem), _i(dimElem), _i(nbNodes), _p(coord),
+                                           _i(coord.shape[1]))
 
 
 def DC_partition_mesh(elemToNode, nbNodes, nbPart, coord=None):

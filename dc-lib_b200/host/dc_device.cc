@@ -74,6 +74,23 @@ void DC_device_init (int device)
     g_device = device;
 }
 
+void DC_device_select (int device) { g_device = device; }
+
+/* DC_create_tree with the element passes of the tree proper on the device (dc_cuda_tree_*): same
+ * contract and the same bytes (connectivity, elemPerm, nodePerm, tree) as the host entry points.
+ * Runs on the device of DC_device_init / DC_device_select (device 0 before the first call of either). */
+void DC_create_tree_device (int *elemToNode, int nbElem, int dimElem, int nbNodes)
+{
+    dc::create_tree_impl(elemToNode, nbElem, dimElem, nbNodes, nullptr, 3, g_device);
+}
+
+void DC_create_tree_geometric_device (int *elemToNode, int nbElem, int dimElem, int nbNodes,
+                                      const double *coord, int dimNode)
+{
+    if (!coord) dc::fatal("Error: DC_create_tree_geometric_device needs node coordinates.");
+    dc::create_tree_impl(elemToNode, nbElem, dimElem, nbNodes, coord, dimNode, g_device);
+}
+
 void DC_device_set_interface (int nbIntf, const int *neighbourRank, const int *intfIndex, const int *intfNodes)
 {
     g_intfRank.assign(neighbourRank, neighbourRank + nbIntf);
@@ -227,6 +244,16 @@ void DC_device_finalize ()
 
 extern "C" {
 void dc_device_init_ (int *device) { DC_device_init(*device); }
+void dc_device_select_ (int *device) { DC_device_select(*device); }
+void dc_create_tree_device_ (int *elemToNode, int *nbElem, int *dimElem, int *nbNodes)
+{
+    DC_create_tree_device(elemToNode, *nbElem, *dimElem, *nbNodes);
+}
+void dc_create_tree_geometric_device_ (int *elemToNode, int *nbElem, int *dimElem, int *nbNodes,
+                                       const double *coord, int *dimNode)
+{
+    DC_create_tree_geometric_device(elemToNode, *nbElem, *dimElem, *nbNodes, coord, *dimNode);
+}
 void dc_device_set_mesh_ (const double *coord, const int *elemToNode, const int *nodeToNodeRow,
                           const int *nodeToNodeColumn, int *nbElem, int *nbNodes, int *colBase)
 {

@@ -38,6 +38,11 @@ void scatter_rows_inplace(T *tab, const int *perm, int64_t nbItem, int dimItem);
 void color_leaves(int *elemToNode, int nbElem, int dimElem, int nbNodes, int vecSize,
                   int *posToOrig);
 
+/* DC_create_tree / DC_create_tree_geometric (coord != nullptr); device >= 0: the element passes of
+ * the tree proper run on that CUDA device (dc_tree.cc) */
+void create_tree_impl(int *elemToNode, int nbElem, int dimElem, int nbNodes, const double *coord,
+                      int dimNode, int device);
+
 /* tree helpers */
 void free_subtree(tree_t *t);
 tree_t *new_tree_node(int firstElem, int lastElem, int nbSepElem, int firstNode,

@@ -23,6 +23,7 @@
 #include <algorithm>
 #include <omp.h>
 #include "dc_internal.h"
+#include "dc_cuda.h"
 
 tree_t *treeHead = nullptr;
 int *elemPerm = nullptr, *nodePerm = nullptr;
@@ -369,13 +370,85 @@ void TreeBuilder::sep_partitioning(tree_t *&tree, int firstSepElem, int lastSepE
                   firstSepElem, lastSepElem, firstNode, lastNode, 0, true);
 }
 
-}  // namespace dc
+/* The tree proper (every node that is not inside a separator subtree) level by level, the element
+ * passes of a level on the device (dc_cuda_tree_*, csrc/dc_cuda_tree.cu): what tree_creation() does
+ * for isSep = false, with the recursion turned into a breadth-first loop so that one device pass
+ * serves every tree node of a level.  The bookkeeping (tree nodes, part ranges, node ranges, the leaf
+ * rule, the all-straddling guard) is the recursion's, line for line; the separator ranges are
+ * collected and built afterwards on the host, concurrently (they are disjoint element ranges).
+ * reference: tree_creation.cc:379-479 */
+struct SplitSeg { tree_t **slot; int firstPart, lastPart, firstElem, lastElem, firstNode, lastNode; };
+struct SepJob { tree_t **slot; int firstElem, lastElem, firstNode, lastNode; };
 
-/* reference: tree_creation.cc:482-501 + partitioning.cc:167-228 */
-static void create_tree_impl(int *elemToNode, int nbElem, int dimElem, int nbNodes, const double *coord,
-                             int dimNode)
+static void main_tree_on_device(TreeBuilder &b, int device, int nbElem, int nbNodes, const int *nodePart,
+                                const int *nodePartSize, int nbPart, std::vector<SepJob> &jobs, int64_t *launches)
 {
-    using namespace dc;
+    auto is_leaf = [&](int parts, int n) { return parts < 2 || n <= b.maxElem; };
+    if (is_leaf(nbPart, nbElem)) {
+        treeHead = new_tree_node(0, nbElem - 1, 0, 0, nbNodes - 1, false, true);
+        return;
+    }
+    std::vector<int64_t> partPrefix((size_t)nbPart + 1, 0);        /* nodes in parts [0, p) */
+    for (int p = 0; p < nbPart; p++) partPrefix[(size_t)p + 1] = partPrefix[(size_t)p] + nodePartSize[p];
+    auto check = [&](int rc, const char *what) {
+        if (rc == 0) return;
+        fprintf(stderr, "Error: %s (%s)\n", what, dc_cuda_tree_last_error());
+        exit(EXIT_FAILURE);
+    };
+    dc_cuda_tree *t = nullptr;
+    check(dc_cuda_tree_begin(&t, device, b.conn, nbElem, b.dimElem, nodePart, nbNodes), "DC_create_tree on the device: begin");
+    std::vector<SplitSeg> cur{SplitSeg{&treeHead, 0, nbPart - 1, 0, nbElem - 1, 0, nbNodes - 1}}, next;
+    std::vector<int> segFirst, segEnd, pivot, totals, child;
+    while (!cur.empty()) {
+        const size_t ns = cur.size();
+        segFirst.resize(ns); segEnd.resize(ns); pivot.resize(ns); totals.resize(3 * ns); child.assign(3 * ns, -1);
+        for (size_t s = 0; s < ns; s++) {
+            segFirst[s] = cur[s].firstElem;
+            segEnd[s] = cur[s].lastElem + 1;
+            pivot[s] = cur[s].firstPart + (cur[s].lastPart - cur[s].firstPart) / 2;
+        }
+        check(dc_cuda_tree_classify(t, (int)ns, segFirst.data(), segEnd.data(), pivot.data(), totals.data()),
+              "DC_create_tree on the device: classify");
+        next.clear();
+        for (size_t s = 0; s < ns; s++) {
+            const SplitSeg g = cur[s];
+            const int n = g.lastElem - g.firstElem + 1;
+            const int nbLeft = totals[3 * s], nbSep = totals[3 * s + 2];
+            if (nbSep == n) {                         /* every element straddles the cut: stays one leaf */
+                *g.slot = new_tree_node(g.firstElem, g.lastElem, 0, g.firstNode, g.lastNode, false, true);
+                continue;
+            }
+            const int nbLeftNodes = (int)(partPrefix[(size_t)pivot[s] + 1] - partPrefix[(size_t)g.firstPart]);
+            const int nbRightNodes = (g.lastNode - g.firstNode + 1) - nbLeftNodes;
+            tree_t *node = new_tree_node(g.firstElem, g.lastElem, nbSep, g.firstNode, g.lastNode, false, false);
+            *g.slot = node;
+            const SplitSeg kids[2] = {
+                SplitSeg{&node->left, g.firstPart, pivot[s], g.firstElem, g.firstElem + nbLeft - 1, g.firstNode,
+                         g.lastNode - nbRightNodes},
+                SplitSeg{&node->right, pivot[s] + 1, g.lastPart, g.firstElem + nbLeft, g.lastElem - nbSep,
+                         g.firstNode + nbLeftNodes, g.lastNode}};
+            for (int k = 0; k < 2; k++) {
+                const SplitSeg &c = kids[k];
+                if (is_leaf(c.lastPart - c.firstPart + 1, c.lastElem - c.firstElem + 1)) {
+                    *c.slot = new_tree_node(c.firstElem, c.lastElem, 0, c.firstNode, c.lastNode, false, true);
+                } else {
+                    child[3 * s + (size_t)k] = (int)next.size();
+                    next.push_back(c);
+                }
+            }
+            if (nbSep > 0) jobs.push_back(SepJob{&node->sep, g.lastElem - nbSep + 1, g.lastElem, g.firstNode, g.lastNode});
+        }
+        check(dc_cuda_tree_scatter(t, child.data()), "DC_create_tree on the device: scatter");
+        cur.swap(next);
+    }
+    check(dc_cuda_tree_end(t, b.conn, b.posToOrig, launches), "DC_create_tree on the device: copy back");
+}
+
+/* reference: tree_creation.cc:482-501 + partitioning.cc:167-228.  device >= 0: the element passes of
+ * the tree proper run on that CUDA device (DC_create_tree_device, DC_device.h). */
+void create_tree_impl(int *elemToNode, int nbElem, int dimElem, int nbNodes, const double *coord,
+                      int dimNode, int device)
+{
     DC_free_tree();
     elemPerm = new int[nbElem > 0 ? nbElem : 1];
     nodePerm = new int[nbNodes > 0 ? nbNodes : 1];
@@ -417,12 +490,35 @@ static void create_tree_impl(int *elemToNode, int nbElem, int dimElem, int nbNod
     std::vector<int> nodePartSize((size_t)(nbPart > 0 ? nbPart : 1), 0);
     for (int i = 0; i < nbNodes; i++) nodePartSize[nodePart[i]]++;
 
-    #pragma omp parallel num_threads(nt)
-    #pragma omp single
-    b.tree_creation(treeHead, nullptr, nodePart.data(), nodePartSize.data(), 0, nbPart - 1, 0,
-                    nbElem - 1, 0, nbNodes - 1, 0, false);
-
-    lap("recursion");
+    if (device >= 0) {
+        std::vector<SepJob> jobs;
+        int64_t launches = 0;
+        main_tree_on_device(b, device, nbElem, nbNodes, nodePart.data(), nodePartSize.data(), nbPart, jobs, &launches);
+        lap("device split");
+        if (verbose) fprintf(stderr, "[dc_tree] %zu separator subtrees, %lld kernel launches\n", jobs.size(), (long long)launches);
+        /* separator subtrees: disjoint element ranges, built concurrently */
+        #pragma omp parallel num_threads(nt)
+        #pragma omp single
+        {
+            for (size_t j = 0; j < jobs.size(); j++) {
+                const SepJob job = jobs[j];
+                if (job.lastElem - job.firstElem + 1 <= maxElem) {
+                    b.sep_partitioning(*job.slot, job.firstElem, job.lastElem, job.firstNode, job.lastNode);
+                } else {
+                    #pragma omp task default(shared) firstprivate(job)
+                    b.sep_partitioning(*job.slot, job.firstElem, job.lastElem, job.firstNode, job.lastNode);
+                }
+            }
+            #pragma omp taskwait
+        }
+        lap("separators");
+    } else {
+        #pragma omp parallel num_threads(nt)
+        #pragma omp single
+        b.tree_creation(treeHead, nullptr, nodePart.data(), nodePartSize.data(), 0, nbPart - 1, 0,
+                        nbElem - 1, 0, nbNodes - 1, 0, false);
+        lap("recursion");
+    }
     #pragma omp parallel for schedule(static) if (nbConn > (1 << 16))
     for (int64_t k = 0; k < nbConn; k++) elemToNode[k]++;
 
@@ -433,9 +529,11 @@ static void create_tree_impl(int *elemToNode, int nbElem, int dimElem, int nbNod
     for (int pos = 0; pos < nbElem; pos++) elemPerm[posToOrig[pos]] = pos;
 }
 
+}  // namespace dc
+
 void DC_create_tree (int *elemToNode, int nbElem, int dimElem, int nbNodes)
 {
-    create_tree_impl(elemToNode, nbElem, dimElem, nbNodes, nullptr, 3);
+    dc::create_tree_impl(elemToNode, nbElem, dimElem, nbNodes, nullptr, 3, -1);
 }
 
 /* Same contract as DC_create_tree, with the node partitions cut by recursive coordinate
@@ -445,7 +543,7 @@ void DC_create_tree_geometric (int *elemToNode, int nbElem, int dimElem, int nbN
                                const double *coord, int dimNode)
 {
     if (!coord) dc::fatal("Error: DC_create_tree_geometric needs node coordinates.");
-    create_tree_impl(elemToNode, nbElem, dimElem, nbNodes, coord, dimNode);
+    dc::create_tree_impl(elemToNode, nbElem, dimElem, nbNodes, coord, dimNode, -1);
 }
 
 /* reference: tree_creation.cc:176-239 (BULK_SYNCHRONOUS, no STATS): every leaf,

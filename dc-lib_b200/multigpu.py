@@ -10,7 +10,7 @@ dc_cuda_unpack_add_edges.
 """
 import numpy as np
 
-from . import (DC_create_tree, DC_create_tree_geometric, DC_finalize_tree, DC_partition_mesh, DC_permute_double_2d_array,
+from . import (DC_create_tree, DC_create_tree_device, DC_create_tree_geometric, DC_create_tree_geometric_device, DC_device_select, DC_finalize_tree, DC_partition_mesh, DC_permute_double_2d_array,
                DC_renumber_int_array, DC_set_num_threads, DC_set_vec_size, build_csr_fast, flatten_tree, get_node_perm,
                kuhn_cube_fast, pack_edges, unpack_add_edges)
 
@@ -40,6 +40,18 @@ def plane_edges(node_perm, row, col, n, side):
     return np.ascontiguousarray(idx[keep][np.argsort(key, kind="stable")], dtype=np.int64)
 
 
+def _create_tree(conn, E, N, coord, builder, device):
+    """DC_create_tree / DC_create_tree_geometric; with a CUDA device the element passes of the tree
+    proper run there (DC_create_tree_device, include/DC_device.h) -- same bytes either way."""
+    if device is not None:
+        import torch
+        DC_device_select(torch.device(device).index or 0)
+    if builder == "geometric":
+        (DC_create_tree_geometric_device if device is not None else DC_create_tree_geometric)(conn, E, 4, N, coord)
+    else:
+        (DC_create_tree_device if device is not None else DC_create_tree)(conn, E, 4, N)
+
+
 def build_slab(n, rank, world, builder="geometric", vec=0, seed=12345, csr_device=None):
     """Appendix-A driver for slab `rank` of a bar of `world` jittered Kuhn cubes stacked along x.
     Returns the user-side arrays, the flattened tree and, per neighbour, the local CSR edges
@@ -47,10 +59,7 @@ def build_slab(n, rank, world, builder="geometric", vec=0, seed=12345, csr_devic
     conn, coord, N = kuhn_cube_fast(n, seed=seed, x_offset=rank * n)
     E = conn.shape[0]
     DC_set_vec_size(vec)
-    if builder == "geometric":
-        DC_create_tree_geometric(conn, E, 4, N, coord)
-    else:
-        DC_create_tree(conn, E, 4, N)
+    _create_tree(conn, E, N, coord, builder, csr_device)
     node_perm = get_node_perm(N)
     DC_permute_double_2d_array(coord, N, 3)
     DC_renumber_int_array(conn.reshape(-1), 4 * E)
@@ -113,10 +122,7 @@ def build_part(conn_g, coord_g, elem_part, rank, world, builder="metis", vec=0, 
     coord = np.ascontiguousarray(coord_g[nodes])
     E, N = conn.shape[0], nodes.shape[0]
     DC_set_vec_size(vec)
-    if builder == "geometric":
-        DC_create_tree_geometric(conn, E, 4, N, coord)
-    else:
-        DC_create_tree(conn, E, 4, N)
+    _create_tree(conn, E, N, coord, builder, csr_device)
     node_perm = get_node_perm(N)
     DC_permute_double_2d_array(coord, N, 3)
     DC_renumber_int_array(conn.reshape(-1), 4 * E)

@@ -27,6 +27,17 @@
 
 /* Select the CUDA device and create the library's device context. */
 void DC_device_init (int device);
+/* DC_create_tree (METIS node partition on the host, include/DC.h) and DC_create_tree_geometric with the
+ * level-wise element passes of the tree proper -- create_elem_part, the stable 3-way order and the row
+ * permutation of every tree node, src/tree_creation.cc:352-375, 415-430 -- on the device
+ * (dc_cuda_tree_*, include/dc_cuda.h); separator subtrees and the node partition stay on the host.
+ * Same contract, same bytes: connectivity order, elemPerm, nodePerm and tree equal the host builders'.
+ * They run on the device of DC_device_init, or of DC_device_select when the tree is created before the
+ * device context exists (device 0 by default). */
+void DC_device_select (int device);
+void DC_create_tree_device (int *elemToNode, int nbElem, int dimElem, int nbNodes);
+void DC_create_tree_geometric_device (int *elemToNode, int nbElem, int dimElem, int nbNodes,
+                                      const double *coord, int dimNode);
 /* Upload mesh + CSR pattern and flatten the finalized tree into the device schedule.
  * elemToNode: 1-based, tree order, renumbered; coord: [nbNodes][3] permuted;
  * nodeToNodeColumn numbering base colBase (0 or 1). */
@@ -72,6 +83,10 @@ void DC_device_exchange_connect (int intf, const void *handle128);
 
 extern "C" {
     void dc_device_init_ (int *device);
+    void dc_device_select_ (int *device);
+    void dc_create_tree_device_ (int *elemToNode, int *nbElem, int *dimElem, int *nbNodes);
+    void dc_create_tree_geometric_device_ (int *elemToNode, int *nbElem, int *dimElem, int *nbNodes,
+                                           const double *coord, int *dimNode);
     void dc_device_set_mesh_ (const double *coord, const int *elemToNode, const int *nodeToNodeRow,
                               const int *nodeToNodeColumn, int *nbElem, int *nbNodes, int *colBase);
     void dc_device_update_coords_ (const double *coord);

@@ -202,6 +202,31 @@ int  dc_cuda_csr_columns(dc_cuda_csr *handle, int *d_col, int colBase, void *str
 int  dc_cuda_csr_node_to_elem(dc_cuda_csr *handle, int64_t *d_ptr, int *d_val, void *stream);
 void dc_cuda_csr_end(dc_cuda_csr *handle);
 
+/* The level-wise element split of DC_create_tree on the device ("GPU-assisted
+ * create_elem_part / 3-way stable partition / permute per level; METIS stays host").  At every node of
+ * the tree the reference classes the node's elements by the partition of their nodes -- all left of the
+ * pivot part, all right, straddling = separator (create_elem_part, src/tree_creation.cc:352-375) --
+ * orders them stably by class (DC_create_permutation, src/permutations.cc:169-180) and moves the
+ * connectivity rows (DC_permute_int_2d_array, :51-80; merge into elemPerm, :118-130).  Here one LEVEL
+ * of the tree proper is one pass over all elements on the device; the caller keeps the recursion's
+ * bookkeeping (tree nodes, part and node ranges) and builds the separator subtrees on the host.
+ *   begin     h_conn [nbElem][dimElem] 0-BASED node ids in the current element order, h_nodePart[nbNodes]
+ *             the node partition (METIS or coordinate bisection); every element starts in segment 0
+ *   classify  segments of the level = disjoint position ranges [h_segFirst[s], h_segEnd[s]) with pivot part
+ *             h_pivot[s]; returns h_totals[3 s + {0, 1, 2}] = elements left / right / straddling
+ *   scatter   moves rows (stable inside a class: left, right, separator) and numbers the elements for the
+ *             next level: h_child[3 s + k] = next segment of class k of segment s, -1 = not split further
+ *   end       copies rows and the position -> original element map back (either may be NULL), frees
+ * Rows and map equal the host builder's byte for byte (tests/test_gpu_tree_device.py). */
+typedef struct dc_cuda_tree dc_cuda_tree;
+int  dc_cuda_tree_begin(dc_cuda_tree **handle, int device, const int *h_conn, int nbElem, int dimElem,
+                        const int *h_nodePart, int nbNodes);
+int  dc_cuda_tree_classify(dc_cuda_tree *handle, int nbSeg, const int *h_segFirst, const int *h_segEnd,
+                           const int *h_pivot, int *h_totals);
+int  dc_cuda_tree_scatter(dc_cuda_tree *handle, const int *h_child);
+int  dc_cuda_tree_end(dc_cuda_tree *handle, int *h_conn, int *h_posToOrig, int64_t *launches);
+const char *dc_cuda_tree_last_error(void);
+
 /* Tuning knobs: "unit_threads" = CTA size of the unit kernel (128, 256 or 512; default 256);
  * "persistent" = 1 (default): SMs x resident CTAs stride over the units and prefetch the next
  * unit's inputs, 0: one CTA per unit; "exchange_reserve" = CTA slots dc_cuda_assemble_exchange leaves

@@ -168,17 +168,18 @@ class RefLib:
 class MineLib:
     """Same driver surface over the product's host library."""
 
-    def __init__(self, vec=0, geometric=False):
+    def __init__(self, vec=0, geometric=False, device=False):
         self.vec = vec
         self.geometric = geometric
+        self.device = device          # element passes of the tree proper on the GPU (DC_device.h)
         dc.DC_set_vec_size(vec)
 
     def create_tree(self, conn, E, N, coord=None):
         dc.DC_set_vec_size(self.vec)
         if self.geometric:
-            dc.DC_create_tree_geometric(conn, E, 4, N, coord)
+            (dc.DC_create_tree_geometric_device if self.device else dc.DC_create_tree_geometric)(conn, E, 4, N, coord)
         else:
-            dc.DC_create_tree(conn, E, 4, N)
+            (dc.DC_create_tree_device if self.device else dc.DC_create_tree)(conn, E, 4, N)
 
     def permute_double_2d(self, tab, n, dim):
         dc.DC_permute_double_2d_array(tab, n, dim)
