@@ -192,7 +192,19 @@ def setup_device_parts(n, rank, world, device, slots=512, dist=None, seed=2024, 
     if world > 1:
         part_t = torch.empty(conn_g.shape[0], dtype=torch.int32, device=device)
         if rank == 0:
-            part = DC_partition_mesh(conn_g, n_glob, world, coord_g if partition == "geometric" else None)
+            # DC_PARTITION_CACHE=<dir>: the element partition (a host-only step: METIS on the nodal graph)
+            # is kept there per (mesh, parts), so that a run on GPUs does not leave them idle behind it
+            import os
+            cache = os.environ.get("DC_PARTITION_CACHE")
+            path = os.path.join(cache, f"c4_part_n{n}_w{world}_{partition}_s{seed}.npy") if cache else None
+            if path and os.path.exists(path):
+                part = np.load(path).astype(np.int32)
+                assert part.shape[0] == conn_g.shape[0]
+            else:
+                part = DC_partition_mesh(conn_g, n_glob, world, coord_g if partition == "geometric" else None)
+                if path:
+                    os.makedirs(cache, exist_ok=True)
+                    np.save(path, part.astype(np.int8))
             part_t.copy_(torch.from_numpy(part))
         dist.broadcast(part_t, src=0)
         part = part_t.cpu().numpy()
