@@ -258,6 +258,8 @@ def main():
     ctx.set_option("persistent", args.persistent)
     if "DC_BENCH_RESERVE" in os.environ:
         ctx.set_option("exchange_reserve", int(os.environ["DC_BENCH_RESERVE"]))
+    if "DC_BENCH_PACK_EARLY" in os.environ:
+        ctx.set_option("exchange_pack_early", int(os.environ["DC_BENCH_PACK_EARLY"]))
     E, N, nnz, st = info["E"], info["N"], info["nnz"], info["stats"]
     op, prm = (dc.OP_ELASTICITY, [LAMBDA, MU]) if dim == 3 else (dc.OP_LAPLACIAN, None)
     per = dim * dim
@@ -309,6 +311,30 @@ def main():
     k1.record()
     torch.cuda.synchronize()
     kernel_ms = k0.elapsed_time(k1) / args.steps
+    # DC_BENCH_EXCHANGE_SWEEP=1 (several GPUs): the step timed again for every placement of the pack
+    # (beside the interior units / before them) and a few sizes of the CTA reserve -- the evidence behind
+    # the defaults of dc_cuda_assemble_exchange; the options are restored afterwards
+    sweep = None
+    if exch and overlap and os.environ.get("DC_BENCH_EXCHANGE_SWEEP"):
+        sweep = {}
+        for early in (0, 1):
+            for reserve in (4, 16, 48):
+                ctx.set_option("exchange_pack_early", early)
+                ctx.set_option("exchange_reserve", reserve)
+                for _ in range(2):
+                    step()
+                barrier()
+                s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s0.record()
+                for _ in range(args.steps):
+                    step()
+                s1.record()
+                barrier()
+                t = torch.tensor([s0.elapsed_time(s1) / args.steps], dtype=torch.float64, device=device)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                sweep[f"pack_early={early},reserve={reserve}"] = round(float(t[0]), 4)
+        ctx.set_option("exchange_pack_early", int(os.environ.get("DC_BENCH_PACK_EARLY", "-1")))
+        ctx.set_option("exchange_reserve", int(os.environ.get("DC_BENCH_RESERVE", "4")))
     sampler.stop_flag = True
     sampler.join()
 
@@ -413,6 +439,8 @@ def main():
             line["setup"]["partition_s"] = info.get("partition_s")
             line["setup"]["mesh_s"] = info.get("mesh_s")
         line["interface_bytes_per_step_per_gpu"] = exch.bytes_per_step
+        if sweep:
+            line["exchange_sweep_ms_per_step"] = sweep
     if not args.no_cpu_baseline and world == 1:      # the CPU arm is reported at N = 1 only
         base = cpu_reference(dim, 3, 1, leaf_nodes=args.leaf_nodes)
         base.pop("ms_per_step")

@@ -64,6 +64,7 @@ struct dc_cuda_ctx {
     /* multi-GPU step (dc_cuda_assemble_exchange): units that own interface rows come first in d_units */
     int64_t nbFrontUnits = 0;
     int exchangeReserve = 4;             /* CTA slots the interior launch leaves to the pack / unpack kernels */
+    int exchangePackEarly = -1;          /* 1: pack before the interior launch, 0: beside it, -1: by the byte / element ratio */
     cudaStream_t sideStream = nullptr;
     cudaEvent_t evFront = nullptr, evJoin = nullptr;
 };
@@ -399,14 +400,27 @@ extern "C" int dc_cuda_assemble_exchange_with(dc_cuda_ctx *c, dc_cuda_exchange *
     }
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t front = c->nbFrontUnits > 0 ? c->nbFrontUnits : c->nbUnits;
+    /* Where the pack runs.  Beside the interior units it only has the few CTA slots the persistent grid
+     * leaves free (`exchange_reserve`), where a gather is latency-bound (about 10 GB/s per slot): fine when
+     * the interior takes long -- weak scaling, 0.2-0.3 bytes sent per interior element, the exchange then
+     * costs 0.2 % of the step -- but with many neighbours and a short interior (one mesh cut over 8 GPUs:
+     * 4 bytes per interior element) the pack would end after the interior and the neighbours' unpack wait
+     * for it.  Then it runs BEFORE the interior launch on the whole GPU (tens of microseconds) and only
+     * the unpack stays beside the interior units. */
+    bool early = c->exchangePackEarly > 0;
+    if (c->exchangePackEarly < 0) {
+        const double interiorElems = (double)c->nbElem * (double)(c->nbUnits - front) / (double)(c->nbUnits > 0 ? c->nbUnits : 1);
+        early = (double)dc_cuda_exchange_bytes(x) * 0.5 > 1.0 * interiorElems;
+    }
     dc_launch_args a;
     fill_args(c, DC_MODE_DETERMINISTIC, &a);
     a.unitFirst = 0; a.unitCount = front;
     int rc = launcher(&a, h_params, nbParams, d_values, stream);
     c->launches += a.launches;
     if (rc) return explain(rc);
+    if (early && dc_cuda_exchange_pack(x, d_values, s)) return fail(-15, dc_cuda_exchange_last_error());
     CK(cudaEventRecord(c->evFront, s));
-    if (front < c->nbUnits) {            /* enqueued BEFORE the pack: see above */
+    if (front < c->nbUnits) {            /* enqueued BEFORE a pack on the side stream: see above */
         fill_args(c, DC_MODE_DETERMINISTIC, &a);
         a.unitFirst = front; a.unitCount = c->nbUnits - front;
         a.reserveCtas = c->exchangeReserve; a.skipBigRows = 1;
@@ -415,7 +429,7 @@ extern "C" int dc_cuda_assemble_exchange_with(dc_cuda_ctx *c, dc_cuda_exchange *
         if (rc) return explain(rc);
     }
     CK(cudaStreamWaitEvent(c->sideStream, c->evFront, 0));
-    if (dc_cuda_exchange_pack(x, d_values, c->sideStream)) return fail(-15, dc_cuda_exchange_last_error());
+    if (!early && dc_cuda_exchange_pack(x, d_values, c->sideStream)) return fail(-15, dc_cuda_exchange_last_error());
     if (dc_cuda_exchange_unpack(x, d_values, c->sideStream)) return fail(-15, dc_cuda_exchange_last_error());
     c->launches += 2 * dc_cuda_exchange_neighbours(x);
     CK(cudaEventRecord(c->evJoin, c->sideStream));
@@ -750,6 +764,11 @@ extern "C" int dc_cuda_set_option(dc_cuda_ctx *c, const char *name, int value)
         if (value != 128 && value != 256 && value != 512)
             return fail(-12, "dc_cuda_set_option: unit_threads must be 128, 256 or 512");
         c->threads = value;
+        return 0;
+    }
+    if (!strcmp(name, "exchange_pack_early")) {
+        if (value < -1 || value > 1) return fail(-12, "dc_cuda_set_option: exchange_pack_early must be -1 (auto), 0 or 1");
+        c->exchangePackEarly = value;
         return 0;
     }
     if (!strcmp(name, "exchange_reserve")) {

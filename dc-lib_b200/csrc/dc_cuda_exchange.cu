@@ -75,6 +75,8 @@ __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned l
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+constexpr int XCH_ILP = 8;     /* words in flight per thread */
+
 /* buf[k][:] = values[edge[k]][:] into the NEIGHBOUR's receive buffer; the block that finishes last
  * raises the neighbour's flag (every block fences its stores system-wide before it counts itself
  * done, so the flag is raised after all of them) */
@@ -83,10 +85,10 @@ __global__ void __launch_bounds__(256) push_edges(const double *__restrict__ val
                                                   unsigned long long *flag, unsigned long long stamp, unsigned int *done)
 {
     const int64_t total = nbEdges * perEdge, stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t w0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w0 < total; w0 += 4 * stride) {
-        double v[4];
+    for (int64_t w0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w0 < total; w0 += XCH_ILP * stride) {
+        double v[XCH_ILP];
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
+        for (int q = 0; q < XCH_ILP; q++) {
             const int64_t w = w0 + q * stride;
             if (w < total) {
                 const int64_t k = w / perEdge;
@@ -94,7 +96,7 @@ __global__ void __launch_bounds__(256) push_edges(const double *__restrict__ val
             }
         }
 #pragma unroll
-        for (int q = 0; q < 4; q++)
+        for (int q = 0; q < XCH_ILP; q++)
             if (w0 + q * stride < total) buf[w0 + q * stride] = v[q];
     }
     __threadfence_system();
@@ -117,13 +119,13 @@ __global__ void __launch_bounds__(256) wait_add_edges(double *__restrict__ value
         while (ld_acquire_sys(flag) < stamp) __nanosleep(64);
     __syncthreads();
     const int64_t total = nbEdges * perEdge, stride = (int64_t)gridDim.x * blockDim.x;
-    /* four independent words per thread and trip: the kernel often runs on the few CTA slots the
+    /* XCH_ILP independent words per thread and trip: the kernel often runs on the few CTA slots the
      * persistent assembly grid leaves free, where only memory-level parallelism hides the latency */
-    for (int64_t w0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w0 < total; w0 += 4 * stride) {
-        double *dst[4];
-        double add[4], old[4];
+    for (int64_t w0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w0 < total; w0 += XCH_ILP * stride) {
+        double *dst[XCH_ILP];
+        double add[XCH_ILP], old[XCH_ILP];
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
+        for (int q = 0; q < XCH_ILP; q++) {
             const int64_t w = w0 + q * stride;
             dst[q] = nullptr;
             if (w < total) {
@@ -134,7 +136,7 @@ __global__ void __launch_bounds__(256) wait_add_edges(double *__restrict__ value
             }
         }
 #pragma unroll
-        for (int q = 0; q < 4; q++)
+        for (int q = 0; q < XCH_ILP; q++)
             if (dst[q]) *dst[q] = __dadd_rn(old[q], add[q]);
     }
 }

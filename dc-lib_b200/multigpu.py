@@ -268,6 +268,9 @@ class InterfaceExchange:
         if not self.nbs:
             return
         dist = self.dist
+        if self.on_gpu and stream is None:
+            # NCCL orders its send / recv against torch's CURRENT stream: pack and unpack-add must run there too
+            stream = self.torch.cuda.current_stream().cuda_stream
         ops = []
         for nb in self.nbs:
             self._pack(values, nb, stream)

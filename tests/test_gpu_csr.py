@@ -10,9 +10,20 @@ from common import MineLib, prepare_mesh
 pytestmark = pytest.mark.gpu
 
 
+def _numpy_csr(conn, N, colBase):
+    """Independent restatement: edge (i, j) iff an element holds both nodes (diagonal included),
+    columns ascending inside a row -- the 16 node pairs of every element, sorted and made unique."""
+    c = conn.astype(np.int64) - 1
+    key = np.unique((np.repeat(c, 4, axis=1) * N + np.tile(c, (1, 4))).reshape(-1))
+    row = np.concatenate(([0], np.cumsum(np.bincount(key // N, minlength=N)))).astype(np.int32)
+    return row, (key % N + colBase).astype(np.int32)
+
+
 def _check(conn, N, colBase):
     import torch
     want_row, want_col = dc.build_csr(conn, N, colBase) if conn.shape[0] < 20000 else dc.build_csr_fast(conn, N, colBase)
+    np_row, np_col = _numpy_csr(conn, N, colBase)            # the checker of both builders
+    assert np.array_equal(want_row, np_row) and np.array_equal(want_col, np_col)
     d_conn = torch.from_numpy(conn).cuda()
     row, col, ptr, val = dc.build_csr_device(d_conn, N, colBase, node_to_elem=True)
     assert np.array_equal(row.cpu().numpy(), want_row)

@@ -1,6 +1,6 @@
 """Per-phase cycle counts of gather_units (clock64 stamps, debug hook dc_cuda_debug_phases): thread 0's
 phases and the end of the tasks of every warp, on the bench geometry.
-usage: python tools/phase_times.py <cube> <slots> <threads> [leaf_nodes=62]"""
+usage: python tools/phase_times.py <cube> <slots> <threads> [leaf_nodes=62] [op=elasticity|laplacian]"""
 import sys, os, ctypes
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -9,17 +9,19 @@ import dc_lib_b200 as dc
 import bench
 n = int(sys.argv[1]); slots = int(sys.argv[2]); threads = int(sys.argv[3])
 leaf_nodes = int(sys.argv[4]) if len(sys.argv) > 4 else 62
-dc.DC_set_max_elem_per_part(bench.leaf_capacity(n, leaf_nodes))
+lap = len(sys.argv) > 5 and sys.argv[5].startswith("lap")
+dc.DC_set_max_elem_per_part(bench.leaf_capacity(n, leaf_nodes) if leaf_nodes > 0 else 200)
 w = bench.build_workload(dc, n, 0, "geometric")
-plan = dc.HostPlan(w["conn"], w["N"], w["row"], w["col"], 0, w["rec"], slots)
+plan = dc.HostPlan(w["conn"], w["N"], w["row"], w["col"], 0, w["rec"], slots, bank_model=1 if lap else 0)
 ctx = dc.Context(0); ctx.set_mesh(w["conn"], w["coord"], w["row"], w["col"], 0); ctx.upload_plan(plan)
 ctx.set_option("unit_threads", threads)
-vals = torch.empty(w["nnz"] * 9, dtype=torch.float64, device="cuda")
-prm = [bench.LAMBDA, bench.MU]
-for _ in range(3): ctx.assemble(dc.OP_ELASTICITY, prm, dc.MODE_DETERMINISTIC, vals)
+vals = torch.empty(w["nnz"] * (1 if lap else 9), dtype=torch.float64, device="cuda")
+prm = None if lap else [bench.LAMBDA, bench.MU]
+OP = dc.OP_LAPLACIAN if lap else dc.OP_ELASTICITY
+for _ in range(3): ctx.assemble(OP, prm, dc.MODE_DETERMINISTIC, vals)
 L = dc.lib(); L.dc_cuda_debug_phases.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
 L.dc_cuda_debug_phases(ctx.h, None)
-ctx.assemble(dc.OP_ELASTICITY, prm, dc.MODE_DETERMINISTIC, vals)
+ctx.assemble(OP, prm, dc.MODE_DETERMINISTIC, vals)
 nu = plan.c.nbUnits
 out = np.zeros((nu, 24), dtype=np.int64)
 L.dc_cuda_debug_phases(ctx.h, out.ctypes.data)

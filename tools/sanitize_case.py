@@ -1,4 +1,5 @@
-"""Small deterministic + atomic + list assembly, for compute-sanitizer runs."""
+"""Small deterministic + atomic + list assembly, the tree passes, the CSR build and the permutation
+kernels, for compute-sanitizer runs (compute-sanitizer --tool memcheck python tools/sanitize_case.py)."""
 import sys, os, tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -19,4 +20,12 @@ for sym in (True, False):
             ok = got.tobytes() == want.tobytes() if mode != dc.MODE_ATOMIC else np.abs(got - want).max() <= 1e-12 * np.abs(want).max()
             print("sym", sym, "dim", dim, "mode", mode, "ok", bool(ok), flush=True)
             assert ok
+with tempfile.TemporaryDirectory() as tmp:
+    for vec, geometric in ((0, False), (4, True)):
+        a = common.prepare_mesh(common.MineLib(vec, geometric), 9, tmp, tag="host")
+        b = common.prepare_mesh(common.MineLib(vec, geometric, device=True), 9, tmp, tag="dev")
+        assert a["tree"] == b["tree"] and a["conn"].tobytes() == b["conn"].tobytes()
+        print("tree on the device", vec, geometric, "ok", flush=True)
+row, col = dc.build_csr_device(torch.from_numpy(mesh["conn"]).cuda(), mesh["N"], 0)
+assert np.array_equal(row.cpu().numpy(), mesh["row"]) and np.array_equal(col.cpu().numpy(), mesh["col"])
 print("done")
