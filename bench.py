@@ -318,7 +318,7 @@ def main():
     if exch and overlap and os.environ.get("DC_BENCH_EXCHANGE_SWEEP"):
         sweep = {}
         for early in (0, 1):
-            for reserve in (4, 16, 48):
+            for reserve in (4, 16, 32, 48):
                 ctx.set_option("exchange_pack_early", early)
                 ctx.set_option("exchange_reserve", reserve)
                 for _ in range(2):
@@ -333,8 +333,8 @@ def main():
                 t = torch.tensor([s0.elapsed_time(s1) / args.steps], dtype=torch.float64, device=device)
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 sweep[f"pack_early={early},reserve={reserve}"] = round(float(t[0]), 4)
-        ctx.set_option("exchange_pack_early", int(os.environ.get("DC_BENCH_PACK_EARLY", "-1")))
-        ctx.set_option("exchange_reserve", int(os.environ.get("DC_BENCH_RESERVE", "4")))
+        ctx.set_option("exchange_pack_early", int(os.environ.get("DC_BENCH_PACK_EARLY", "0")))
+        ctx.set_option("exchange_reserve", int(os.environ.get("DC_BENCH_RESERVE", "-1")))
     sampler.stop_flag = True
     sampler.join()
 

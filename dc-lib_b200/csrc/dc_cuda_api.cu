@@ -63,8 +63,8 @@ struct dc_cuda_ctx {
     long long *d_phaseClock = nullptr;   /* debug: per-unit phase stamps (dc_cuda_debug_phases) */
     /* multi-GPU step (dc_cuda_assemble_exchange): units that own interface rows come first in d_units */
     int64_t nbFrontUnits = 0;
-    int exchangeReserve = 4;             /* CTA slots the interior launch leaves to the pack / unpack kernels */
-    int exchangePackEarly = -1;          /* 1: pack before the interior launch, 0: beside it, -1: by the byte / element ratio */
+    int exchangeReserve = -1;            /* CTA slots the interior launch leaves to the pack / unpack kernels; -1: 4 or 16 (below) */
+    int exchangePackEarly = 0;           /* 1: pack on the whole GPU before the interior launch, 0: beside it */
     cudaStream_t sideStream = nullptr;
     cudaEvent_t evFront = nullptr, evJoin = nullptr;
 };
@@ -400,18 +400,24 @@ extern "C" int dc_cuda_assemble_exchange_with(dc_cuda_ctx *c, dc_cuda_exchange *
     }
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t front = c->nbFrontUnits > 0 ? c->nbFrontUnits : c->nbUnits;
-    /* Where the pack runs.  Beside the interior units it only has the few CTA slots the persistent grid
-     * leaves free (`exchange_reserve`), where a gather is latency-bound (about 10 GB/s per slot): fine when
-     * the interior takes long -- weak scaling, 0.2-0.3 bytes sent per interior element, the exchange then
-     * costs 0.2 % of the step -- but with many neighbours and a short interior (one mesh cut over 8 GPUs:
-     * 4 bytes per interior element) the pack would end after the interior and the neighbours' unpack wait
-     * for it.  Then it runs BEFORE the interior launch on the whole GPU (tens of microseconds) and only
-     * the unpack stays beside the interior units. */
-    bool early = c->exchangePackEarly > 0;
-    if (c->exchangePackEarly < 0) {
+    /* The pack and unpack kernels run beside the interior units on the CTA slots the persistent grid
+     * leaves free, where a gather is latency-bound (about 10 GB/s per slot), so the right number of slots
+     * follows the bytes sent per interior element.  Weak scaling sends 0.2-0.3: four slots hide the
+     * exchange completely (ms/step = 1.002 x kernel) and more only slow the interior down.  One mesh cut
+     * over several GPUs sends 2-4 bytes per interior element to 3-7 neighbours: measured optimum 16 slots
+     * at 2.3 (4 GPUs, 25 M tets each: 2.86 / 2.61 / 2.78 ms with 4 / 16 / 48) and 32 at 4.0 (8 GPUs, 12.6 M
+     * tets each: 1.83 / 1.57 / 1.39 ms with 4 / 16 / 32), i.e. about 8 slots per byte (profiles/README.md).
+     * Packing on the whole GPU BEFORE the interior launch (exchange_pack_early) measured slower in both. */
+    int reserve = c->exchangeReserve;
+    if (reserve < 0) {
         const double interiorElems = (double)c->nbElem * (double)(c->nbUnits - front) / (double)(c->nbUnits > 0 ? c->nbUnits : 1);
-        early = (double)dc_cuda_exchange_bytes(x) * 0.5 > 1.0 * interiorElems;
+        const double bytesPerElem = (double)dc_cuda_exchange_bytes(x) * 0.5 / (interiorElems > 1.0 ? interiorElems : 1.0);
+        reserve = (int)(8.0 * bytesPerElem + 0.5);
+        reserve = (reserve + 3) & ~3;
+        if (reserve < 4) reserve = 4;
+        if (reserve > 48) reserve = 48;
     }
+    const bool early = c->exchangePackEarly > 0;
     dc_launch_args a;
     fill_args(c, DC_MODE_DETERMINISTIC, &a);
     a.unitFirst = 0; a.unitCount = front;
@@ -423,7 +429,7 @@ extern "C" int dc_cuda_assemble_exchange_with(dc_cuda_ctx *c, dc_cuda_exchange *
     if (front < c->nbUnits) {            /* enqueued BEFORE a pack on the side stream: see above */
         fill_args(c, DC_MODE_DETERMINISTIC, &a);
         a.unitFirst = front; a.unitCount = c->nbUnits - front;
-        a.reserveCtas = c->exchangeReserve; a.skipBigRows = 1;
+        a.reserveCtas = reserve; a.skipBigRows = 1;
         rc = launcher(&a, h_params, nbParams, d_values, stream);
         c->launches += a.launches;
         if (rc) return explain(rc);
@@ -767,12 +773,12 @@ extern "C" int dc_cuda_set_option(dc_cuda_ctx *c, const char *name, int value)
         return 0;
     }
     if (!strcmp(name, "exchange_pack_early")) {
-        if (value < -1 || value > 1) return fail(-12, "dc_cuda_set_option: exchange_pack_early must be -1 (auto), 0 or 1");
+        if (value < 0 || value > 1) return fail(-12, "dc_cuda_set_option: exchange_pack_early must be 0 or 1");
         c->exchangePackEarly = value;
         return 0;
     }
     if (!strcmp(name, "exchange_reserve")) {
-        if (value < 0 || value > 64) return fail(-12, "dc_cuda_set_option: exchange_reserve must be 0..64");
+        if (value < -1 || value > 64) return fail(-12, "dc_cuda_set_option: exchange_reserve must be -1 (automatic) or 0..64");
         c->exchangeReserve = value;
         return 0;
     }

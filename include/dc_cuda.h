@@ -230,11 +230,10 @@ const char *dc_cuda_tree_last_error(void);
 /* Tuning knobs: "unit_threads" = CTA size of the unit kernel (128, 256 or 512; default 256);
  * "persistent" = 1 (default): SMs x resident CTAs stride over the units and prefetch the next
  * unit's inputs, 0: one CTA per unit; "exchange_reserve" = CTA slots dc_cuda_assemble_exchange leaves
- * free beside the interior units for the pack / unpack kernels (default 4); "exchange_pack_early" = 1: the
- * pack runs on the whole GPU between the interface units and the interior launch (short interiors with
- * many neighbours: one mesh cut over several GPUs), 0: beside the interior units on the reserved slots
- * (long interiors: the exchange is hidden completely), -1 (default): chosen by the bytes sent per
- * interior element (> 1: early). */
+ * free beside the interior units for the pack / unpack kernels (default -1: about 8 slots per byte sent per interior element,
+ * between 4 -- long interiors, the exchange is hidden completely -- and 48 -- one mesh cut over many
+ * GPUs); "exchange_pack_early" = 1: the pack runs on the whole GPU between the interface
+ * units and the interior launch instead of beside it (default 0; measured slower). */
 int  dc_cuda_set_option(dc_cuda_ctx *ctx, const char *name, int value);
 
 /* Number of kernels this context has launched (for honest launch accounting). */
