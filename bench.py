@@ -401,12 +401,15 @@ def main():
     b_alg = 16 * E + 24 * N + 4 * (N + 1) + 4 * nnz + 8 * per * nnz
     traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if dim == 3 and os.path.exists(tpath):
+    if os.path.exists(tpath):
         # DRAM bytes per launch from the committed ncu --set full capture of this kernel (same
         # operator, schedule and tree builder, smaller cube), scaled by the element count
         with open(tpath) as f:
             tj = json.load(f)
-        traffic, traffic_src = tj["dram_bytes_per_element"] * E, tj["source"]
+        if dim == 1:
+            tj = tj.get("laplacian")
+        if tj:
+            traffic, traffic_src = tj["dram_bytes_per_element"] * E, tj["source"]
     achieved = b_alg / (kernel_ms * 1e-3) / 1e9
     line = {
         "metric": "assembled elements/s (fp64, CSR scatter-add)",
