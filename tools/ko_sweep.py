@@ -10,6 +10,7 @@ import torch
 import dc_lib_b200 as dc
 from dc_lib_b200 import multigpu
 
+import bench
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 160
 slots = int(sys.argv[2]) if len(sys.argv) > 2 else 512
 kos = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0, 1, 2, 3, 4, 8, 16, 32, 36, 19, 27, 63]
@@ -20,6 +21,7 @@ THREADS = int(os.environ.get("DC_SWEEP_THREADS", "256"))
 SYM = int(os.environ.get("DC_SWEEP_SYM", "1"))
 OP, PRM = (dc.OP_ELASTICITY, [LAMBDA, MU]) if DIM == 3 else (dc.OP_LAPLACIAN, None)
 names = {1: "transposed stores", 2: "direct stores", 4: "diag tasks", 8: "record build", 16: "accumulation loops", 32: "upper tasks"}
+dc.DC_set_max_elem_per_part(bench.leaf_capacity(n, int(os.environ.get("DC_SWEEP_LEAF_NODES", "62"))))   # the bench geometry
 for w in windows:
     if w:
         os.environ["DC_PLAN_UNIT_NODES"] = w
