@@ -28,6 +28,7 @@ WORKLOADS = {
     "e256": (256, 3, 0, "geometric"),        # 100M tets, elasticity
     "e160": (160, 3, 0, "geometric"),        # 24.6M tets, elasticity
     "l160": (160, 1, 0, "geometric"),        # 24.6M tets, Laplacian
+    "c1": (40, 1, 0, "metis"),               # BASELINE config 1: 40^3, Laplacian, pure D&C (the reference's CPU case)
     "c2": (40, 3, 4, "metis"),               # BASELINE config 2: 40^3, elasticity, D&C + colouring
     "m100": (100, 3, 0, "metis"),            # 6M tets, elasticity (METIS tree, as the reference builds it)
     "m64": (64, 3, 0, "metis"),
